@@ -1,0 +1,633 @@
+// libbp_r1cs.so -- C ABI (include/bp_r1cs.h) over the CUDA kernels in kernels.cuh / staged.cuh.
+//
+// Host-side responsibilities: device buffer growth, pinned staging for H2D of enforce/alloc batches,
+// ingest conversion launches, result read-back.  No evaluation ever happens on the CPU.
+#include "../../include/bp_r1cs.h"
+
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "kernels.cuh"
+#include "staged.cuh"
+
+namespace {
+
+using namespace bp;
+
+constexpr size_t kStageBytes = 32u << 20;  // per pinned staging buffer
+constexpr int kNumStage = 2;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;  // bytes
+};
+
+}  // namespace
+
+struct bp_cs {
+    int field = 0;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    uint64_t n_rows = 0, nnz = 0, n_inputs = 0, n_aux = 0, row_base = 0;
+    DevBuf row_ptr, cols, vals, inputs, aux;
+    DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
+    long long* d_result = nullptr;  // [0] first_bad
+    unsigned int* d_err = nullptr;
+    void* h_pinned_small = nullptr;  // 64 B: result read-back / single-element set,get
+    void* h_stage[kNumStage] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[kNumStage] = {nullptr, nullptr};
+    int stage_next = 0;
+    FieldConsts fc;
+    int64_t opt_kernel = 1;  // 0 = direct, 1 = TMA-staged
+    int64_t launches = 0;
+    StagedPlan plan;  // tiling of the staged kernel (rebuilt lazily when rows change)
+    bool plan_valid = false;
+};
+
+namespace {
+
+int fail(bp_cs* h, int code, const char* fmt, ...) {
+    if (h) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        h->err = buf;
+    }
+    return code;
+}
+
+#define CU(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? BP_E_OOM : BP_E_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                     \
+    } while (0)
+
+#define DISPATCH_FIELD(h, EXPR)                      \
+    switch ((h)->field) {                            \
+        case 0: { constexpr int F = 0; EXPR; } break; \
+        case 1: { constexpr int F = 1; EXPR; } break; \
+        case 2: { constexpr int F = 2; EXPR; } break; \
+    }
+
+// grow `b` to at least `need` bytes, preserving the first `keep` bytes
+int ensure(bp_cs* h, DevBuf& b, size_t need, size_t keep) {
+    if (need <= b.cap) return BP_OK;
+    size_t cap = std::max(need, b.cap + b.cap / 2);
+    cap = (cap + 255) & ~size_t(255);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, cap);
+    if (e != cudaSuccess && cap > need) {  // retry with the exact size before giving up
+        (void)cudaGetLastError();
+        cap = (need + 255) & ~size_t(255);
+        e = cudaMalloc(&np, cap);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, BP_E_OOM, "cudaMalloc(%zu bytes): %s", cap, cudaGetErrorString(e));
+    }
+    if (b.p && keep) CU(h, cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, h->stream));
+    if (b.p) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaFree(b.p));
+    }
+    b.p = np;
+    b.cap = cap;
+    return BP_OK;
+}
+
+// 2^k mod p on the host, with the same limb code the device uses.
+template <int F> void pow2_mod_p(int k, uint32_t* out) {
+    uint32_t x[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < k; ++i) {
+        uint32_t y[8];
+        (void)addn<8>(y, x, x);  // < 2p < 2^256
+        reduce_once<F>(y);
+        std::memcpy(x, y, 32);
+    }
+    std::memcpy(out, x, 32);
+}
+
+template <int F> void make_consts(FieldConsts& fc) {
+    pow2_mod_p<F>(544, fc.kA);
+    pow2_mod_p<F>(832, fc.kB);
+    uint32_t pl[8];
+    for (int i = 0; i < 8; ++i) pl[i] = PL<F>(i);
+    (void)subn<8>(fc.kC, pl, fc.kA);
+}
+
+int grid_for(const bp_cs* h, uint64_t n, int block, int per_sm) {
+    uint64_t g = (n + block - 1) / block;
+    uint64_t cap = (uint64_t)h->sm_count * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(g, cap));
+}
+
+CsrView view(const bp_cs* h) {
+    CsrView m;
+    m.row_ptr = (const uint32_t*)h->row_ptr.p;
+    m.cols = (const uint32_t*)h->cols.p;
+    m.vals = (const uint4*)h->vals.p;
+    m.inputs = (const uint4*)h->inputs.p;
+    m.aux = (const uint4*)h->aux.p;
+    m.n_rows = (uint32_t)h->n_rows;
+    m.n_inputs = (uint32_t)h->n_inputs;
+    m.n_aux = (uint32_t)h->n_aux;
+    m.row_base = h->row_base;
+    return m;
+}
+
+// Copy `bytes` from a caller buffer to device memory on the handle's stream.  Pinned/registered or
+// device-accessible sources go straight through; pageable memory is bounced through the pinned ring so
+// the DMA overlaps the next host memcpy.
+int upload(bp_cs* h, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return BP_OK;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, src);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    if (e == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+        CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        return BP_OK;
+    }
+    if (e == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged)) {
+        CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return BP_OK;
+    }
+    size_t off = 0;
+    while (off < bytes) {
+        const int s = h->stage_next;
+        h->stage_next = (s + 1) % kNumStage;
+        const size_t n = std::min(kStageBytes, bytes - off);
+        CU(h, cudaEventSynchronize(h->stage_ev[s]));
+        std::memcpy(h->h_stage[s], (const char*)src + off, n);
+        CU(h, cudaMemcpyAsync((char*)dst + off, h->h_stage[s], n, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaEventRecord(h->stage_ev[s], h->stream));
+        off += n;
+    }
+    return BP_OK;
+}
+
+int read_flags(bp_cs* h, long long* first_bad, unsigned int* err) {
+    char* hp = (char*)h->h_pinned_small;
+    CU(h, cudaMemcpyAsync(hp, h->d_result, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(hp + 8, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(first_bad, hp, 8);
+    std::memcpy(err, hp + 8, 4);
+    return BP_OK;
+}
+
+int clear_err(bp_cs* h) {
+    CU(h, cudaMemsetAsync(h->d_err, 0, 4, h->stream));
+    return BP_OK;
+}
+
+int check_err_word(bp_cs* h, const char* what) {
+    char* hp = (char*)h->h_pinned_small;
+    CU(h, cudaMemcpyAsync(hp + 8, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    unsigned int e;
+    std::memcpy(&e, hp + 8, 4);
+    if (e & 2u) return fail(h, BP_E_RANGE, "%s: a field element is not canonical (>= p)", what);
+    if (e & 1u) return fail(h, BP_E_RANGE, "%s: a column index is out of range", what);
+    return BP_OK;
+}
+
+// Launch K1/K2 on the handle's stream.  `out` selects emit mode when any of az/bz/cz is set.
+int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4* cz) {
+    init_result<<<1, 1, 0, h->stream>>>(dev_first_bad, h->d_err);
+    h->launches++;
+    if (h->n_rows == 0) {
+        CU(h, cudaGetLastError());
+        return BP_OK;
+    }
+    CsrView m = view(h);
+    CheckOut o{dev_first_bad, h->d_err, az, bz, cz};
+    const bool emit = az || bz || cz;
+    if (h->opt_kernel == 1 && !emit) {
+        int rc = BP_OK;
+        DISPATCH_FIELD(h, rc = staged_launch<F>(h->plan, h->plan_valid, m, o, h->sm_count, h->stream, h->launches));
+        if (rc == 1) return fail(h, BP_E_OOM, "staged kernel: plan allocation failed");
+        if (rc == 0) {
+            CU(h, cudaGetLastError());
+            return BP_OK;
+        }
+        // rc == 2: instance not eligible for the staged kernel (a row larger than a tile) -> direct kernel
+    }
+    const int block = 128;
+    const int grid = grid_for(h, h->n_rows, block, 8);
+    if (emit) {
+        DISPATCH_FIELD(h, (check_direct<F, true><<<grid, block, 0, h->stream>>>(m, o)));
+    } else {
+        DISPATCH_FIELD(h, (check_direct<F, false><<<grid, block, 0, h->stream>>>(m, o)));
+    }
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return BP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bp_abi_version(void) { return BP_ABI_VERSION; }
+
+const char* bp_cs_last_error(const bp_cs* cs) { return cs ? cs->err.c_str() : "null handle"; }
+
+int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz, uint64_t reserve_vars, bp_cs** out) {
+    if (!out || field < 0 || field > 2) return BP_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        (void)cudaGetLastError();
+        return BP_E_CUDA;  // no CPU fallback
+    }
+    bp_cs* h = new (std::nothrow) bp_cs();
+    if (!h) return BP_E_OOM;
+    h->field = field;
+    h->device = device;
+    auto bail = [&](int code) {
+        bp_cs_free(h);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(BP_E_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(BP_E_CUDA);
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BP_E_CUDA);
+    h->stream = h->own_stream;
+    if (cudaMalloc(&h->d_result, 16) != cudaSuccess) return bail(BP_E_OOM);
+    h->d_err = (unsigned int*)(h->d_result + 1);
+    if (cudaMemset(h->d_result, 0, 16) != cudaSuccess) return bail(BP_E_CUDA);
+    if (cudaMallocHost(&h->h_pinned_small, 64) != cudaSuccess) return bail(BP_E_OOM);
+    for (int s = 0; s < kNumStage; ++s) {
+        if (cudaMallocHost(&h->h_stage[s], kStageBytes) != cudaSuccess) return bail(BP_E_OOM);
+        if (cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
+    }
+    DISPATCH_FIELD(h, make_consts<F>(h->fc));
+    // inputs = [ONE]  (test_cs.rs:169, witness_cs.rs:95)
+    const uint64_t one[4] = {1, 0, 0, 0};
+    uint64_t idx = 0;
+    size_t rv = (size_t)std::max<uint64_t>(reserve_vars, 1);
+    if (ensure(h, h->inputs, std::max<size_t>(32 * 1024, 32), 0) != BP_OK) return bail(BP_E_OOM);
+    if (reserve_vars && ensure(h, h->aux, rv * 32, 0) != BP_OK) return bail(BP_E_OOM);
+    if (reserve_rows && ensure(h, h->row_ptr, (3 * (size_t)reserve_rows + 1) * 4, 0) != BP_OK) return bail(BP_E_OOM);
+    if (reserve_nnz) {
+        if (ensure(h, h->cols, (size_t)reserve_nnz * 4, 0) != BP_OK) return bail(BP_E_OOM);
+        if (ensure(h, h->vals, (size_t)reserve_nnz * 32, 0) != BP_OK) return bail(BP_E_OOM);
+    }
+    if (ensure(h, h->row_ptr, 4, 0) != BP_OK) return bail(BP_E_OOM);
+    if (cudaMemsetAsync(h->row_ptr.p, 0, 4, h->stream) != cudaSuccess) return bail(BP_E_CUDA);
+    if (bp_cs_alloc(h, 0, one, 1, &idx) != BP_OK) return bail(BP_E_CUDA);
+    *out = h;
+    return BP_OK;
+}
+
+void bp_cs_free(bp_cs* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->scan_tmp, &h->scratch})
+        if (b->p) cudaFree(b->p);
+    staged_plan_free(h->plan);
+    if (h->d_result) cudaFree(h->d_result);
+    if (h->h_pinned_small) cudaFreeHost(h->h_pinned_small);
+    for (int s = 0; s < kNumStage; ++s) {
+        if (h->h_stage[s]) cudaFreeHost(h->h_stage[s]);
+        if (h->stage_ev[s]) cudaEventDestroy(h->stage_ev[s]);
+    }
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    (void)cudaGetLastError();
+    delete h;
+}
+
+int bp_cs_set_stream(bp_cs* h, void* s) {
+    if (!h) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return BP_OK;
+}
+
+int bp_cs_set_row_base(bp_cs* h, uint64_t b) {
+    if (!h) return BP_E_ARG;
+    h->row_base = b;
+    return BP_OK;
+}
+
+int bp_cs_sync(bp_cs* h) {
+    if (!h) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return BP_OK;
+}
+
+int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
+    if (!h || !key) return BP_E_ARG;
+    if (!std::strcmp(key, "kernel")) {
+        if (v != 0 && v != 1) return fail(h, BP_E_ARG, "kernel must be 0 (direct) or 1 (staged)");
+        h->opt_kernel = v;
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "tile_terms")) {
+        if (v < 64 || v > 4096) return fail(h, BP_E_ARG, "tile_terms out of range");
+        h->plan.tile_terms = (uint32_t)v;
+        h->plan_valid = false;
+        return BP_OK;
+    }
+    return fail(h, BP_E_ARG, "unknown option '%s'", key);
+}
+
+int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
+    if (!h || !key || !v) return BP_E_ARG;
+    if (!std::strcmp(key, "kernel")) { *v = h->opt_kernel; return BP_OK; }
+    if (!std::strcmp(key, "launches")) { *v = h->launches; return BP_OK; }
+    if (!std::strcmp(key, "sm_count")) { *v = h->sm_count; return BP_OK; }
+    if (!std::strcmp(key, "tiles")) { *v = h->plan_valid ? (int64_t)h->plan.n_tiles : -1; return BP_OK; }
+    if (!std::strcmp(key, "last_kernel")) { *v = h->plan.last_used ? 1 : 0; return BP_OK; }
+    return fail(h, BP_E_ARG, "unknown option '%s'", key);
+}
+
+int bp_cs_counts(bp_cs* h, uint64_t* n_inputs, uint64_t* n_aux, uint64_t* n_rows, uint64_t* nnz) {
+    if (!h) return BP_E_ARG;
+    if (n_inputs) *n_inputs = h->n_inputs;
+    if (n_aux) *n_aux = h->n_aux;
+    if (n_rows) *n_rows = h->n_rows;
+    if (nnz) *nnz = h->nnz;
+    return BP_OK;
+}
+
+int bp_cs_alloc(bp_cs* h, int is_aux, const uint64_t* vals, uint64_t n, uint64_t* first_index) {
+    if (!h || (!vals && n)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    DevBuf& b = is_aux ? h->aux : h->inputs;
+    uint64_t& cnt = is_aux ? h->n_aux : h->n_inputs;
+    if (cnt + n >= 0x80000000ull) return fail(h, BP_E_RANGE, "more than 2^31-1 variables in one index space");
+    int rc = ensure(h, b, (size_t)(cnt + n) * 32, (size_t)cnt * 32);
+    if (rc != BP_OK) return rc;
+    if (n) {
+        rc = clear_err(h);
+        if (rc != BP_OK) return rc;
+        rc = upload(h, (char*)b.p + cnt * 32, vals, (size_t)n * 32);
+        if (rc != BP_OK) return rc;
+        DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>(
+                              (const uint4*)((char*)b.p + cnt * 32), n, h->d_err)));
+        h->launches++;
+        CU(h, cudaGetLastError());
+        rc = check_err_word(h, "bp_cs_alloc");
+        if (rc != BP_OK) return rc;  // cnt not advanced: the rejected values are not part of the system
+    }
+    if (first_index) *first_index = cnt;
+    cnt += n;
+    return BP_OK;
+}
+
+int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint64_t* vals) {
+    if (!h || (!vals && n)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
+    if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "set_range [%llu,+%llu) exceeds %llu", (unsigned long long)first,
+                                                   (unsigned long long)n, (unsigned long long)cnt);
+    if (!n) return BP_OK;
+    // Validate on the host BEFORE touching device state so a rejected value leaves the witness intact.
+    {
+        uint32_t pl[8];
+        DISPATCH_FIELD(h, { for (int i = 0; i < 8; ++i) pl[i] = PL<F>(i); });
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, vals);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        const bool host_readable = !(e == cudaSuccess && at.type == cudaMemoryTypeDevice);
+        if (host_readable) {
+            for (uint64_t i = 0; i < n; ++i) {
+                const uint32_t* x = (const uint32_t*)(vals + 4 * i);
+                int lt = 0;
+                for (int j = 7; j >= 0; --j) {
+                    if (x[j] < pl[j]) { lt = 1; break; }
+                    if (x[j] > pl[j]) break;
+                }
+                if (!lt) return fail(h, BP_E_RANGE, "bp_cs_set_range: element %llu is not canonical (>= p)", (unsigned long long)i);
+            }
+        }
+    }
+    DevBuf& b = is_aux ? h->aux : h->inputs;
+    return upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32);
+}
+
+int bp_cs_set(bp_cs* h, int is_aux, uint64_t idx, const uint64_t v[4]) { return bp_cs_set_range(h, is_aux, idx, 1, v); }
+
+int bp_cs_witness(bp_cs* h, int is_aux, uint64_t first, uint64_t n, uint64_t* out) {
+    if (!h || (!out && n)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
+    if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "witness range [%llu,+%llu) exceeds %llu", (unsigned long long)first,
+                                                   (unsigned long long)n, (unsigned long long)cnt);
+    if (!n) return BP_OK;
+    const DevBuf& b = is_aux ? h->aux : h->inputs;
+    CU(h, cudaMemcpyAsync(out, (const char*)b.p + first * 32, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return BP_OK;
+}
+
+int bp_cs_get(bp_cs* h, int is_aux, uint64_t idx, uint64_t v[4]) { return bp_cs_witness(h, is_aux, idx, 1, v); }
+
+int bp_cs_enforce(bp_cs* h, uint64_t n_rows, const uint32_t* lens, const uint32_t* cols, const uint64_t* coeffs) {
+    if (!h || (n_rows && !lens)) return BP_E_ARG;
+    if (!n_rows) return BP_OK;
+    CU(h, cudaSetDevice(h->device));
+    uint64_t add = 0;
+    for (uint64_t i = 0; i < 3 * n_rows; ++i) add += lens[i];
+    if (add && (!cols || !coeffs)) return BP_E_ARG;
+    if (h->nnz + add >= 0xffffffffull || 3 * (h->n_rows + n_rows) + 1 >= 0xffffffffull)
+        return fail(h, BP_E_RANGE, "nnz or LC count would reach 2^32 in one handle; shard the rows");
+    const size_t lc_old = 3 * (size_t)h->n_rows, lc_add = 3 * (size_t)n_rows;
+    if (lc_add + 1 > 0x7fffffffull) return fail(h, BP_E_RANGE, "more than 2^31 LCs in one enforce batch; split the call");
+    int rc;
+    if ((rc = ensure(h, h->row_ptr, (lc_old + lc_add + 1) * 4, (lc_old + 1) * 4)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->cols, (size_t)(h->nnz + add) * 4, (size_t)h->nnz * 4)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->vals, (size_t)(h->nnz + add) * 32, (size_t)h->nnz * 32)) != BP_OK) return rc;
+    uint32_t* rp = (uint32_t*)h->row_ptr.p;
+    // lens -> row_ptr[lc_old .. lc_old+lc_add] : exclusive scan of (lens ++ [0]) then + nnz
+    // stage the lens right where the scan output goes, shifted by one slot so in-place scan is safe
+    if ((rc = ensure(h, h->scratch, (lc_add + 1) * 4, 0)) != BP_OK) return rc;
+    if ((rc = upload(h, h->scratch.p, lens, lc_add * 4)) != BP_OK) return rc;
+    CU(h, cudaMemsetAsync((char*)h->scratch.p + lc_add * 4, 0, 4, h->stream));
+    size_t tmp_bytes = 0;
+    CU(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const uint32_t*)h->scratch.p, rp + lc_old, (int)(lc_add + 1), h->stream));
+    if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
+    CU(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp_bytes, (const uint32_t*)h->scratch.p, rp + lc_old, (int)(lc_add + 1), h->stream));
+    if (h->nnz) {
+        add_base<<<grid_for(h, lc_add + 1, 256, 8), 256, 0, h->stream>>>(rp + lc_old, (uint32_t)(lc_add + 1), (uint32_t)h->nnz);
+        h->launches++;
+    }
+    if (add) {
+        if ((rc = upload(h, (uint32_t*)h->cols.p + h->nnz, cols, (size_t)add * 4)) != BP_OK) return rc;
+        if ((rc = upload(h, (char*)h->vals.p + h->nnz * 32, coeffs, (size_t)add * 32)) != BP_OK) return rc;
+        if ((rc = clear_err(h)) != BP_OK) return rc;
+        DISPATCH_FIELD(h, (to_internal<F><<<grid_for(h, add, 128, 16), 128, 0, h->stream>>>(
+                              (uint4*)h->vals.p, rp, (uint32_t)lc_old, (uint32_t)lc_add, (uint32_t)h->nnz, (uint32_t)add, h->fc, h->d_err)));
+        h->launches++;
+        CU(h, cudaGetLastError());
+        if ((rc = check_err_word(h, "bp_cs_enforce")) != BP_OK) return rc;  // rows not committed
+    } else {
+        CU(h, cudaGetLastError());
+    }
+    h->n_rows += n_rows;
+    h->nnz += add;
+    h->plan_valid = false;
+    return BP_OK;
+}
+
+int bp_cs_check_async(bp_cs* h, int64_t* dev_result) {
+    if (!h || !dev_result) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    return launch_check(h, (long long*)dev_result, nullptr, nullptr, nullptr);
+}
+
+int bp_cs_first_unsatisfied(bp_cs* h, int64_t* row) {
+    if (!h || !row) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    int rc = launch_check(h, h->d_result, nullptr, nullptr, nullptr);
+    if (rc != BP_OK) return rc;
+    long long fb;
+    unsigned int e;
+    if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;
+    if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
+    *row = fb == 0x7fffffffffffffffLL ? -1 : (int64_t)(fb - (long long)h->row_base);
+    return BP_OK;
+}
+
+int bp_cs_eval_async(bp_cs* h, uint64_t* az, uint64_t* bz, uint64_t* cz) {
+    if (!h) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (!az && !bz && !cz) return BP_OK;
+    return launch_check(h, h->d_result, (uint4*)az, (uint4*)bz, (uint4*)cz);
+}
+
+int bp_cs_eval(bp_cs* h, uint64_t* az, uint64_t* bz, uint64_t* cz) {
+    if (!h) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if ((!az && !bz && !cz) || h->n_rows == 0) return BP_OK;
+    const size_t bytes = (size_t)h->n_rows * 32;
+    const int want = (az ? 1 : 0) + (bz ? 1 : 0) + (cz ? 1 : 0);
+    int rc = ensure(h, h->scratch, bytes * want, 0);
+    if (rc != BP_OK) return rc;
+    char* p = (char*)h->scratch.p;
+    uint4 *da = nullptr, *db = nullptr, *dc = nullptr;
+    if (az) { da = (uint4*)p; p += bytes; }
+    if (bz) { db = (uint4*)p; p += bytes; }
+    if (cz) { dc = (uint4*)p; p += bytes; }
+    if ((rc = launch_check(h, h->d_result, da, db, dc)) != BP_OK) return rc;
+    if (az) CU(h, cudaMemcpyAsync(az, da, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (bz) CU(h, cudaMemcpyAsync(bz, db, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (cz) CU(h, cudaMemcpyAsync(cz, dc, bytes, cudaMemcpyDeviceToHost, h->stream));
+    long long fb;
+    unsigned int e;
+    if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;
+    if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
+    return BP_OK;
+}
+
+int bp_cs_eval_lc(bp_cs* h, const uint32_t* cols, const uint64_t* coeffs, uint32_t n, uint64_t out[4]) {
+    if (!h || !out || (n && (!cols || !coeffs))) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    // scratch: [vals 32n][cols 4n][row_ptr 8][out 32]
+    const size_t off_cols = (size_t)n * 32, off_rp = off_cols + (((size_t)n * 4 + 15) & ~size_t(15)), off_out = off_rp + 16;
+    int rc = ensure(h, h->scratch, off_out + 32, 0);
+    if (rc != BP_OK) return rc;
+    char* s = (char*)h->scratch.p;
+    if ((rc = clear_err(h)) != BP_OK) return rc;
+    if (n) {
+        if ((rc = upload(h, s, coeffs, (size_t)n * 32)) != BP_OK) return rc;
+        if ((rc = upload(h, s + off_cols, cols, (size_t)n * 4)) != BP_OK) return rc;
+        const uint32_t rp[2] = {0, n};
+        std::memcpy((char*)h->h_pinned_small + 16, rp, 8);
+        CU(h, cudaMemcpyAsync(s + off_rp, (char*)h->h_pinned_small + 16, 8, cudaMemcpyHostToDevice, h->stream));
+        // one LC of type A (lc index 0)
+        DISPATCH_FIELD(h, (to_internal<F><<<grid_for(h, n, 128, 16), 128, 0, h->stream>>>((uint4*)s, (const uint32_t*)(s + off_rp), 0u, 1u,
+                                                                                         0u, n, h->fc, h->d_err)));
+        h->launches++;
+    }
+    DISPATCH_FIELD(h, (eval_lc_kernel<F><<<1, 32, 0, h->stream>>>((const uint32_t*)(s + off_cols), (const uint4*)s, n, view(h),
+                                                                 (uint4*)(s + off_out), h->d_err)));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(h->h_pinned_small, s + off_out, 32, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = check_err_word(h, "bp_cs_eval_lc")) != BP_OK) return rc;
+    std::memcpy(out, h->h_pinned_small, 32);
+    return BP_OK;
+}
+
+int bp_cs_synth_rows(bp_cs* h, uint64_t seed, uint32_t t, uint64_t n_vars, uint64_t n_inputs, uint64_t row0, uint64_t n_rows) {
+    if (!h) return BP_E_ARG;
+    if (t < 1 || n_vars < 2ull * t || n_inputs > n_vars || n_inputs < 1) return fail(h, BP_E_ARG, "bad synthetic parameters");
+    if (!n_rows) return BP_OK;
+    CU(h, cudaSetDevice(h->device));
+    const size_t lc_old = 3 * (size_t)h->n_rows, lc_add = 3 * (size_t)n_rows;
+    if (lc_old + lc_add + 1 >= 0xffffffffull || lc_add + 1 > 0x7fffffffull) return fail(h, BP_E_RANGE, "LC count too large for one handle/call");
+    int rc;
+    if ((rc = ensure(h, h->row_ptr, (lc_old + lc_add + 1) * 4, (lc_old + 1) * 4)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->scratch, (lc_add + 1) * 4, 0)) != BP_OK) return rc;
+    uint32_t* rp = (uint32_t*)h->row_ptr.p;
+    synth_lens<<<grid_for(h, lc_add, 256, 8), 256, 0, h->stream>>>((uint32_t*)h->scratch.p, seed, t, 3 * row0, (uint32_t)lc_add);
+    h->launches++;
+    CU(h, cudaMemsetAsync((char*)h->scratch.p + lc_add * 4, 0, 4, h->stream));
+    size_t tmp_bytes = 0;
+    CU(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const uint32_t*)h->scratch.p, rp + lc_old, (int)(lc_add + 1), h->stream));
+    if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
+    CU(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp_bytes, (const uint32_t*)h->scratch.p, rp + lc_old, (int)(lc_add + 1), h->stream));
+    // the scan is 32-bit: bound the chunk's nnz with 64-bit host arithmetic first, then read the exact total back
+    if ((uint64_t)lc_add * (2ull * t - 1) >= 0xffffffffull) return fail(h, BP_E_RANGE, "synthetic chunk too large; split the call");
+    uint32_t add32 = 0;
+    CU(h, cudaMemcpyAsync(h->h_pinned_small, rp + lc_old + lc_add, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(&add32, h->h_pinned_small, 4);
+    const uint64_t add = add32;
+    if (h->nnz + add >= 0xffffffffull)
+        return fail(h, BP_E_RANGE, "nnz would reach 2^32 in one handle; shard the rows");
+    if (h->nnz) {
+        add_base<<<grid_for(h, lc_add + 1, 256, 8), 256, 0, h->stream>>>(rp + lc_old, (uint32_t)(lc_add + 1), (uint32_t)h->nnz);
+        h->launches++;
+    }
+    if ((rc = ensure(h, h->cols, (size_t)(h->nnz + add) * 4, (size_t)h->nnz * 4)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->vals, (size_t)(h->nnz + add) * 32, (size_t)h->nnz * 32)) != BP_OK) return rc;
+    DISPATCH_FIELD(h, (synth_fill<F><<<grid_for(h, lc_add, 128, 16), 128, 0, h->stream>>>(
+                          (uint32_t*)h->cols.p, (uint4*)h->vals.p, rp, (uint32_t)lc_old, (uint32_t)lc_add, seed, 3 * row0, n_vars, n_inputs,
+                          h->fc)));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    h->n_rows += n_rows;
+    h->nnz += add;
+    h->plan_valid = false;
+    return BP_OK;
+}
+
+int bp_cs_synth_witness(bp_cs* h, uint64_t seed, uint64_t n_vars, uint64_t n_inputs) {
+    if (!h) return BP_E_ARG;
+    if (n_inputs < 1 || n_inputs > n_vars || n_vars >= 0x80000000ull) return fail(h, BP_E_ARG, "bad synthetic parameters");
+    CU(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure(h, h->inputs, (size_t)n_inputs * 32, 0)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->aux, (size_t)std::max<uint64_t>(n_vars - n_inputs, 1) * 32, 0)) != BP_OK) return rc;
+    DISPATCH_FIELD(h, (synth_witness<F><<<grid_for(h, n_vars, 256, 8), 256, 0, h->stream>>>((uint4*)h->inputs.p, (uint4*)h->aux.p, seed,
+                                                                                          n_vars, n_inputs)));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    h->n_inputs = n_inputs;
+    h->n_aux = n_vars - n_inputs;
+    return BP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+/* bp_r1cs.h -- C ABI of the B200 R1CS evaluation engine (libbp_r1cs.so).
+ *
+ * This is the drop-in boundary for ONE path of argumentcomputer/bellpepper: batch evaluation of
+ * LinearCombination<F> over the witness (three CSR sparse-matrix x vector products over a 255-bit
+ * prime field) followed by the element-wise (A.w) o (B.w) == C.w check, i.e. the work of
+ * TestConstraintSystem::which_is_unsatisfied / eval_lc / LinearCombination::eval.
+ *
+ * The reference has no FFI: its boundary is the Rust trait `ConstraintSystem<Scalar>`
+ * (crates/bellpepper-core/src/constraint_system.rs:61-237).  A replacement backend is a Rust type that
+ * implements the trait, keeps names/namespaces/closures on the host, and forwards FLAT data to these
+ * entry points (binding shown in INTEGRATION.md and rust/bellpepper-b200/).  Each entry point cites the
+ * reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - Field elements cross the boundary as 4 x uint64_t little-endian limbs of the CANONICAL residue
+ *    (what `PrimeField::to_repr()` yields; test_cs.rs:108-111).  Values >= p are rejected (BP_E_RANGE).
+ *    Montgomery / pre-scaled forms are device-internal.
+ *  - Columns are uint32_t: bit 31 clear = Index::Input(i), bit 31 set = Index::Aux(i)  (lc.rs:27-30).
+ *    Input 0 is the constant ONE (constraint_system.rs:73-75) and is an ordinary, mutable witness slot
+ *    (test_cs.rs:160-169, 270-275).
+ *  - Every function returns BP_OK or a negative error class; nothing throws or aborts across the
+ *    boundary.  bp_cs_last_error() gives the message for the handle's last failure.
+ *  - A handle is thread-compatible, not thread-safe (`ConstraintSystem: Send`, all mutation through
+ *    `&mut self`).  Every call selects the handle's device itself; no reliance on the caller's current
+ *    CUDA device.  The caller owns every buffer it passes; the library copies before returning.
+ *  - There is no CPU fallback: without a usable CUDA device bp_cs_new fails with BP_E_CUDA.
+ */
+#ifndef BP_R1CS_H
+#define BP_R1CS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_ABI_VERSION 1
+
+enum {
+    BP_OK = 0,
+    BP_E_CUDA = -1,  /* CUDA runtime failure (no device, launch error, ...) */
+    BP_E_OOM = -2,   /* host or device allocation failed */
+    BP_E_RANGE = -3, /* index >= count, value >= p, nnz >= 2^32 */
+    BP_E_STATE = -4, /* call not valid in the handle's current state */
+    BP_E_ARG = -5    /* null pointer / unknown field / bad option */
+};
+
+enum {
+    BP_FIELD_BLS12_381_FR = 0, /* blstrs::Scalar -- the only field the reference's tests use */
+    BP_FIELD_PALLAS_FR = 1,    /* pasta Fq */
+    BP_FIELD_VESTA_FR = 2      /* pasta Fp */
+};
+
+#define BP_COL_AUX 0x80000000u
+
+typedef struct bp_cs bp_cs;
+
+/* ---- lifetime --------------------------------------------------------------------------------------
+ * TestConstraintSystem::new (test_cs.rs:157-178) / WitnessCS::new (witness_cs.rs:94-101): the new
+ * system holds inputs = [ONE], no aux, no constraints.  `reserve_*` are capacity hints (0 = grow on
+ * demand) that avoid device reallocation while rows stream in. */
+int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz, uint64_t reserve_vars, bp_cs** out);
+void bp_cs_free(bp_cs* cs);
+const char* bp_cs_last_error(const bp_cs* cs);
+int bp_abi_version(void);
+
+/* ---- witness ingest --------------------------------------------------------------------------------
+ * alloc / alloc_input (test_cs.rs:380-408, witness_cs.rs:103-123), extend_inputs / extend_aux
+ * (witness_cs.rs:171-177) and the fill of allocate_empty (witness_cs.rs:179-193): append `n` values
+ * to one index space; *first_index receives the index of the first appended element. */
+int bp_cs_alloc(bp_cs* cs, int is_aux, const uint64_t* vals_le, uint64_t n, uint64_t* first_index);
+
+/* set (test_cs.rs:270-282): overwrite one element.  get (test_cs.rs:311-323). */
+int bp_cs_set(bp_cs* cs, int is_aux, uint64_t idx, const uint64_t v[4]);
+int bp_cs_get(bp_cs* cs, int is_aux, uint64_t idx, uint64_t v[4]);
+
+/* Bulk overwrite of an existing range [first, first+n): SizedWitness::generate_witness_into
+ * (witness_cs.rs:12, 28-40) writing into the slices returned by allocate_empty. */
+int bp_cs_set_range(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, const uint64_t* vals_le);
+
+/* scalar_inputs / scalar_aux (test_cs.rs:180-189), inputs_slice / aux_slice (witness_cs.rs:195-201). */
+int bp_cs_witness(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, uint64_t* out_le);
+
+/* ---- constraint ingest -----------------------------------------------------------------------------
+ * enforce (test_cs.rs:410-427) for a batch of rows.  For row r: lens[3r], lens[3r+1], lens[3r+2] are
+ * |A|, |B|, |C|; the rows' terms follow each other in `cols` / `coeffs_le` in A, B, C order, each LC in
+ * the reference's iteration order (inputs then aux, ascending index: lc.rs:155-160).  Zero-length LCs
+ * and zero coefficients are legal.  Row indices are assigned in call order (test_cs.rs:419). */
+int bp_cs_enforce(bp_cs* cs, uint64_t n_rows, const uint32_t* lens, const uint32_t* cols, const uint64_t* coeffs_le);
+
+/* num_inputs / num_constraints (test_cs.rs:266, 295) and sizes. */
+int bp_cs_counts(bp_cs* cs, uint64_t* n_inputs, uint64_t* n_aux, uint64_t* n_rows, uint64_t* nnz);
+
+/* ---- the hot path ----------------------------------------------------------------------------------
+ * which_is_unsatisfied / is_satisfied (test_cs.rs:239-264): *row = index of the FIRST row with
+ * (A.w)(B.w) != C.w, or -1 when every row holds.  The host side maps the row to its path.
+ * A term whose column is out of range makes the call fail with BP_E_RANGE (the reference panics on the
+ * slice index, test_cs.rs:146-147). */
+int bp_cs_first_unsatisfied(bp_cs* cs, int64_t* row);
+
+/* Same check, asynchronous: enqueue on the handle's stream and leave the result in DEVICE memory as one
+ * int64 (first failing GLOBAL row = row_base + local row; INT64_MAX when satisfied) so that a row-sharded
+ * multi-GPU caller can min-all-reduce it without a host round trip.  No host synchronisation. */
+int bp_cs_check_async(bp_cs* cs, int64_t* dev_result);
+
+/* Batched LinearCombination::eval over all rows (lc.rs:245-267): canonical A.w, B.w, C.w, n_rows x 4
+ * limbs each, into HOST buffers (any may be NULL). */
+int bp_cs_eval(bp_cs* cs, uint64_t* az, uint64_t* bz, uint64_t* cz);
+/* Same into DEVICE buffers, asynchronous on the handle's stream. */
+int bp_cs_eval_async(bp_cs* cs, uint64_t* dev_az, uint64_t* dev_bz, uint64_t* dev_cz);
+
+/* LinearCombination::eval for one ad-hoc LC (lc.rs:245-267). */
+int bp_cs_eval_lc(bp_cs* cs, const uint32_t* cols, const uint64_t* coeffs_le, uint32_t n_terms, uint64_t out[4]);
+
+/* ---- execution control -----------------------------------------------------------------------------*/
+/* Use an existing CUDA stream (cudaStream_t as void*; NULL = the handle's own stream) for all work. */
+int bp_cs_set_stream(bp_cs* cs, void* cuda_stream);
+/* Row-sharded use: global index of this handle's row 0 (default 0). */
+int bp_cs_set_row_base(bp_cs* cs, uint64_t row_base);
+/* Block until all enqueued work of this handle is complete. */
+int bp_cs_sync(bp_cs* cs);
+/* Tuning / introspection knobs: "kernel" (0 = direct CSR, 1 = TMA-staged), "launches" (read-only). */
+int bp_cs_set_option(bp_cs* cs, const char* key, int64_t value);
+int bp_cs_get_option(bp_cs* cs, const char* key, int64_t* value);
+
+/* ---- measurement fixture: synthetic instances generated in HBM ----------------------------------------
+ * Not a reference interface.  Appends rows [row0, row0+n_rows) of the counter-based synthetic R1CS
+ * (recipe: DESIGN.md "Synthetic instances"; CPU twin: oracle/bp_oracle.c bpo_synth_*) and, with
+ * bp_cs_synth_witness, REPLACES the witness by the recipe's n_vars elements (n_inputs of them inputs). */
+int bp_cs_synth_rows(bp_cs* cs, uint64_t seed, uint32_t t, uint64_t n_vars, uint64_t n_inputs, uint64_t row0, uint64_t n_rows);
+int bp_cs_synth_witness(bp_cs* cs, uint64_t seed, uint64_t n_vars, uint64_t n_inputs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BP_R1CS_H */

@@ -1,0 +1,50 @@
+"""CPU-side checks of the boundary: the library loads without a GPU and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+from bellpepper_b200 import ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bp_r1cs.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    assert set(syms) == set(ffi.SIGNATURES), set(syms) ^ set(ffi.SIGNATURES)
+
+
+def test_library_loads_and_exports_every_symbol():
+    L = ffi.load()
+    for s in declared_symbols():
+        assert hasattr(L, s), s
+    assert L.bp_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device bp_cs_new must fail with BP_E_CUDA (there is no CPU path)."""
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    L = ffi.load()
+    h = ffi.vp()
+    assert L.bp_cs_new(0, 0, 0, 0, 0, ctypes.byref(h)) == ffi.BP_E_CUDA
+    assert not h.value
+    assert L.bp_cs_new(7, 0, 0, 0, 0, ctypes.byref(h)) == ffi.BP_E_ARG
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bellpepper_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert not re.search(r"#\s*include[^\n]*oracle|dlopen|libbp_oracle", src), f

@@ -1,0 +1,249 @@
+"""GPU parity (run with -m gpu on the B200): the CUDA path through the C ABI vs the CPU oracle, bit-exact."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_api, synth
+from oracle.fields import FIELDS
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import Handle  # noqa: E402
+
+FIDS = sorted(FIELDS)
+KERNELS = [0, 1]
+
+
+@pytest.mark.parametrize("fid", FIDS)
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("t,n_vars,n_rows", [(6, 5000, 4000), (32, 3000, 700), (1, 64, 500)])
+def test_host_ingested_synthetic_matches_oracle(fid, kernel, t, n_vars, n_rows):
+    lens, cols, coeffs, inputs, aux = c_api.synth_instance(fid, synth.SEED, t, n_vars, synth.N_INPUTS, n_rows)
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    bad, az_r, bz_r, cz_r = inst.eval(2)
+    with Handle(fid) as h:
+        h.opt("kernel", kernel)
+        h.load_instance(lens, cols, coeffs, inputs, aux)
+        assert h.counts() == (inputs.shape[0], aux.shape[0], n_rows, cols.size)
+        assert h.first_unsatisfied() == bad
+        az, bz, cz = h.eval(n_rows)
+        assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
+
+
+@pytest.mark.parametrize("fid", FIDS)
+def test_device_generator_matches_oracle_recipe(fid):
+    t, n_vars, n_rows, row0 = 6, 10000, 6000, 123
+    lens, cols, coeffs = c_api.synth_rows(fid, synth.SEED, t, n_vars, synth.N_INPUTS, row0, n_rows)
+    w = c_api.synth_witness(fid, synth.SEED, 0, n_vars)
+    inst = c_api.Instance(fid, lens, cols, coeffs, w[: synth.N_INPUTS], w[synth.N_INPUTS:])
+    bad, az_r, bz_r, cz_r = inst.eval(2)
+    with Handle(fid) as h:
+        h.ok(h.L.bp_cs_synth_witness(h.h, synth.SEED, n_vars, synth.N_INPUTS))
+        # two chunks: exercises appending to a non-empty CSR
+        h.ok(h.L.bp_cs_synth_rows(h.h, synth.SEED, t, n_vars, synth.N_INPUTS, row0, 2500))
+        h.ok(h.L.bp_cs_synth_rows(h.h, synth.SEED, t, n_vars, synth.N_INPUTS, row0 + 2500, n_rows - 2500))
+        assert h.counts() == (synth.N_INPUTS, n_vars - synth.N_INPUTS, n_rows, cols.size)
+        got = np.zeros((n_vars - synth.N_INPUTS, 4), np.uint64)
+        h.ok(h.L.bp_cs_witness(h.h, 1, 0, got.shape[0], got.ctypes.data))
+        assert (got == w[synth.N_INPUTS:]).all()
+        az, bz, cz = h.eval(n_rows)
+        assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
+        for kernel in KERNELS:
+            h.opt("kernel", kernel)
+            assert h.first_unsatisfied() == bad
+
+
+def _satisfiable(fid, t, n_base, n_rows):
+    """SURVEY 8d second variant: C_i := 1 * aux[new_i], w[new_i] := Az_i * Bz_i  => every row holds."""
+    p = FIELDS[fid].p
+    lens, cols, coeffs, inputs, aux = c_api.synth_instance(fid, synth.SEED, t, n_base, synth.N_INPUTS, n_rows)
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    _, az, bz, _ = inst.eval(2)
+    azi, bzi = c_api.limbs_to_ints(az), c_api.limbs_to_ints(bz)
+    n_aux0 = aux.shape[0]
+    new_lens, new_cols, new_coeffs = [], [], []
+    k = 0
+    for r in range(n_rows):
+        la, lb, lc = (int(x) for x in lens[3 * r: 3 * r + 3])
+        new_lens += [la, lb, 1]
+        new_cols += list(cols[k: k + la + lb]) + [(n_aux0 + r) | 0x80000000]
+        new_coeffs.append(coeffs[k: k + la + lb])
+        new_coeffs.append(np.array([[1, 0, 0, 0]], np.uint64))
+        k += la + lb + lc
+    prod = c_api.ints_to_limbs([(a * b) % p for a, b in zip(azi, bzi)])
+    return (np.asarray(new_lens, np.uint32), np.asarray(new_cols, np.uint32), np.concatenate(new_coeffs),
+            inputs, np.concatenate([aux, prod]))
+
+
+@pytest.mark.parametrize("fid", FIDS)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_satisfiable_then_flip_first_failure(fid, kernel):
+    p = FIELDS[fid].p
+    n_rows = 3000
+    lens, cols, coeffs, inputs, aux = _satisfiable(fid, 4, 2000, n_rows)
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    assert inst.check(2, False) == -1
+    rng = random.Random(99 + fid)
+    with Handle(fid) as h:
+        h.opt("kernel", kernel)
+        h.load_instance(lens, cols, coeffs, inputs, aux)
+        assert h.first_unsatisfied() == -1
+        for _ in range(6):  # flip-and-recheck (boolean.rs:783-787, num.rs:753-762): no matrix re-upload
+            idx = rng.randrange(aux.shape[0])
+            old = c_api.limbs_to_ints(aux[idx: idx + 1])[0]
+            new = (old + 1 + rng.randrange(p - 1)) % p
+            v = c_api.ints_to_limbs([new])
+            h.ok(h.L.bp_cs_set(h.h, 1, idx, v.ctypes.data))
+            inst.set(True, idx, new)
+            want = inst.check(2, False)
+            assert h.first_unsatisfied() == want and want >= 0
+            v = c_api.ints_to_limbs([old])
+            h.ok(h.L.bp_cs_set(h.h, 1, idx, v.ctypes.data))
+            inst.set(True, idx, old)
+            assert h.first_unsatisfied() == -1
+        # two failures: the MINIMUM row index is reported (test_cs.rs:493-496)
+        i1, i2 = aux.shape[0] - 5, aux.shape[0] - 900
+        for i in (i1, i2):
+            v = c_api.ints_to_limbs([12345])
+            h.ok(h.L.bp_cs_set(h.h, 1, i, v.ctypes.data))
+            inst.set(True, i, 12345)
+        assert h.first_unsatisfied() == inst.check(1, True) == n_rows - 900
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_ragged_empty_and_fat_rows(kernel):
+    """Zero-length LCs, 0-coefficients, a 1500-term MultiEq-like row, and rows of every small shape."""
+    fid = 0
+    p = FIELDS[fid].p
+    rng = random.Random(5)
+    n_aux = 4000
+    aux_vals = [rng.randrange(p) for _ in range(n_aux)]
+    inputs_vals = [1, 7, 9]
+    rows = []
+
+    def lc(n, sparse_from=0):
+        idx = sorted(rng.sample(range(sparse_from, n_aux), n))
+        return [(i | 0x80000000, rng.choice([0, 1, p - 1, 2, rng.randrange(p)])) for i in idx]
+
+    for r in range(700):
+        shape = r % 7
+        if shape == 0:
+            rows.append(([], [], []))
+        elif shape == 1:
+            rows.append((lc(1), [], lc(2)))
+        elif shape == 2:
+            rows.append(([(0, 1), (1, 5)] + lc(3), lc(1), []))
+        elif shape == 3:
+            rows.append((lc(2), lc(2), lc(1)))
+        elif shape == 4:
+            rows.append(([], [], lc(256)))
+        elif shape == 5:
+            rows.append((lc(1500 if r == 5 else 40), [(0, 1)], lc(245)))
+        else:
+            rows.append((lc(5), lc(2), lc(3)))
+    lens, cols, coeffs = [], [], []
+    for a, b, c in rows:
+        for l in (a, b, c):
+            lens.append(len(l))
+            cols += [x for x, _ in l]
+            coeffs += [v for _, v in l]
+    lens, cols = np.asarray(lens, np.uint32), np.asarray(cols, np.uint32)
+    coeffs = c_api.ints_to_limbs(coeffs)
+    inputs, aux = c_api.ints_to_limbs(inputs_vals), c_api.ints_to_limbs(aux_vals)
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    bad, az_r, bz_r, cz_r = inst.eval(2)
+    with Handle(fid) as h:
+        h.opt("kernel", kernel)
+        # ingest in three uneven batches
+        first = ctypes.c_uint64()
+        h.ok(h.L.bp_cs_alloc(h.h, 0, inputs[1:].ctypes.data, 2, ctypes.byref(first)))
+        assert first.value == 1
+        h.ok(h.L.bp_cs_alloc(h.h, 1, aux.ctypes.data, n_aux, ctypes.byref(first)))
+        assert first.value == 0
+        off = np.concatenate([[0], np.cumsum(lens)])
+        for r0, r1 in ((0, 1), (1, 300), (300, 700)):
+            k0, k1 = int(off[3 * r0]), int(off[3 * r1])
+            l_, c_, v_ = lens[3 * r0: 3 * r1].copy(), cols[k0:k1].copy(), coeffs[k0:k1].copy()
+            h.ok(h.L.bp_cs_enforce(h.h, r1 - r0, l_.ctypes.data, c_.ctypes.data if k1 > k0 else None, v_.ctypes.data if k1 > k0 else None))
+        assert h.first_unsatisfied() == bad
+        az, bz, cz = h.eval(700)
+        assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
+
+
+def test_errors_and_empty_system():
+    fid = 0
+    p = FIELDS[fid].p
+    with Handle(fid) as h:
+        assert h.first_unsatisfied() == -1  # empty system is satisfied (test_cs.rs:475)
+        assert h.counts() == (1, 0, 0, 0)
+        one = np.zeros(4, np.uint64)
+        h.ok(h.L.bp_cs_get(h.h, 0, 0, one.ctypes.data))
+        assert list(one) == [1, 0, 0, 0]
+        bad = c_api.ints_to_limbs([p])  # not canonical
+        first = ctypes.c_uint64()
+        assert h.L.bp_cs_alloc(h.h, 1, bad.ctypes.data, 1, ctypes.byref(first)) == -3
+        assert "canonical" in h.err()
+        assert h.counts()[1] == 0
+        ok = c_api.ints_to_limbs([p - 1])
+        h.ok(h.L.bp_cs_alloc(h.h, 1, ok.ctypes.data, 1, ctypes.byref(first)))
+        assert h.L.bp_cs_set(h.h, 1, 0, bad.ctypes.data) == -3
+        assert h.L.bp_cs_set(h.h, 1, 1, ok.ctypes.data) == -3  # index out of range
+        assert h.L.bp_cs_get(h.h, 0, 5, one.ctypes.data) == -3
+        # non-canonical coefficient rejected, row not committed
+        lens = np.asarray([1, 0, 0], np.uint32)
+        cols = np.asarray([0x80000000], np.uint32)
+        assert h.L.bp_cs_enforce(h.h, 1, lens.ctypes.data, cols.ctypes.data, bad.ctypes.data) == -3
+        assert h.counts()[2] == 0
+        # column out of range is detected at check time (reference: slice-index panic, test_cs.rs:146-147)
+        cols = np.asarray([0x80000000 | 7], np.uint32)
+        h.ok(h.L.bp_cs_enforce(h.h, 1, lens.ctypes.data, cols.ctypes.data, ok.ctypes.data))
+        row = ctypes.c_int64()
+        assert h.L.bp_cs_first_unsatisfied(h.h, ctypes.byref(row)) == -3
+    assert ffi_new_bad_device() == -1
+
+
+def ffi_new_bad_device():
+    from bellpepper_b200 import ffi
+
+    L = ffi.load()
+    hh = ffi.vp()
+    return L.bp_cs_new(0, 4096, 0, 0, 0, ctypes.byref(hh))
+
+
+@pytest.mark.parametrize("fid", FIDS)
+def test_eval_lc(fid):
+    p = FIELDS[fid].p
+    rng = random.Random(fid)
+    aux = [rng.randrange(p) for _ in range(300)]
+    with Handle(fid) as h:
+        a = c_api.ints_to_limbs(aux)
+        first = ctypes.c_uint64()
+        h.ok(h.L.bp_cs_alloc(h.h, 1, a.ctypes.data, len(aux), ctypes.byref(first)))
+        for n in (0, 1, 5, 33, 300):
+            idx = sorted(rng.sample(range(300), n))
+            co = [rng.choice([1, p - 1, rng.randrange(p)]) for _ in idx]
+            cols = np.asarray([0] + [i | 0x80000000 for i in idx], np.uint32)
+            vals = c_api.ints_to_limbs([3] + co)
+            out = np.zeros(4, np.uint64)
+            h.ok(h.L.bp_cs_eval_lc(h.h, cols.ctypes.data, vals.ctypes.data, n + 1, out.ctypes.data))
+            want = (3 + sum(c * aux[i] for c, i in zip(co, idx))) % p
+            assert c_api.limbs_to_ints(out)[0] == want
+
+
+def test_row_base_and_device_result():
+    """Row-sharded use: global row numbering + result left in device memory (torch used for memory only)."""
+    import torch
+
+    fid = 0
+    lens, cols, coeffs, inputs, aux = c_api.synth_instance(fid, synth.SEED, 3, 500, synth.N_INPUTS, 100)
+    with Handle(fid) as h:
+        h.load_instance(lens, cols, coeffs, inputs, aux)
+        h.ok(h.L.bp_cs_set_row_base(h.h, 1_000_000))
+        out = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+        h.ok(h.L.bp_cs_set_stream(h.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        h.ok(h.L.bp_cs_check_async(h.h, ctypes.c_void_p(out.data_ptr())))
+        torch.cuda.synchronize()
+        assert int(out.item()) == 1_000_000  # random rows: row 0 fails
+        assert h.first_unsatisfied() == 0
