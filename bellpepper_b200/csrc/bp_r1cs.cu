@@ -44,7 +44,7 @@ struct bp_cs {
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
     long long* d_result = nullptr;  // [0] first_bad
     unsigned int* d_err = nullptr;
-    void* h_pinned_small = nullptr;  // 64 B: result read-back / single-element set,get
+    void* h_pinned_small = nullptr;  // 64 B: [0,32) element, [32,40) first_bad, [40,44) err word, [48,56) tiny row_ptr
     void* h_stage[kNumStage] = {nullptr, nullptr};
     cudaEvent_t stage_ev[kNumStage] = {nullptr, nullptr};
     int stage_next = 0;
@@ -182,11 +182,11 @@ int upload(bp_cs* h, void* dst, const void* src, size_t bytes) {
 
 int read_flags(bp_cs* h, long long* first_bad, unsigned int* err) {
     char* hp = (char*)h->h_pinned_small;
-    CU(h, cudaMemcpyAsync(hp, h->d_result, 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(hp + 8, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(hp + 32, h->d_result, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(hp + 40, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    std::memcpy(first_bad, hp, 8);
-    std::memcpy(err, hp + 8, 4);
+    std::memcpy(first_bad, hp + 32, 8);
+    std::memcpy(err, hp + 40, 4);
     return BP_OK;
 }
 
@@ -197,10 +197,10 @@ int clear_err(bp_cs* h) {
 
 int check_err_word(bp_cs* h, const char* what) {
     char* hp = (char*)h->h_pinned_small;
-    CU(h, cudaMemcpyAsync(hp + 8, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(hp + 40, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     unsigned int e;
-    std::memcpy(&e, hp + 8, 4);
+    std::memcpy(&e, hp + 40, 4);
     if (e & 2u) return fail(h, BP_E_RANGE, "%s: a field element is not canonical (>= p)", what);
     if (e & 1u) return fail(h, BP_E_RANGE, "%s: a column index is out of range", what);
     return BP_OK;
@@ -318,7 +318,7 @@ int bp_cs_set_stream(bp_cs* h, void* s) {
     if (!h) return BP_E_ARG;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;  // cudaStreamLegacy (0x1) / cudaStreamPerThread (0x2) are valid values
     return BP_OK;
 }
 
@@ -553,8 +553,8 @@ int bp_cs_eval_lc(bp_cs* h, const uint32_t* cols, const uint64_t* coeffs, uint32
         if ((rc = upload(h, s, coeffs, (size_t)n * 32)) != BP_OK) return rc;
         if ((rc = upload(h, s + off_cols, cols, (size_t)n * 4)) != BP_OK) return rc;
         const uint32_t rp[2] = {0, n};
-        std::memcpy((char*)h->h_pinned_small + 16, rp, 8);
-        CU(h, cudaMemcpyAsync(s + off_rp, (char*)h->h_pinned_small + 16, 8, cudaMemcpyHostToDevice, h->stream));
+        std::memcpy((char*)h->h_pinned_small + 48, rp, 8);
+        CU(h, cudaMemcpyAsync(s + off_rp, (char*)h->h_pinned_small + 48, 8, cudaMemcpyHostToDevice, h->stream));
         // one LC of type A (lc index 0)
         DISPATCH_FIELD(h, (to_internal<F><<<grid_for(h, n, 128, 16), 128, 0, h->stream>>>((uint4*)s, (const uint32_t*)(s + off_rp), 0u, 1u,
                                                                                          0u, n, h->fc, h->d_err)));

@@ -113,7 +113,8 @@ int bp_cs_eval_async(bp_cs* cs, uint64_t* dev_az, uint64_t* dev_bz, uint64_t* de
 int bp_cs_eval_lc(bp_cs* cs, const uint32_t* cols, const uint64_t* coeffs_le, uint32_t n_terms, uint64_t out[4]);
 
 /* ---- execution control -----------------------------------------------------------------------------*/
-/* Use an existing CUDA stream (cudaStream_t as void*; NULL = the handle's own stream) for all work. */
+/* Use an existing CUDA stream (cudaStream_t as void*) for all work.  NULL = the handle's own non-blocking
+ * stream; the legacy default stream is cudaStreamLegacy, i.e. (void*)0x1. */
 int bp_cs_set_stream(bp_cs* cs, void* cuda_stream);
 /* Row-sharded use: global index of this handle's row 0 (default 0). */
 int bp_cs_set_row_base(bp_cs* cs, uint64_t row_base);

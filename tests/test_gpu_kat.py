@@ -53,7 +53,9 @@ def test_panics():  # test_cs.rs:325-333, 363-367, 280, 321
 
     with pytest.raises(bp.SynthesisError):
         cs.alloc("y", boom)
-    assert cs.scalar_aux() == [1] and "y" not in cs.named_objects
+    # the duplicate-path alloc pushed its value BEFORE the path check panicked (test_cs.rs:386-390), the
+    # '/'-name one panicked in compute_path before pushing, the failing closure pushed nothing
+    assert cs.scalar_aux() == [1, 2] and "y" not in cs.named_objects
 
 
 def test_allocated_bit():  # crates/bellpepper-core/src/gadgets/boolean.rs:777-788, :86-91

@@ -242,7 +242,7 @@ def test_row_base_and_device_result():
         h.load_instance(lens, cols, coeffs, inputs, aux)
         h.ok(h.L.bp_cs_set_row_base(h.h, 1_000_000))
         out = torch.zeros(1, dtype=torch.int64, device="cuda:0")
-        h.ok(h.L.bp_cs_set_stream(h.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        h.ok(h.L.bp_cs_set_stream(h.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream or 1)))
         h.ok(h.L.bp_cs_check_async(h.h, ctypes.c_void_p(out.data_ptr())))
         torch.cuda.synchronize()
         assert int(out.item()) == 1_000_000  # random rows: row 0 fails

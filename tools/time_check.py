@@ -26,7 +26,7 @@ N = 1 << a.log_rows
 n_vars = 1 << (a.log_vars if a.log_vars is not None else a.log_rows)
 h = ffi.vp()
 assert L.bp_cs_new(a.field, 0, N, int(N * 3 * a.t * 1.02) + 1024, n_vars, ctypes.byref(h)) == 0
-st = torch.cuda.current_stream().cuda_stream
+st = torch.cuda.current_stream().cuda_stream or 1  # 0 = legacy default stream -> cudaStreamLegacy
 assert L.bp_cs_set_stream(h, ctypes.c_void_p(st)) == 0
 t0 = time.time()
 assert L.bp_cs_synth_witness(h, 0x5962BE3D763D318D, n_vars, 16) == 0
