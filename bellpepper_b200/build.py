@@ -27,14 +27,15 @@ def _stale(target: str, sources) -> bool:
 
 def _sources():
     return (glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))
-            + glob.glob(os.path.join(CSRC, "host", "*.hpp"))
+            + glob.glob(os.path.join(CSRC, "host", "*.hpp")) + glob.glob(os.path.join(CSRC, "host", "*.cpp"))
             + glob.glob(os.path.join(HERE, "..", "include", "*.h")))
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources()
     if force or _stale(LIB, srcs):
-        cmd = ["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "bp_r1cs.cu")]
+        cmd = ["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "bp_r1cs.cu"),
+               os.path.join(CSRC, "host", "fixtures.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True, cwd=CSRC)

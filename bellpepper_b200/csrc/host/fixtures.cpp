@@ -1,0 +1,251 @@
+// C wrappers over the C++ host front-end (see include/bp_fixtures.h).
+#include "../../../include/bp_fixtures.h"
+
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "gadgets.hpp"
+
+using namespace bph;
+
+namespace {
+
+// Forwards witness always, rows only while enabled (row sharding by compression block).
+struct FilterSink : Sink {
+    Sink* inner;
+    bool rows_enabled = true;
+    uint64_t rows_dropped = 0;
+    explicit FilterSink(Sink* s) : inner(s) {}
+    void alloc(int is_aux, const uint64_t* v, uint64_t n) override { inner->alloc(is_aux, v, n); }
+    void enforce(uint64_t n_rows, const uint32_t* l, const uint32_t* c, const uint64_t* v, uint64_t nnz) override {
+        if (rows_enabled) inner->enforce(n_rows, l, c, v, nnz);
+        else rows_dropped += n_rows;
+    }
+    bp_cs* handle() override { return inner->handle(); }
+};
+
+}  // namespace
+
+struct bp_tcs {
+    int field;
+    bool named;
+    bp_cs* h = nullptr;
+    std::unique_ptr<Sink> base;
+    std::unique_ptr<FilterSink> filter;
+    std::unique_ptr<TestConstraintSystem> named_cs;
+    std::unique_ptr<BulkConstraintSystem> bulk_cs;
+    std::string err;
+};
+
+namespace {
+
+template <class F> int guarded(bp_tcs* t, F&& f) {
+    try {
+        f();
+        return BP_OK;
+    } catch (const SynthesisError& e) {
+        t->err = e.what();
+        return e.kind == SynthesisError::Native ? BP_E_CUDA : BP_E_STATE;
+    } catch (const std::out_of_range& e) {
+        t->err = e.what();
+        return BP_E_RANGE;
+    } catch (const std::exception& e) {
+        t->err = e.what();
+        return BP_E_STATE;
+    }
+}
+
+template <class CS> void alloc_message_bits(CS& cs, const uint8_t* msg, uint64_t len, std::vector<Boolean>& bits) {
+    bits.reserve(len * 8);
+    for (uint64_t i = 0; i < len; ++i)
+        for (int j = 7; j >= 0; --j) {
+            auto ns = cs.ns([&] { return "input bit " + std::to_string(i) + " " + std::to_string(j); });
+            bits.push_back(Boolean::from(AllocatedBit::alloc(ns, (OptBool)((msg[i] >> j) & 1))));
+        }
+}
+
+void bits_to_bytes_be(const std::vector<Boolean>& bits, uint8_t* out) {
+    for (size_t i = 0; i < bits.size() / 8; ++i) {
+        uint8_t b = 0;
+        for (int j = 0; j < 8; ++j) {
+            const OptBool v = bits[8 * i + j].get_value();
+            if (v < 0) throw SynthesisError::assignment_missing();
+            b = (uint8_t)((b << 1) | v);
+        }
+        out[i] = b;
+    }
+}
+
+// sha256() with row filtering per compression block; same circuit as gadgets.hpp `sha256`.
+template <class CS>
+void sha256_sharded(CS& cs, FilterSink& fs, const uint8_t* msg, uint64_t len, uint64_t bb, uint64_t be, uint8_t digest[32], uint64_t* rows_before) {
+    // the input-bit rows belong to "block -1": kept by the shard that holds block 0
+    cs.flush();
+    fs.rows_enabled = bb == 0;
+    std::vector<Boolean> input;
+    alloc_message_bits(cs, msg, len, input);
+    std::vector<Boolean> padded = input;
+    const uint64_t plen = padded.size();
+    padded.push_back(Boolean::constant(true));
+    while ((padded.size() + 64) % 512 != 0) padded.push_back(Boolean::constant(false));
+    for (int i = 63; i >= 0; --i) padded.push_back(Boolean::constant((plen >> i) & 1));
+    std::vector<UInt32> cur = sha256_iv();
+    uint64_t before = 0;
+    for (uint64_t blk = 0; blk < padded.size() / 512; ++blk) {
+        cs.flush();
+        const bool keep = blk >= bb && blk < be;
+        if (keep && !fs.rows_enabled && blk == bb) before = fs.rows_dropped;
+        fs.rows_enabled = keep;
+        auto ns = cs.ns([&] { return "block " + std::to_string(blk); });
+        cur = sha256_compression_function(ns, padded.data() + 512 * blk, cur);
+    }
+    cs.flush();
+    fs.rows_enabled = true;
+    std::vector<Boolean> out;
+    for (auto& wd : cur) wd.into_bits_be(out);
+    bits_to_bytes_be(out, digest);
+    if (rows_before) *rows_before = before;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bp_tcs_new(int field, int device, int named, uint64_t reserve_rows, uint64_t reserve_nnz, uint64_t reserve_vars, bp_tcs** out) {
+    if (!out || field < 0 || field > 2) return BP_E_ARG;
+    *out = nullptr;
+    std::unique_ptr<bp_tcs> t(new bp_tcs());
+    t->field = field;
+    t->named = named != 0;
+    if (device >= 0) {
+        const int rc = bp_cs_new(field, device, reserve_rows, reserve_nnz, reserve_vars, &t->h);
+        if (rc != BP_OK) return rc;
+        t->base.reset(new DeviceSink(t->h));
+    } else {
+        t->base.reset(new HostSink());
+    }
+    t->filter.reset(new FilterSink(t->base.get()));
+    if (t->named) t->named_cs.reset(new TestConstraintSystem(field, t->filter.get()));
+    else t->bulk_cs.reset(new BulkConstraintSystem(field, t->filter.get()));
+    *out = t.release();
+    return BP_OK;
+}
+
+void bp_tcs_free(bp_tcs* t) {
+    if (!t) return;
+    t->named_cs.reset();
+    t->bulk_cs.reset();
+    if (t->h) bp_cs_free(t->h);
+    delete t;
+}
+
+const char* bp_tcs_last_error(const bp_tcs* t) { return t ? t->err.c_str() : "null"; }
+bp_cs* bp_tcs_handle(bp_tcs* t) { return t ? t->h : nullptr; }
+
+int bp_tcs_flush(bp_tcs* t) {
+    if (!t) return BP_E_ARG;
+    return guarded(t, [&] {
+        if (t->named) t->named_cs->flush();
+        else t->bulk_cs->flush();
+    });
+}
+
+int bp_tcs_sha256_block(bp_tcs* t, const uint8_t block[64], uint8_t out32[32]) {
+    if (!t || !block || !out32) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            std::vector<Boolean> bits;
+            for (int i = 0; i < 512; ++i) {
+                auto ns = cs.ns([&] { return "input bit " + std::to_string(i); });
+                bits.push_back(Boolean::from(AllocatedBit::alloc(ns, (OptBool)((block[i / 8] >> (7 - i % 8)) & 1))));
+            }
+            std::vector<UInt32> r = sha256_compression_function(cs, bits.data(), sha256_iv());
+            std::vector<Boolean> ob;
+            for (auto& wd : r) wd.into_bits_be(ob);
+            bits_to_bytes_be(ob, out32);
+            cs.flush();
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
+int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t bb, uint64_t be, uint8_t digest[32], uint64_t* rows_before) {
+    if (!t || (!msg && len) || !digest) return BP_E_ARG;
+    return guarded(t, [&] {
+        if (t->named) sha256_sharded(*t->named_cs, *t->filter, msg, len, bb, be, digest, rows_before);
+        else sha256_sharded(*t->bulk_cs, *t->filter, msg, len, bb, be, digest, rows_before);
+    });
+}
+
+int64_t bp_tcs_which_is_unsatisfied(bp_tcs* t, char* path, uint64_t cap) {
+    if (!t) return -5;
+    int64_t row = -1;
+    const int rc = guarded(t, [&] {
+        row = t->named ? t->named_cs->first_unsatisfied_row() : t->bulk_cs->first_unsatisfied_row();
+        if (path && cap) {
+            path[0] = 0;
+            if (row >= 0 && t->named) {
+                const std::string& p = t->named_cs->row_path((uint64_t)row);
+                std::strncpy(path, p.c_str(), cap - 1);
+                path[cap - 1] = 0;
+            }
+        }
+    });
+    return rc == BP_OK ? row : (int64_t)rc - 1;
+}
+
+int bp_tcs_set(bp_tcs* t, const char* path, const uint64_t v[4]) {
+    if (!t || !path || !v) return BP_E_ARG;
+    if (!t->named) return BP_E_STATE;
+    return guarded(t, [&] {
+        Fr x;
+        std::memcpy(x.l, v, 32);
+        t->named_cs->set(path, x);
+    });
+}
+
+int bp_tcs_get(bp_tcs* t, const char* path, uint64_t v[4]) {
+    if (!t || !path || !v) return BP_E_ARG;
+    if (!t->named) return BP_E_STATE;
+    return guarded(t, [&] {
+        const Fr x = t->named_cs->get(path);
+        std::memcpy(v, x.l, 32);
+    });
+}
+
+uint64_t bp_tcs_num_constraints(const bp_tcs* t) { return t->named ? t->named_cs->num_constraints() : t->bulk_cs->num_constraints(); }
+uint64_t bp_tcs_num_inputs(const bp_tcs* t) { return t->named ? t->named_cs->num_inputs() : t->bulk_cs->num_inputs(); }
+uint64_t bp_tcs_num_aux(const bp_tcs* t) { return t->named ? t->named_cs->num_aux() : t->bulk_cs->num_aux(); }
+
+int bp_tcs_row_path(const bp_tcs* t, uint64_t row, char* path, uint64_t cap) {
+    if (!t || !path || !cap) return BP_E_ARG;
+    if (!t->named) return BP_E_STATE;
+    if (row >= t->named_cs->num_constraints()) return BP_E_RANGE;
+    const std::string& p = t->named_cs->row_path(row);
+    std::strncpy(path, p.c_str(), cap - 1);
+    path[cap - 1] = 0;
+    return BP_OK;
+}
+
+int bp_tcs_host_csr(bp_tcs* t, const uint32_t** lens, uint64_t* n_rows, const uint32_t** cols, const uint64_t** coeffs, uint64_t* nnz,
+                    const uint64_t** inputs, uint64_t* n_inputs, const uint64_t** aux, uint64_t* n_aux) {
+    if (!t) return BP_E_ARG;
+    HostSink* hs = dynamic_cast<HostSink*>(t->base.get());
+    if (!hs) return BP_E_STATE;
+    const int rc = bp_tcs_flush(t);
+    if (rc != BP_OK) return rc;
+    *lens = hs->lens.data();
+    *n_rows = hs->lens.size() / 3;
+    *cols = hs->cols.data();
+    *coeffs = hs->coeffs.data();
+    *nnz = hs->cols.size();
+    *inputs = hs->inputs.data();
+    *n_inputs = hs->inputs.size() / 4;
+    *aux = hs->aux.data();
+    *n_aux = hs->aux.size() / 4;
+    return BP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""ctypes binding of include/bp_fixtures.h: the C++ host front-end (B200-backed TestConstraintSystem mirror +
+gadget circuits).  Used by tests and bench.py; production C++ users include csrc/host/*.hpp directly."""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import ffi
+
+vp = ctypes.c_void_p
+u64p = ctypes.POINTER(ctypes.c_uint64)
+_SIGS = {
+    "bp_tcs_new": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(vp)]),
+    "bp_tcs_free": (None, [vp]),
+    "bp_tcs_last_error": (ctypes.c_char_p, [vp]),
+    "bp_tcs_handle": (vp, [vp]),
+    "bp_tcs_flush": (ctypes.c_int, [vp]),
+    "bp_tcs_sha256_block": (ctypes.c_int, [vp, vp, vp]),
+    "bp_tcs_sha256": (ctypes.c_int, [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, u64p]),
+    "bp_tcs_which_is_unsatisfied": (ctypes.c_int64, [vp, vp, ctypes.c_uint64]),
+    "bp_tcs_set": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
+    "bp_tcs_get": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
+    "bp_tcs_num_constraints": (ctypes.c_uint64, [vp]),
+    "bp_tcs_num_inputs": (ctypes.c_uint64, [vp]),
+    "bp_tcs_num_aux": (ctypes.c_uint64, [vp]),
+    "bp_tcs_row_path": (ctypes.c_int, [vp, ctypes.c_uint64, vp, ctypes.c_uint64]),
+    "bp_tcs_host_csr": (ctypes.c_int, [vp] + [ctypes.POINTER(vp), u64p, ctypes.POINTER(vp), ctypes.POINTER(vp), u64p,
+                                              ctypes.POINTER(vp), u64p, ctypes.POINTER(vp), u64p]),
+}
+_bound = False
+U64_MAX = (1 << 64) - 1
+
+
+def _lib():
+    global _bound
+    L = ffi.load()
+    if not _bound:
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _bound = True
+    return L
+
+
+def available() -> bool:
+    try:
+        return hasattr(_lib(), "bp_tcs_sha256")
+    except Exception:
+        return False
+
+
+def xorshift_bytes(n: int, seed=(0x3DBE6259, 0x8D313D76, 0x3237DB17, 0xE5BC0654)) -> bytes:
+    """The reference tests' XorShiftRng stream (`next_u32() as u8`); seed words are the LE u32s of the seed bytes
+    [0x59,0x62,0xbe,0x3d, 0x76,0x3d,0x31,0x8d, 0x17,0xdb,0x37,0x32, 0x54,0x06,0xbc,0xe5] (sha256.rs:312-315)."""
+    x, y, z, w = seed
+    out = np.empty(n, np.uint8)
+    for i in range(n):
+        t = (x ^ (x << 11)) & 0xFFFFFFFF
+        x, y, z = y, z, w
+        w = (w ^ (w >> 19) ^ t ^ (t >> 8)) & 0xFFFFFFFF
+        out[i] = w & 0xFF
+    return out.tobytes()
+
+
+class Tcs:
+    """One C++ TestConstraintSystem (+ its device handle or host recorder)."""
+
+    def __init__(self, field: int, device: int = 0, named: bool = True, reserve=(0, 0, 0)):
+        self.L = _lib()
+        self.t = vp()
+        rc = self.L.bp_tcs_new(field, device, int(named), *reserve, ctypes.byref(self.t))
+        if rc != 0:
+            raise RuntimeError(f"bp_tcs_new -> {rc} (device {device}; there is no CPU evaluation path)")
+        self.field = field
+
+    def close(self, keep_handle: bool = False):
+        if self.t:
+            self.L.bp_tcs_free(self.t)
+            self.t = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"bp_tcs error {rc}: {(self.L.bp_tcs_last_error(self.t) or b'').decode()}")
+
+    @property
+    def handle(self):
+        return self.L.bp_tcs_handle(self.t)
+
+    def sha256_block(self, block: bytes) -> bytes:
+        assert len(block) == 64
+        out = ctypes.create_string_buffer(32)
+        self._ck(self.L.bp_tcs_sha256_block(self.t, block, out))
+        return out.raw
+
+    def sha256(self, msg: bytes, block_begin: int = 0, block_end: int = U64_MAX) -> Tuple[bytes, int]:
+        out = ctypes.create_string_buffer(32)
+        before = ctypes.c_uint64()
+        self._ck(self.L.bp_tcs_sha256(self.t, msg, len(msg), block_begin, block_end, out, ctypes.byref(before)))
+        return out.raw, before.value
+
+    def which_is_unsatisfied(self) -> Optional[str]:
+        buf = ctypes.create_string_buffer(512)
+        row = self.L.bp_tcs_which_is_unsatisfied(self.t, buf, 512)
+        if row < -1:
+            self._ck(int(row) + 1)
+        return None if row < 0 else (buf.value.decode() or str(row))
+
+    def first_unsatisfied_row(self) -> int:
+        row = self.L.bp_tcs_which_is_unsatisfied(self.t, None, 0)
+        if row < -1:
+            self._ck(int(row) + 1)
+        return int(row)
+
+    def is_satisfied(self) -> bool:
+        return self.first_unsatisfied_row() < 0
+
+    def set(self, path: str, value: int):
+        v = np.frombuffer(int(value).to_bytes(32, "little"), dtype="<u8").copy()
+        self._ck(self.L.bp_tcs_set(self.t, path.encode(), v.ctypes.data))
+
+    def get(self, path: str) -> int:
+        v = np.zeros(4, np.uint64)
+        self._ck(self.L.bp_tcs_get(self.t, path.encode(), v.ctypes.data))
+        return int.from_bytes(v.tobytes(), "little")
+
+    def num_constraints(self) -> int:
+        return self.L.bp_tcs_num_constraints(self.t)
+
+    def num_inputs(self) -> int:
+        return self.L.bp_tcs_num_inputs(self.t)
+
+    def num_aux(self) -> int:
+        return self.L.bp_tcs_num_aux(self.t)
+
+    def row_path(self, row: int) -> str:
+        buf = ctypes.create_string_buffer(512)
+        self._ck(self.L.bp_tcs_row_path(self.t, row, buf, 512))
+        return buf.value.decode()
+
+    def host_csr(self):
+        """(lens, cols, coeffs[nnz,4], inputs[n,4], aux[n,4]) copies of a host-recording system."""
+        p = [vp() for _ in range(5)]
+        n = [ctypes.c_uint64() for _ in range(4)]
+        self._ck(self.L.bp_tcs_host_csr(self.t, ctypes.byref(p[0]), ctypes.byref(n[0]), ctypes.byref(p[1]), ctypes.byref(p[2]),
+                                         ctypes.byref(n[1]), ctypes.byref(p[3]), ctypes.byref(n[2]), ctypes.byref(p[4]), ctypes.byref(n[3])))
+        n_rows, nnz, n_in, n_aux = (x.value for x in n)
+
+        def arr(ptr, count, ctype, dtype):
+            if count == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(count,)).copy()
+
+        lens = arr(p[0], 3 * n_rows, ctypes.c_uint32, np.uint32)
+        cols = arr(p[1], nnz, ctypes.c_uint32, np.uint32)
+        coeffs = arr(p[2], 4 * nnz, ctypes.c_uint64, np.uint64).reshape(-1, 4)
+        inputs = arr(p[3], 4 * n_in, ctypes.c_uint64, np.uint64).reshape(-1, 4)
+        aux = arr(p[4], 4 * n_aux, ctypes.c_uint64, np.uint64).reshape(-1, 4)
+        return lens, cols, coeffs, inputs, aux
+
+
+def chain_message(blocks: int) -> bytes:
+    """Message whose sha256() circuit has exactly `blocks` compression calls (the last one holds the padding)."""
+    return xorshift_bytes(64 * blocks - 9)
+
+
+def sha256_chain_host_csr(field: int, blocks: int):
+    with Tcs(field, device=-1, named=False) as t:
+        t.sha256(chain_message(blocks))
+        return t.host_csr()
+
+
+def sha256_chain_into_new_handle(field: int, device: int, blocks: int, rank: int = 0, world: int = 1):
+    """BASELINE configs[1]: sha256 gadget over `blocks` chained compression blocks, rows of this rank's block range
+    streamed into a fresh device handle.  Returns (bp_cs handle as c_void_p, info); the caller frees via `info['tcs']`."""
+    b0, b1 = rank * blocks // world, (rank + 1) * blocks // world
+    per_block_rows, per_block_terms, per_block_vars = 26400, 170000, 26500
+    t = Tcs(field, device, named=False,
+            reserve=((b1 - b0) * per_block_rows + 4096, (b1 - b0) * per_block_terms + 65536, blocks * per_block_vars + 4096))
+    digest, before = t.sha256(chain_message(blocks), b0, b1)
+    L = ffi.load()
+    h = vp(t.handle)
+    assert L.bp_cs_set_row_base(h, before) == 0
+    info = {"rows_total": t.num_constraints(), "row0": before, "blocks": blocks, "digest": digest.hex(), "tcs": t}
+    return h, info

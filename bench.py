@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- R1CS constraints/sec of the (A.w) o (B.w) == C.w satisfaction check on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.  For N > 1 it is launched under torchrun (one rank per GPU).
+
+A "step" is one pass of the hot path -- `which_is_unsatisfied` over every constraint of the workload with
+the current witness -- i.e. one launch of the check kernel (plus its one-thread result-init kernel), and for
+N > 1 the min-all-reduce of the first-unsatisfied row.
+
+  value     constraints/s, matrices and witness resident in HBM, CUDA-event timed on the launching stream
+  e2e       the same through the C ABI with the witness in pinned HOST memory: per step H2D of the whole
+            witness (bp_cs_set_range), the check, and the D2H of the result (bp_cs_first_unsatisfied)
+  roofline  algorithmic bytes (36 B/term + 12 B/row + 32 B/variable) / measured duration vs the
+            measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the CPU restatement of the reference's loop (oracle/bp_oracle.c; the reference is Rust and cannot
+            be built in this image) on a bounded sample of the same workload, all host threads
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x5962BE3D763D318D
+N_INPUTS = 16
+
+WORKLOADS = {
+    # name: (kind, field, params) -- BASELINE.json configs
+    "sha256_chain_4096_pallas": ("sha256", 1, {"blocks": 4096}),                       # configs[1] (metric config)
+    "synthetic_2p24_t6_bls12_381": ("synthetic", 0, {"log_rows": 24, "t": 6}),        # configs[3]
+    "synthetic_2p27_t32_pallas": ("synthetic", 1, {"log_rows": 27, "t": 32}),         # configs[4] (8 GPUs)
+    "synthetic_2p20_t6_bls12_381": ("synthetic", 0, {"log_rows": 20, "t": 6}),        # small, for quick checks
+    "sha256_chain_64_pallas": ("sha256", 1, {"blocks": 64}),
+}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(L, ffi, name, rank, world, device):
+    """Create a handle holding this rank's row shard of the workload (rows sharded contiguously)."""
+    kind, field, prm = WORKLOADS[name]
+    h = ffi.vp()
+    info = {"field": field}
+    t0 = time.time()
+    if kind == "synthetic":
+        n_rows_total = 1 << prm["log_rows"]
+        n_vars = n_rows_total
+        t = prm["t"]
+        r0 = rank * n_rows_total // world
+        r1 = (rank + 1) * n_rows_total // world
+        n = r1 - r0
+        rc = L.bp_cs_new(field, device, n, int(n * 3 * t * 1.01) + 4096, n_vars, ctypes.byref(h))
+        assert rc == 0, f"bp_cs_new -> {rc} (no CUDA device? there is no CPU path)"
+        assert L.bp_cs_synth_witness(h, SEED, n_vars, N_INPUTS) == 0, L.bp_cs_last_error(h)
+        CH = 1 << 20
+        for s in range(r0, r1, CH):
+            rc = L.bp_cs_synth_rows(h, SEED, t, n_vars, N_INPUTS, s, min(CH, r1 - s))
+            assert rc == 0, L.bp_cs_last_error(h)
+        assert L.bp_cs_set_row_base(h, r0) == 0
+        info.update(rows_total=n_rows_total, row0=r0, t=t)
+    elif kind == "sha256":
+        from bellpepper_b200 import fixtures
+
+        h, finfo = fixtures.sha256_chain_into_new_handle(field, device, prm["blocks"], rank, world)
+        info.update(finfo)
+    else:
+        raise ValueError(kind)
+    assert L.bp_cs_sync(h) == 0
+    info["ingest_s"] = round(time.time() - t0, 3)
+    c = [ctypes.c_uint64() for _ in range(4)]
+    assert L.bp_cs_counts(h, *[ctypes.byref(x) for x in c]) == 0
+    info["n_inputs"], info["n_aux"], info["rows"], info["nnz"] = [x.value for x in c]
+    return h, info
+
+
+def cpu_reference_rate(name, sample_rows_log2, threads, steps=1, warmup=0):
+    """The CPU restatement of the reference loop on a bounded sample (first 2^k rows) of the workload."""
+    from oracle import c_api, lib
+
+    kind, field, prm = WORKLOADS[name]
+    if kind == "synthetic":
+        n_vars = 1 << prm["log_rows"]
+        n = min(1 << sample_rows_log2, 1 << prm["log_rows"])
+        lens, cols, coeffs = c_api.synth_rows(field, SEED, prm["t"], n_vars, N_INPUTS, 0, n)
+        w = c_api.synth_witness(field, SEED, 0, n_vars)
+        inst = c_api.Instance(field, lens, cols, coeffs, w[:N_INPUTS], w[N_INPUTS:])
+        sample = f"first 2^{sample_rows_log2} rows of {name} (full {n_vars}-element witness)"
+    else:
+        from bellpepper_b200 import fixtures
+
+        blocks = max(1, min(prm["blocks"], (1 << sample_rows_log2) // 26400))
+        lens, cols, coeffs, inputs, aux = fixtures.sha256_chain_host_csr(field, blocks)
+        n = lens.size // 3
+        inst = c_api.Instance(field, lens, cols, coeffs, inputs, aux)
+        sample = f"first {blocks} blocks ({n} rows) of {name}"
+    threads = threads or lib().bpo_max_threads()
+    for _ in range(warmup):
+        inst.check(threads, False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        inst.check(threads, False)
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt * 1e3, threads, sample, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BP_BENCH_WORKLOAD", "default"))
+    ap.add_argument("--cpu-sample-log2", type=int, default=22)
+    ap.add_argument("--kernel", type=int, default=None, help="force kernel variant (0 direct, 1 staged)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = a.workload
+    if workload == "default":
+        workload = default_workload()
+    kind, field, prm = WORKLOADS[workload]
+    from bellpepper_b200.fields import NAME as FIELD_NAME
+
+    base = {
+        "metric": "R1CS constraints/sec (256-bit Fp SpMV x3 + Hadamard check)",
+        "unit": "constraints/s",
+        "n_gpus": a.gpus,
+        "steps": a.steps,
+        "warmup": a.warmup,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "u256 (8x u32 limbs, integer mod p)",
+        "data": "synthetic",
+        "config": {"workload": workload, "field": FIELD_NAME[field], **prm,
+                   "l2_policy": "inputs_larger_than_l2", "parallelism": f"row-sharded x{a.gpus}, witness replicated"},
+    }
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        rate, ms, threads, sample, n = cpu_reference_rate(workload, a.cpu_sample_log2, 0, steps=max(1, a.steps), warmup=min(a.warmup, 1))
+        out = dict(base)
+        out.update({
+            "impl": "reference", "value": rate, "ms_per_step": ms,
+            "cpu_baseline": {"value": rate, "unit": "constraints/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference is Rust (no toolchain in this image): C restatement of test_cs.rs:137-155,239-253, OpenMP over rows "
+                    "(the reference itself is single-threaded); each step checks the bounded sample named in cpu_baseline.sample",
+        })
+        print(json.dumps(out), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from bellpepper_b200 import ffi
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = ffi.load()
+    h, info = build_workload(L, ffi, workload, rank, world, local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    assert L.bp_cs_set_stream(h, ctypes.c_void_p(stream.cuda_stream)) == 0
+    if a.kernel is not None:
+        assert L.bp_cs_set_option(h, b"kernel", a.kernel) == 0
+
+    result = torch.zeros(1, dtype=torch.int64, device=f"cuda:{local_rank}")
+    n_rows_total = info.get("rows_total", info["rows"])
+    n_vars = info["n_inputs"] + info["n_aux"]
+
+    def launches():
+        v = ctypes.c_int64()
+        L.bp_cs_get_option(h, b"launches", ctypes.byref(v))
+        return v.value
+
+    def step_device():
+        rc = L.bp_cs_check_async(h, ctypes.c_void_p(result.data_ptr()))
+        assert rc == 0, L.bp_cs_last_error(h)
+        if world > 1:
+            dist.all_reduce(result, op=dist.ReduceOp.MIN)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(a.warmup):
+            step_device()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        n_launch = launches() - l0
+        ms_total = e0.elapsed_time(e1)
+        first_bad = int(result.item())
+
+        # ---- e2e: witness from pinned host memory every step, result back to the host ----
+        w_in = torch.empty((info["n_inputs"], 4), dtype=torch.int64).pin_memory()
+        w_aux = torch.empty((info["n_aux"], 4), dtype=torch.int64).pin_memory()
+        assert L.bp_cs_witness(h, 0, 0, info["n_inputs"], ctypes.c_void_p(w_in.data_ptr())) == 0
+        assert L.bp_cs_witness(h, 1, 0, info["n_aux"], ctypes.c_void_p(w_aux.data_ptr())) == 0
+        row = ctypes.c_int64()
+
+        def step_e2e():
+            assert L.bp_cs_set_range(h, 0, 0, info["n_inputs"], ctypes.c_void_p(w_in.data_ptr())) == 0, L.bp_cs_last_error(h)
+            assert L.bp_cs_set_range(h, 1, 0, info["n_aux"], ctypes.c_void_p(w_aux.data_ptr())) == 0, L.bp_cs_last_error(h)
+            if world > 1:
+                step_device()
+                return int(result.item())
+            assert L.bp_cs_first_unsatisfied(h, ctypes.byref(row)) == 0, L.bp_cs_last_error(h)
+            return row.value
+
+        e2e_steps = max(3, min(a.steps, 10))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_step = ms_total / a.steps
+    t_ms = torch.tensor([ms_step, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms = float(t_ms[0]), float(t_ms[1])
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        alg_bytes = info["nnz"] * 36 + info["rows"] * 12 + n_vars * 32  # this rank's shard + the whole witness
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        used = ctypes.c_int64()
+        L.bp_cs_get_option(h, b"last_kernel", ctypes.byref(used))
+        out = dict(base)
+        out.update({
+            "value": n_rows_total / (ms_step * 1e-3),
+            "ms_per_step": ms_step,
+            "e2e": {"value": n_rows_total / (e2e_ms * 1e-3), "unit": "constraints/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": n_vars * 32, "d2h_bytes_per_step": 12 if world == 1 else 8,
+                    "what": "witness (pinned host) -> bp_cs_set_range -> check -> result to host; matrices resident (ingested once)"},
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": f"of {peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "staged" if used.value else "direct"},
+            "clocks": clocks,
+            "first_unsatisfied_row": None if first_bad == 0x7FFFFFFFFFFFFFFF else first_bad,
+            "instance": {k: info[k] for k in ("rows", "nnz", "n_inputs", "n_aux", "ingest_s")},
+        })
+        if not a.no_cpu_baseline:
+            rate, ms, threads, sample, n = cpu_reference_rate(workload, a.cpu_sample_log2, 0, steps=1, warmup=0)
+            out["cpu_baseline"] = {"value": rate, "unit": "constraints/s", "cores": threads, "kind": "port", "sample": sample,
+                                   "ms": ms}
+        print(json.dumps(out), flush=True)
+    L.bp_cs_free(h)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def default_workload():
+    """configs[1] (the metric's config) once the gadget front-end is built into the library, else configs[3]."""
+    try:
+        from bellpepper_b200 import fixtures  # noqa: F401
+
+        if fixtures.available():
+            return "sha256_chain_4096_pallas"
+    except Exception:
+        pass
+    return "synthetic_2p24_t6_bls12_381"
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,58 @@
+/* bp_fixtures.h -- C entry points of the C++ host front-end (bellpepper_b200/csrc/host/): the B200-backed
+ * TestConstraintSystem mirror and the gadget circuits that produce BASELINE configs 1-3.
+ *
+ * The front-end itself is header-only C++ (cs.hpp, lc.hpp, gadgets.hpp) and is what a C++ user includes; these
+ * C wrappers exist so that pytest (ctypes) and bench.py can drive it.  They replace nothing in the reference on
+ * their own: the reference-side equivalents are `TestConstraintSystem` (crates/bellpepper-core/src/util_cs/
+ * test_cs.rs) and the gadget functions cited at each entry point.
+ */
+#ifndef BP_FIXTURES_H
+#define BP_FIXTURES_H
+
+#include <stdint.h>
+#include "bp_r1cs.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bp_tcs bp_tcs;
+
+/* device >= 0: rows/witness stream into a fresh bp_cs on that device (evaluation available).
+ * device <  0: host recording only (structure export for CPU-side tests and the CPU baseline; no evaluation).
+ * named != 0 keeps the reference's path bookkeeping (test_cs.rs:325-375); named == 0 skips every annotation. */
+int bp_tcs_new(int field, int device, int named, uint64_t reserve_rows, uint64_t reserve_nnz, uint64_t reserve_vars, bp_tcs** out);
+void bp_tcs_free(bp_tcs* t);
+const char* bp_tcs_last_error(const bp_tcs* t);
+bp_cs* bp_tcs_handle(bp_tcs* t);   /* NULL for host recording */
+int bp_tcs_flush(bp_tcs* t);
+
+/* sha256_compression_function over 512 freshly allocated bits ("input bit i") with the IV
+ * (crates/bellpepper/src/gadgets/sha256.rs:310-336 test_full_block).  out32 = the 8 output words, big-endian. */
+int bp_tcs_sha256_block(bp_tcs* t, const uint8_t block[64], uint8_t out32[32]);
+
+/* sha256() gadget over `len` message bytes, each bit allocated as "input bit <byte> <bit>" most significant
+ * first (sha256.rs:50-77, 365-417).  Only rows of compression blocks [block_begin, block_end) are kept (row
+ * sharding for multi-GPU; pass 0, UINT64_MAX for all); every witness element is always kept.  *rows_before
+ * receives the number of rows that precede the first kept row (the shard's global row base). */
+int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t block_begin, uint64_t block_end, uint8_t digest[32],
+                  uint64_t* rows_before);
+
+/* TestConstraintSystem surface (test_cs.rs:239-323).  which_is_unsatisfied: returns the row (>= 0), -1 when
+ * satisfied, < -1 on error; `path` (cap bytes) receives the constraint's path when named. */
+int64_t bp_tcs_which_is_unsatisfied(bp_tcs* t, char* path, uint64_t cap);
+int bp_tcs_set(bp_tcs* t, const char* path, const uint64_t v[4]);
+int bp_tcs_get(bp_tcs* t, const char* path, uint64_t v[4]);
+uint64_t bp_tcs_num_constraints(const bp_tcs* t);
+uint64_t bp_tcs_num_inputs(const bp_tcs* t);
+uint64_t bp_tcs_num_aux(const bp_tcs* t);
+int bp_tcs_row_path(const bp_tcs* t, uint64_t row, char* path, uint64_t cap);
+
+/* Host recording: borrow the recorded CSR (valid until the next call on `t`). */
+int bp_tcs_host_csr(bp_tcs* t, const uint32_t** lens, uint64_t* n_rows, const uint32_t** cols, const uint64_t** coeffs, uint64_t* nnz,
+                    const uint64_t** inputs, uint64_t* n_inputs, const uint64_t** aux, uint64_t* n_aux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,114 @@
+"""C++ host front-end (csrc/host/*.hpp) on the CPU: it must emit exactly the rows, columns, coefficients and
+witness the oracle's Python restatement of the reference gadgets emits, and reproduce the reference's structural
+known-answers.  No evaluation happens here except by the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from bellpepper_b200 import fixtures
+from oracle import c_api
+from oracle import gadgets_py as G
+from oracle.fields import FIELDS
+from oracle.r1cs_py import TestConstraintSystem
+
+
+def oracle_csr(cs):
+    lens, cols, coeffs, inputs, aux = cs.to_csr()
+    return (np.asarray(lens, np.uint32), np.asarray(cols, np.uint32), c_api.ints_to_limbs(coeffs),
+            c_api.ints_to_limbs(inputs), c_api.ints_to_limbs(aux))
+
+
+def same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and (x == y).all()
+
+
+def test_xorshift_streams_agree():
+    assert fixtures.xorshift_bytes(100) == G.xorshift_bytes(G.SEED_3D, 100)
+
+
+@pytest.mark.parametrize("fid", sorted(FIELDS))
+def test_sha256_block_identical_to_oracle_gadgets(fid):  # sha256.rs:310-336: 25840 (+512)
+    F = FIELDS[fid]
+    block = fixtures.xorshift_bytes(64)
+    cs = TestConstraintSystem(F)
+    bits = []
+    for i in range(512):
+        with cs.namespace(f"input bit {i}") as ns:
+            bits.append(G.Boolean.from_bit(G.AllocatedBit.alloc(ns, bool((block[i // 8] >> (7 - i % 8)) & 1))))
+    out = G.sha256_compression_function(cs, F, bits, G.sha256_iv())
+    with fixtures.Tcs(fid, device=-1, named=True) as t:
+        out32 = t.sha256_block(block)
+        assert t.num_constraints() == cs.num_constraints() == 25840 + 512
+        assert t.num_aux() == len(cs.aux) and t.num_inputs() == 1
+        same(t.host_csr(), oracle_csr(cs))
+        # constraint paths are the reference's (test_cs.rs:363-375)
+        for row in (0, 511, 512, 5000, 26351):
+            assert t.row_path(row) == cs.constraints[row][3]
+    want = b"".join(int(w.value).to_bytes(4, "big") for w in out)
+    assert out32 == want
+
+
+def test_sha256_two_blocks_identical_and_digest():  # sha256.rs:338-363: 44874 (+512); digest vs hashlib
+    fid = 0
+    F = FIELDS[fid]
+    msg = fixtures.xorshift_bytes(64)
+    cs = TestConstraintSystem(F)
+    bits = []
+    for i, byte in enumerate(msg):
+        for j in range(7, -1, -1):
+            with cs.namespace(f"input bit {i} {j}") as ns:
+                bits.append(G.Boolean.from_bit(G.AllocatedBit.alloc(ns, bool((byte >> j) & 1))))
+    G.sha256(cs, F, bits)
+    for named in (True, False):
+        with fixtures.Tcs(fid, device=-1, named=named) as t:
+            digest, before = t.sha256(msg)
+            assert digest == hashlib.sha256(msg).digest() and before == 0
+            assert t.num_constraints() - 512 == 44874
+            same(t.host_csr(), oracle_csr(cs))
+
+
+def test_constant_input_gives_no_constraints():  # sha256.rs:283-308
+    with fixtures.Tcs(0, device=-1, named=True) as t:
+        digest, _ = t.sha256(b"")
+        assert digest == hashlib.sha256(b"").digest()
+        assert t.num_constraints() == 0
+
+
+def test_row_sharding_by_block_partitions_the_rows():
+    fid = 1
+    msg = fixtures.chain_message(4)
+    with fixtures.Tcs(fid, device=-1, named=False) as t:
+        t.sha256(msg)
+        full = t.host_csr()
+    n_full = full[0].size // 3
+    off = np.concatenate([[0], np.cumsum(full[0].astype(np.int64))])
+    got_rows = 0
+    for b0, b1 in ((0, 1), (1, 3), (3, 4)):
+        with fixtures.Tcs(fid, device=-1, named=False) as t:
+            digest, before = t.sha256(msg, b0, b1)
+            lens, cols, coeffs, inputs, aux = t.host_csr()
+        assert digest == hashlib.sha256(msg).digest()
+        assert before == got_rows
+        n = lens.size // 3
+        assert (lens == full[0][3 * before: 3 * (before + n)]).all()
+        k0, k1 = int(off[3 * before]), int(off[3 * (before + n)])
+        assert (cols == full[1][k0:k1]).all() and (coeffs == full[2][k0:k1]).all()
+        assert (aux == full[4]).all() and (inputs == full[3]).all()  # witness is replicated, rows are sharded
+        got_rows += n
+    assert got_rows == n_full
+
+
+def test_front_end_output_satisfies_the_oracle_and_flips():
+    fid = 2
+    with fixtures.Tcs(fid, device=-1, named=True) as t:
+        t.sha256(fixtures.xorshift_bytes(3))
+        lens, cols, coeffs, inputs, aux = t.host_csr()
+        paths = [t.row_path(r) for r in range(t.num_constraints())]
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    assert inst.check(4, False) == -1
+    inst.set(True, 5, 2)  # aux 5 is message bit 5: its own boolean constraint (row 5) is the first to fail
+    bad = inst.check(1, True)
+    assert bad == 5 and paths[bad] == "input bit 0 2/boolean constraint"
