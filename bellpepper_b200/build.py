@@ -38,6 +38,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
                os.path.join(CSRC, "host", "fixtures.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        if os.environ.get("BP_EXPERIMENTAL_VARIANTS") == "1":
+            cmd.insert(1, "-DBP_EXPERIMENTAL_VARIANTS")
         subprocess.run(cmd, check=True, cwd=CSRC)
     mb = os.path.join(CSRC, "microbench.cu")
     if os.path.exists(mb) and (force or _stale(MICROBENCH, srcs)):

@@ -1,4 +1,4 @@
-// libbp_r1cs.so -- C ABI (include/bp_r1cs.h) over the CUDA kernels in kernels.cuh / staged.cuh.
+// libbp_r1cs.so -- C ABI (include/bp_r1cs.h) over the CUDA kernels in kernels.cuh.
 //
 // Host-side responsibilities: device buffer growth, pinned staging for H2D of enforce/alloc batches,
 // ingest conversion launches, result read-back.  No evaluation ever happens on the CPU.
@@ -15,7 +15,6 @@
 #include <string>
 
 #include "kernels.cuh"
-#include "staged.cuh"
 
 namespace {
 
@@ -40,8 +39,14 @@ struct bp_cs {
     std::string err;
 
     uint64_t n_rows = 0, nnz = 0, n_inputs = 0, n_aux = 0, row_base = 0;
+    uint64_t n_gen = 0;  // terms that need a full 256x256 product (drives the kernel-configuration heuristic)
     DevBuf row_ptr, cols, vals, inputs, aux;
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
+    DevBuf fat_rows;           // plan: rows handled by check_fat_rows (+ one u32 counter at the end)
+    uint64_t fat_terms = 96;   // rows with more terms than this go to the warp-per-row kernel
+    int64_t kernels_mask = 3;  // measurement aid: bit 0 = launch check_rows, bit 1 = launch check_fat_rows
+    int64_t variant = -1;      // < 0: the default kernel configuration; >= 0: an experimental variant id (see launch_check)
+    bool plan_valid = false;
     long long* d_result = nullptr;  // [0] first_bad
     unsigned int* d_err = nullptr;
     void* h_pinned_small = nullptr;  // 64 B: [0,32) element, [32,40) first_bad, [40,44) err word, [48,56) tiny row_ptr
@@ -49,10 +54,7 @@ struct bp_cs {
     cudaEvent_t stage_ev[kNumStage] = {nullptr, nullptr};
     int stage_next = 0;
     FieldConsts fc;
-    int64_t opt_kernel = 1;  // 0 = direct, 1 = TMA-staged
     int64_t launches = 0;
-    StagedPlan plan;  // tiling of the staged kernel (rebuilt lazily when rows change)
-    bool plan_valid = false;
 };
 
 namespace {
@@ -123,11 +125,8 @@ template <int F> void pow2_mod_p(int k, uint32_t* out) {
 }
 
 template <int F> void make_consts(FieldConsts& fc) {
-    pow2_mod_p<F>(544, fc.kA);
-    pow2_mod_p<F>(832, fc.kB);
-    uint32_t pl[8];
-    for (int i = 0; i < 8; ++i) pl[i] = PL<F>(i);
-    (void)subn<8>(fc.kC, pl, fc.kA);
+    pow2_mod_p<F>(544, fc.k288m);
+    pow2_mod_p<F>(576, fc.k576);
 }
 
 int grid_for(const bp_cs* h, uint64_t n, int block, int per_sm) {
@@ -146,6 +145,7 @@ CsrView view(const bp_cs* h) {
     m.n_rows = (uint32_t)h->n_rows;
     m.n_inputs = (uint32_t)h->n_inputs;
     m.n_aux = (uint32_t)h->n_aux;
+    m.fat_terms = (uint32_t)h->fat_terms;
     m.row_base = h->row_base;
     return m;
 }
@@ -191,22 +191,41 @@ int read_flags(bp_cs* h, long long* first_bad, unsigned int* err) {
 }
 
 int clear_err(bp_cs* h) {
-    CU(h, cudaMemsetAsync(h->d_err, 0, 4, h->stream));
+    CU(h, cudaMemsetAsync(h->d_err, 0, 8, h->stream));  // err word + the per-call GEN-term counter
     return BP_OK;
 }
 
 int check_err_word(bp_cs* h, const char* what) {
     char* hp = (char*)h->h_pinned_small;
-    CU(h, cudaMemcpyAsync(hp + 40, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(hp + 40, h->d_err, 8, cudaMemcpyDeviceToHost, h->stream));  // [40,44) err, [44,48) GEN counter
     CU(h, cudaStreamSynchronize(h->stream));
     unsigned int e;
     std::memcpy(&e, hp + 40, 4);
     if (e & 2u) return fail(h, BP_E_RANGE, "%s: a field element is not canonical (>= p)", what);
+    if (e & 4u) return fail(h, BP_E_RANGE, "%s: a variable index does not fit 28 bits", what);
     if (e & 1u) return fail(h, BP_E_RANGE, "%s: a column index is out of range", what);
     return BP_OK;
 }
 
-// Launch K1/K2 on the handle's stream.  `out` selects emit mode when any of az/bz/cz is set.
+// (Re)build the fat-row list when rows or the threshold changed.
+int ensure_plan(bp_cs* h) {
+    if (h->plan_valid) return BP_OK;
+    int rc = ensure(h, h->fat_rows, ((size_t)h->n_rows + 1) * 4, 0);
+    if (rc != BP_OK) return rc;
+    uint32_t* cnt = (uint32_t*)h->fat_rows.p + h->n_rows;
+    CU(h, cudaMemsetAsync(cnt, 0, 4, h->stream));
+    if (h->n_rows) {
+        collect_fat_rows<<<grid_for(h, h->n_rows, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (uint32_t)h->n_rows,
+                                                                                 (uint32_t)h->fat_terms, (uint32_t*)h->fat_rows.p, cnt);
+        h->launches++;
+        CU(h, cudaGetLastError());
+    }
+    h->plan_valid = true;
+    return BP_OK;
+}
+
+// Launch K1/K2 on the handle's stream: result init, thread-per-row kernel, warp-per-row kernel for the fat rows.
+// Emit mode when any of az/bz/cz is set.
 int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4* cz) {
     init_result<<<1, 1, 0, h->stream>>>(dev_first_bad, h->d_err);
     h->launches++;
@@ -214,27 +233,45 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
         CU(h, cudaGetLastError());
         return BP_OK;
     }
+    int rc = ensure_plan(h);
+    if (rc != BP_OK) return rc;
     CsrView m = view(h);
     CheckOut o{dev_first_bad, h->d_err, az, bz, cz};
     const bool emit = az || bz || cz;
-    if (h->opt_kernel == 1 && !emit) {
-        int rc = BP_OK;
-        DISPATCH_FIELD(h, rc = staged_launch<F>(h->plan, h->plan_valid, m, o, h->sm_count, h->stream, h->launches));
-        if (rc == 1) return fail(h, BP_E_OOM, "staged kernel: plan allocation failed");
-        if (rc == 0) {
-            CU(h, cudaGetLastError());
-            return BP_OK;
-        }
-        // rc == 2: instance not eligible for the staged kernel (a row larger than a tile) -> direct kernel
-    }
     const int block = 128;
-    const int grid = grid_for(h, h->n_rows, block, 8);
+    const int grid = grid_for(h, h->n_rows, block, 16);
+    const uint32_t* fat = (const uint32_t*)h->fat_rows.p;
+    const uint32_t* n_fat = fat + h->n_rows;
+    const int fat_grid = h->sm_count * 8;
+    // (VT, MBT): feature bits / min blocks per SM of the thread-per-row kernel; (VF, MBF): of the warp-per-row kernel.
+#define BP_LAUNCH(EMITF, VT, MBT, VF, MBF)                                                                                                     \
+    do {                                                                                                                                       \
+        if (h->kernels_mask & 1) DISPATCH_FIELD(h, (check_rows<F, EMITF, VT, MBT><<<grid, block, 0, h->stream>>>(m, o, h->fc)));                \
+        if (h->kernels_mask & 2) DISPATCH_FIELD(h, (check_fat_rows<F, EMITF, VF, MBF><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat))); \
+    } while (0)
     if (emit) {
-        DISPATCH_FIELD(h, (check_direct<F, true><<<grid, block, 0, h->stream>>>(m, o)));
+        BP_LAUNCH(true, 0, 4, 0, 4);
     } else {
-        DISPATCH_FIELD(h, (check_direct<F, false><<<grid, block, 0, h->stream>>>(m, o)));
+        // default configuration by instance statistics: product-heavy instances park az/bz in shared memory
+        const int64_t variant = h->variant >= 0 ? h->variant : (2 * h->n_gen > h->nnz ? -2 : -1);
+        switch (variant) {
+#ifdef BP_EXPERIMENTAL_VARIANTS
+            case 0: BP_LAUNCH(false, 0, 4, 0, 4); break;
+            case 1: BP_LAUNCH(false, kVMagSkip, 4, kVMagSkip, 4); break;
+            case 2: BP_LAUNCH(false, kVMagSkip | kVBitRow, 4, kVMagSkip | kVBitRow, 4); break;
+            case 3: BP_LAUNCH(false, kVMagSkip | kVBitRow | kVPark, 6, kVMagSkip | kVBitRow | kVPark, 6); break;
+            case 4: BP_LAUNCH(false, kVMagSkip | kVPrefetch, 4, kVMagSkip, 4); break;
+            case 5: BP_LAUNCH(false, kVMagSkip | kVPipe, 5, kVMagSkip | kVPipe, 5); break;
+            case 8: BP_LAUNCH(false, kVMagSkip | kVPark, 6, kVMagSkip | kVPark, 6); break;
+            case 10: BP_LAUNCH(false, kVMagSkip | kVBitRow, 6, kVMagSkip | kVBitRow, 6); break;
+            case 14: BP_LAUNCH(false, 0, 6, 0, 6); break;
+#endif
+            case -2: BP_LAUNCH(false, kVMagSkip | kVBitRow | kVPark, 6, kVMagSkip | kVBitRow, 4); break;  // product-heavy instances
+            default: BP_LAUNCH(false, kVMagSkip | kVBitRow, 6, kVMagSkip | kVBitRow, 4); break;          // measured best on gadget circuits
+        }
     }
-    h->launches++;
+#undef BP_LAUNCH
+    h->launches += 2;
     CU(h, cudaGetLastError());
     return BP_OK;
 }
@@ -300,9 +337,8 @@ void bp_cs_free(bp_cs* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->scan_tmp, &h->scratch})
+    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->scan_tmp, &h->scratch, &h->fat_rows})
         if (b->p) cudaFree(b->p);
-    staged_plan_free(h->plan);
     if (h->d_result) cudaFree(h->d_result);
     if (h->h_pinned_small) cudaFreeHost(h->h_pinned_small);
     for (int s = 0; s < kNumStage; ++s) {
@@ -337,14 +373,17 @@ int bp_cs_sync(bp_cs* h) {
 
 int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
     if (!h || !key) return BP_E_ARG;
-    if (!std::strcmp(key, "kernel")) {
-        if (v != 0 && v != 1) return fail(h, BP_E_ARG, "kernel must be 0 (direct) or 1 (staged)");
-        h->opt_kernel = v;
+    if (!std::strcmp(key, "variant")) {
+        h->variant = v;
         return BP_OK;
     }
-    if (!std::strcmp(key, "tile_terms")) {
-        if (v < 64 || v > 4096) return fail(h, BP_E_ARG, "tile_terms out of range");
-        h->plan.tile_terms = (uint32_t)v;
+    if (!std::strcmp(key, "kernels_mask")) {
+        h->kernels_mask = v & 3;
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "fat_terms")) {
+        if (v < 8 || v > (1 << 30)) return fail(h, BP_E_ARG, "fat_terms out of range");
+        h->fat_terms = (uint64_t)v;
         h->plan_valid = false;
         return BP_OK;
     }
@@ -353,11 +392,21 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
 
 int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
     if (!h || !key || !v) return BP_E_ARG;
-    if (!std::strcmp(key, "kernel")) { *v = h->opt_kernel; return BP_OK; }
+    if (!std::strcmp(key, "fat_terms")) { *v = (int64_t)h->fat_terms; return BP_OK; }
     if (!std::strcmp(key, "launches")) { *v = h->launches; return BP_OK; }
+    if (!std::strcmp(key, "gen_terms")) { *v = (int64_t)h->n_gen; return BP_OK; }
     if (!std::strcmp(key, "sm_count")) { *v = h->sm_count; return BP_OK; }
-    if (!std::strcmp(key, "tiles")) { *v = h->plan_valid ? (int64_t)h->plan.n_tiles : -1; return BP_OK; }
-    if (!std::strcmp(key, "last_kernel")) { *v = h->plan.last_used ? 1 : 0; return BP_OK; }
+    if (!std::strcmp(key, "fat_rows")) {  // number of rows the warp-per-row kernel handles (builds the plan if needed)
+        CU(h, cudaSetDevice(h->device));
+        int rc = ensure_plan(h);
+        if (rc != BP_OK) return rc;
+        CU(h, cudaMemcpyAsync(h->h_pinned_small, (uint32_t*)h->fat_rows.p + h->n_rows, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        uint32_t n;
+        std::memcpy(&n, h->h_pinned_small, 4);
+        *v = n;
+        return BP_OK;
+    }
     return fail(h, BP_E_ARG, "unknown option '%s'", key);
 }
 
@@ -402,28 +451,35 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
     if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "set_range [%llu,+%llu) exceeds %llu", (unsigned long long)first,
                                                    (unsigned long long)n, (unsigned long long)cnt);
     if (!n) return BP_OK;
-    // Validate on the host BEFORE touching device state so a rejected value leaves the witness intact.
-    {
+    DevBuf& b = is_aux ? h->aux : h->inputs;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, vals);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    const bool host_readable = !(e == cudaSuccess && at.type == cudaMemoryTypeDevice);
+    if (host_readable && n <= 4096) {
+        // small updates (set / flip-and-recheck): validate on the host first, so a rejected value leaves the witness intact
         uint32_t pl[8];
         DISPATCH_FIELD(h, { for (int i = 0; i < 8; ++i) pl[i] = PL<F>(i); });
-        cudaPointerAttributes at;
-        cudaError_t e = cudaPointerGetAttributes(&at, vals);
-        if (e != cudaSuccess) (void)cudaGetLastError();
-        const bool host_readable = !(e == cudaSuccess && at.type == cudaMemoryTypeDevice);
-        if (host_readable) {
-            for (uint64_t i = 0; i < n; ++i) {
-                const uint32_t* x = (const uint32_t*)(vals + 4 * i);
-                int lt = 0;
-                for (int j = 7; j >= 0; --j) {
-                    if (x[j] < pl[j]) { lt = 1; break; }
-                    if (x[j] > pl[j]) break;
-                }
-                if (!lt) return fail(h, BP_E_RANGE, "bp_cs_set_range: element %llu is not canonical (>= p)", (unsigned long long)i);
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t* x = (const uint32_t*)(vals + 4 * i);
+            int lt = 0;
+            for (int j = 7; j >= 0; --j) {
+                if (x[j] < pl[j]) { lt = 1; break; }
+                if (x[j] > pl[j]) break;
             }
+            if (!lt) return fail(h, BP_E_RANGE, "bp_cs_set_range: element %llu is not canonical (>= p)", (unsigned long long)i);
         }
+        return upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32);
     }
-    DevBuf& b = is_aux ? h->aux : h->inputs;
-    return upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32);
+    // bulk witness refresh: copy at link speed, validate on the device (on BP_E_RANGE the range's contents are unspecified)
+    int rc = clear_err(h);
+    if (rc != BP_OK) return rc;
+    if ((rc = upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32)) != BP_OK) return rc;
+    DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint4*)((char*)b.p + first * 32), n,
+                                                                                          h->d_err)));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return check_err_word(h, "bp_cs_set_range");
 }
 
 int bp_cs_set(bp_cs* h, int is_aux, uint64_t idx, const uint64_t v[4]) { return bp_cs_set_range(h, is_aux, idx, 1, v); }
@@ -476,11 +532,21 @@ int bp_cs_enforce(bp_cs* h, uint64_t n_rows, const uint32_t* lens, const uint32_
         if ((rc = upload(h, (uint32_t*)h->cols.p + h->nnz, cols, (size_t)add * 4)) != BP_OK) return rc;
         if ((rc = upload(h, (char*)h->vals.p + h->nnz * 32, coeffs, (size_t)add * 32)) != BP_OK) return rc;
         if ((rc = clear_err(h)) != BP_OK) return rc;
-        DISPATCH_FIELD(h, (to_internal<F><<<grid_for(h, add, 128, 16), 128, 0, h->stream>>>(
-                              (uint4*)h->vals.p, rp, (uint32_t)lc_old, (uint32_t)lc_add, (uint32_t)h->nnz, (uint32_t)add, h->fc, h->d_err)));
-        h->launches++;
+        // scratch was used for the lens; reuse it for the per-LC kind bytes once the scan has consumed them
+        uint8_t* kind = (uint8_t*)h->scratch.p;
+        DISPATCH_FIELD(h, (classify_lcs<F><<<grid_for(h, lc_add, 128, 16), 128, 0, h->stream>>>((const uint4*)h->vals.p, rp, (uint32_t)lc_old,
+                                                                                          (uint32_t)lc_add, kind)));
+        DISPATCH_FIELD(h, (convert_terms<F><<<grid_for(h, add, 128, 16), 128, 0, h->stream>>>(
+                              (uint4*)h->vals.p, (uint32_t*)h->cols.p, rp, kind, (uint32_t)lc_old, (uint32_t)lc_add, (uint32_t)h->nnz,
+                              (uint32_t)add, h->fc, h->d_err)));
+        h->launches += 2;
         CU(h, cudaGetLastError());
         if ((rc = check_err_word(h, "bp_cs_enforce")) != BP_OK) return rc;  // rows not committed
+        {
+            unsigned int gen_chunk;
+            std::memcpy(&gen_chunk, (char*)h->h_pinned_small + 44, 4);
+            h->n_gen += gen_chunk;
+        }
     } else {
         CU(h, cudaGetLastError());
     }
@@ -543,8 +609,8 @@ int bp_cs_eval(bp_cs* h, uint64_t* az, uint64_t* bz, uint64_t* cz) {
 int bp_cs_eval_lc(bp_cs* h, const uint32_t* cols, const uint64_t* coeffs, uint32_t n, uint64_t out[4]) {
     if (!h || !out || (n && (!cols || !coeffs))) return BP_E_ARG;
     CU(h, cudaSetDevice(h->device));
-    // scratch: [vals 32n][cols 4n][row_ptr 8][out 32]
-    const size_t off_cols = (size_t)n * 32, off_rp = off_cols + (((size_t)n * 4 + 15) & ~size_t(15)), off_out = off_rp + 16;
+    // scratch: [coeffs 32n][cols 4n (16-aligned)][out 32]
+    const size_t off_cols = (size_t)n * 32, off_out = off_cols + (((size_t)n * 4 + 15) & ~size_t(15));
     int rc = ensure(h, h->scratch, off_out + 32, 0);
     if (rc != BP_OK) return rc;
     char* s = (char*)h->scratch.p;
@@ -552,15 +618,8 @@ int bp_cs_eval_lc(bp_cs* h, const uint32_t* cols, const uint64_t* coeffs, uint32
     if (n) {
         if ((rc = upload(h, s, coeffs, (size_t)n * 32)) != BP_OK) return rc;
         if ((rc = upload(h, s + off_cols, cols, (size_t)n * 4)) != BP_OK) return rc;
-        const uint32_t rp[2] = {0, n};
-        std::memcpy((char*)h->h_pinned_small + 48, rp, 8);
-        CU(h, cudaMemcpyAsync(s + off_rp, (char*)h->h_pinned_small + 48, 8, cudaMemcpyHostToDevice, h->stream));
-        // one LC of type A (lc index 0)
-        DISPATCH_FIELD(h, (to_internal<F><<<grid_for(h, n, 128, 16), 128, 0, h->stream>>>((uint4*)s, (const uint32_t*)(s + off_rp), 0u, 1u,
-                                                                                         0u, n, h->fc, h->d_err)));
-        h->launches++;
     }
-    DISPATCH_FIELD(h, (eval_lc_kernel<F><<<1, 32, 0, h->stream>>>((const uint32_t*)(s + off_cols), (const uint4*)s, n, view(h),
+    DISPATCH_FIELD(h, (eval_lc_kernel<F><<<1, 32, 0, h->stream>>>((const uint32_t*)(s + off_cols), (const uint4*)s, n, view(h), h->fc,
                                                                  (uint4*)(s + off_out), h->d_err)));
     h->launches++;
     CU(h, cudaGetLastError());
@@ -610,6 +669,7 @@ int bp_cs_synth_rows(bp_cs* h, uint64_t seed, uint32_t t, uint64_t n_vars, uint6
     CU(h, cudaGetLastError());
     h->n_rows += n_rows;
     h->nnz += add;
+    h->n_gen += add;  // random coefficients: every term is a full product
     h->plan_valid = false;
     return BP_OK;
 }

@@ -42,6 +42,7 @@ WORKLOADS = {
     "synthetic_2p27_t32_pallas": ("synthetic", 1, {"log_rows": 27, "t": 32}),         # configs[4] (8 GPUs)
     "synthetic_2p20_t6_bls12_381": ("synthetic", 0, {"log_rows": 20, "t": 6}),        # small, for quick checks
     "sha256_chain_64_pallas": ("sha256", 1, {"blocks": 64}),
+    "sha256_chain_512_pallas": ("sha256", 1, {"blocks": 512}),
 }
 
 
@@ -180,7 +181,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BP_BENCH_WORKLOAD", "default"))
     ap.add_argument("--cpu-sample-log2", type=int, default=22)
-    ap.add_argument("--kernel", type=int, default=None, help="force kernel variant (0 direct, 1 staged)")
+    ap.add_argument("--fat-terms", type=int, default=None, help="rows with more terms than this use the warp-per-row kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -238,8 +239,8 @@ def main():
     h, info = build_workload(L, ffi, workload, rank, world, local_rank)
     stream = torch.cuda.Stream(device=local_rank)
     assert L.bp_cs_set_stream(h, ctypes.c_void_p(stream.cuda_stream)) == 0
-    if a.kernel is not None:
-        assert L.bp_cs_set_option(h, b"kernel", a.kernel) == 0
+    if a.fat_terms is not None:
+        assert L.bp_cs_set_option(h, b"fat_terms", a.fat_terms) == 0
 
     result = torch.zeros(1, dtype=torch.int64, device=f"cuda:{local_rank}")
     n_rows_total = info.get("rows_total", info["rows"])
@@ -315,8 +316,8 @@ def main():
         peak, peak_kind = measured_peak_gbs()
         alg_bytes = info["nnz"] * 36 + info["rows"] * 12 + n_vars * 32  # this rank's shard + the whole witness
         achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-        used = ctypes.c_int64()
-        L.bp_cs_get_option(h, b"last_kernel", ctypes.byref(used))
+        fat = ctypes.c_int64()
+        L.bp_cs_get_option(h, b"fat_rows", ctypes.byref(fat))
         out = dict(base)
         out.update({
             "value": n_rows_total / (ms_step * 1e-3),
@@ -327,7 +328,8 @@ def main():
             "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": f"of {peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "staged" if used.value else "direct"},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernels": "check_rows (thread/row) + check_fat_rows (warp/row)", "fat_rows": fat.value},
             "clocks": clocks,
             "first_unsatisfied_row": None if first_bad == 0x7FFFFFFFFFFFFFFF else first_bad,
             "instance": {k: info[k] for k in ("rows", "nnz", "n_inputs", "n_aux", "ingest_s")},

@@ -120,7 +120,8 @@ int bp_cs_set_stream(bp_cs* cs, void* cuda_stream);
 int bp_cs_set_row_base(bp_cs* cs, uint64_t row_base);
 /* Block until all enqueued work of this handle is complete. */
 int bp_cs_sync(bp_cs* cs);
-/* Tuning / introspection knobs: "kernel" (0 = direct CSR, 1 = TMA-staged), "launches" (read-only). */
+/* Tuning / introspection knobs: "fat_terms" (rows with more terms use the warp-per-row kernel; default 96),
+ * read-only: "launches" (kernels launched so far), "fat_rows", "sm_count". */
 int bp_cs_set_option(bp_cs* cs, const char* key, int64_t value);
 int bp_cs_get_option(bp_cs* cs, const char* key, int64_t* value);
 

@@ -22,3 +22,24 @@ extern "C" int field_host_op(int field, int op, const uint32_t* a, const uint32_
     }
     return -1;
 }
+
+// ---- plain-arithmetic primitives ----
+template <int F> static void run2(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    switch (op) {
+        case 10: bp::neg_mod<F>(out, a); break;                                  // a[8] -> out[8]
+        case 11: bp::acc_add8<9>(out, a); break;                                 // out[9] += a[8]
+        case 12: bp::acc_add8<17>(out, a); break;                                // out[17] += a[8]
+        case 13: bp::acc_mad_small<9>(out, a, b[0]); break;                      // out[9] += b0 * a[8]
+        case 14: bp::acc_mad_small<17>(out, a, b[0]); break;
+        case 15: bp::reduce_8p<F>(out, a); break;                                // a[9] -> out[8]
+        case 16: { uint32_t s; out[0] = bp::classify_coeff<F>(a, &s); out[1] = s; } break;
+    }
+}
+extern "C" int field_host_op2(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    switch (field) {
+        case 0: run2<0>(op, a, b, out); return 0;
+        case 1: run2<1>(op, a, b, out); return 0;
+        case 2: run2<2>(op, a, b, out); return 0;
+    }
+    return -1;
+}

@@ -94,3 +94,46 @@ def test_mont_mul_predicates(fh, fid):
             assert fh(fid, 2, a, b, 8) == (a * b * inv256) % p
     assert fh(fid, 5, 0, 0, 1) == 1 and fh(fid, 5, p, 0, 1) == 1 and fh(fid, 5, 1, 0, 1) == 0 and fh(fid, 5, p - 1, 0, 1) == 0
     assert fh(fid, 6, p - 1, 0, 1) == 1 and fh(fid, 6, p, 0, 1) == 0 and fh(fid, 6, (1 << 256) - 1, 0, 1) == 0
+
+
+@pytest.fixture(scope="module")
+def fh2(fh):
+    so = os.path.join(HERE, "host", "libfield_host.so")
+    L = ctypes.CDLL(so)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    L.field_host_op2.argtypes = [ctypes.c_int, ctypes.c_int, u32p, u32p, u32p]
+
+    def call(field, op, a, b, nout, a_limbs=8, out_init=0):
+        A = np.frombuffer(int(a).to_bytes(4 * a_limbs, "little"), np.uint32).copy()
+        B = np.frombuffer(int(b).to_bytes(32, "little"), np.uint32).copy()
+        O = np.frombuffer(int(out_init).to_bytes(4 * nout, "little"), np.uint32).copy()
+        assert L.field_host_op2(field, op, A.ctypes.data_as(u32p), B.ctypes.data_as(u32p), O.ctypes.data_as(u32p)) == 0
+        return int.from_bytes(O.tobytes(), "little")
+
+    return call
+
+
+@pytest.mark.parametrize("fid", sorted(FIELDS))
+def test_plain_primitives(fh2, fid):
+    p = FIELDS[fid].p
+    rng = random.Random(300 + fid)
+    vals = edge(p) + [rng.randrange(p) for _ in range(50)]
+    for x in vals:
+        assert fh2(fid, 10, x, 0, 8) == p - x
+        for acc in (0, 1, p - 1, 7 * p - 3, (1 << 256) - 1):
+            assert fh2(fid, 11, x, 0, 9, out_init=acc) == acc + x
+            big = acc + rng.randrange(1 << 530)
+            assert fh2(fid, 12, x, 0, 17, out_init=big) == big + x
+            for s in (0, 1, 3, 7, 0xFFFFFFFF, rng.randrange(1 << 32)):
+                if acc + s * x < (1 << 288):
+                    assert fh2(fid, 13, x, s, 9, out_init=acc) == acc + s * x
+                assert fh2(fid, 14, x, s, 17, out_init=big) == big + s * x
+    for v in [0, 1, p - 1, p, p + 1, 2 * p, 4 * p - 1, 4 * p, 7 * p + 5, 8 * p - 1] + [rng.randrange(8 * p) for _ in range(300)]:
+        assert fh2(fid, 15, v, 0, 8, a_limbs=9) == v % p
+    K = {"gen": 0, "p1": 1, "m1": 2, "p2": 3, "m2": 4, "ps": 5, "ms": 6, "zero": 7}
+    cases = [(0, "zero", 0), (1, "p1", 0), (p - 1, "m1", 0), (2, "p2", 0), (p - 2, "m2", 0), (3, "ps", 3), (p - 3, "ms", 3),
+             (0xFFFFFFFF, "ps", 0xFFFFFFFF), (p - 0xFFFFFFFF, "ms", 0xFFFFFFFF), (1 << 32, "gen", 0), (p - (1 << 32), "gen", 0),
+             (p >> 1, "gen", 0), (1 << 200, "gen", 0)]
+    for v, cls, s in cases:
+        r = fh2(fid, 16, v, 0, 2)
+        assert (r & 0xFFFFFFFF, r >> 32) == (K[cls], s), (hex(v), cls)

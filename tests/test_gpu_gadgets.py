@@ -1,0 +1,125 @@
+"""Gadget circuits (BASELINE configs 1-3 shapes) through the C++ front-end into the B200 engine vs the oracle."""
+import ctypes
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from bellpepper_b200 import ffi, fixtures
+from oracle import c_api
+from oracle.fields import FIELDS
+
+pytestmark = pytest.mark.gpu
+
+
+def device_eval(t, n_rows):
+    L = ffi.load()
+    h = ffi.vp(t.handle)
+    az, bz, cz = (np.zeros((n_rows, 4), np.uint64) for _ in range(3))
+    assert L.bp_cs_eval(h, az.ctypes.data, bz.ctypes.data, cz.ctypes.data) == 0, L.bp_cs_last_error(h)
+    return az, bz, cz
+
+
+@pytest.mark.parametrize("fid", sorted(FIELDS))
+def test_sha256_two_blocks_bit_exact(fid):
+    """configs[0]-shaped: sha256 gadget, values of every LC of every row equal the oracle's, satisfied, digest right."""
+    msg = fixtures.xorshift_bytes(64)
+    with fixtures.Tcs(fid, device=-1, named=False) as rec:
+        rec.sha256(msg)
+        lens, cols, coeffs, inputs, aux = rec.host_csr()
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    bad, az_r, bz_r, cz_r = inst.eval(4)
+    assert bad == -1
+    with fixtures.Tcs(fid, device=0, named=True) as t:
+        digest, _ = t.sha256(msg)
+        assert digest == hashlib.sha256(msg).digest()
+        n = t.num_constraints()
+        assert n == 44874 + 512 == lens.size // 3
+        assert t.is_satisfied()
+        az, bz, cz = device_eval(t, n)
+        assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
+        L = ffi.load()
+        h = ffi.vp(t.handle)
+        fat = ctypes.c_int64()
+        assert L.bp_cs_get_option(h, b"fat_rows", ctypes.byref(fat)) == 0 and fat.value > 20  # MultiEq rows took the warp path
+        # flip-and-recheck by path (uint32.rs:627-633 idiom); first failure must be the reference's
+        rng = random.Random(fid)
+        paths = ["block 0/w extension 16/computation of w[i]/result bit 0/boolean", "input bit 3 5/boolean",
+                 "block 1/compression round 63/maj/maj 31/maj", "block 1/new h7/result bit 32/boolean"]
+        for path in paths:
+            old = t.get(path)
+            assert old in (0, 1)
+            t.set(path, 1 - old)
+            # oracle: same flip on the flat instance
+            idx = None
+            got = t.which_is_unsatisfied()
+            assert got is not None
+            row = t.first_unsatisfied_row()
+            # find aux index of the path by probing the device value back (names live in the C++ mirror)
+            t.set(path, old)
+            assert t.is_satisfied()
+            assert t.row_path(row) == got
+        # a non-boolean value in a result bit trips its own boolean constraint first or an earlier user of the bit
+        t.set("block 0/w extension 16/computation of w[i]/result bit 5/boolean", rng.randrange(2, FIELDS[fid].p))
+        assert t.which_is_unsatisfied() == "block 0/w extension 16/computation of w[i]/result bit 5/boolean constraint"
+
+
+def test_flip_matches_oracle_first_failure():
+    fid = 1
+    msg = fixtures.xorshift_bytes(130)
+    with fixtures.Tcs(fid, device=-1, named=False) as rec:
+        rec.sha256(msg)
+        lens, cols, coeffs, inputs, aux = rec.host_csr()
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    L = ffi.load()
+    rng = random.Random(11)
+    with fixtures.Tcs(fid, device=0, named=False) as t:
+        t.sha256(msg)
+        h = ffi.vp(t.handle)
+        assert t.is_satisfied()
+        for _ in range(12):
+            idx = rng.randrange(aux.shape[0])
+            old = int(aux[idx][0])
+            new = 1 - old if rng.random() < 0.7 else rng.randrange(FIELDS[fid].p)
+            v = c_api.ints_to_limbs([new])
+            assert L.bp_cs_set(h, 1, idx, v.ctypes.data) == 0
+            inst.set(True, idx, new)
+            assert t.first_unsatisfied_row() == inst.check(4, False)
+            v = c_api.ints_to_limbs([old])
+            assert L.bp_cs_set(h, 1, idx, v.ctypes.data) == 0
+            inst.set(True, idx, old)
+        assert t.is_satisfied()
+
+
+def test_sha256_chain_64_blocks_pallas_satisfied_and_sharded():
+    """configs[1]-shaped (scaled down): 64 chained blocks; whole system satisfied; two row shards agree with the whole."""
+    fid, blocks = 1, 64
+    msg = fixtures.chain_message(blocks)
+    L = ffi.load()
+    with fixtures.Tcs(fid, device=0, named=False) as t:
+        digest, before = t.sha256(msg)
+        assert digest == hashlib.sha256(msg).digest() and before == 0
+        n_total = t.num_constraints()
+        assert t.is_satisfied()
+        h = ffi.vp(t.handle)
+        # corrupt one late witness bit: the failing row is reported with its global index by the shard that owns it
+        victim = t.num_aux() - 40000
+        old = np.zeros(4, np.uint64)
+        assert L.bp_cs_get(h, 1, victim, old.ctypes.data) == 0
+        new = c_api.ints_to_limbs([1 - int(old[0])])
+        assert L.bp_cs_set(h, 1, victim, new.ctypes.data) == 0
+        want = t.first_unsatisfied_row()
+        assert want > 0
+    got = []
+    for b0, b1 in ((0, 40), (40, 64)):
+        with fixtures.Tcs(fid, device=0, named=False) as s:
+            _, before = s.sha256(msg, b0, b1)
+            h = ffi.vp(s.handle)
+            assert L.bp_cs_set_row_base(h, before) == 0
+            assert s.is_satisfied()
+            assert L.bp_cs_set(h, 1, victim, new.ctypes.data) == 0
+            row = ctypes.c_int64()
+            assert L.bp_cs_first_unsatisfied(h, ctypes.byref(row)) == 0
+            got.append(row.value + before if row.value >= 0 else None)
+    assert min(g for g in got if g is not None) == want

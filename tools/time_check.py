@@ -17,7 +17,7 @@ ap.add_argument("--log-rows", type=int, default=22)
 ap.add_argument("--t", type=int, default=6)
 ap.add_argument("--log-vars", type=int, default=None)
 ap.add_argument("--iters", type=int, default=5)
-ap.add_argument("--kernels", default="0,1")
+ap.add_argument("--kernels", default="96", help="comma list of fat_terms values")
 ap.add_argument("--opts", default="")
 a = ap.parse_args()
 
@@ -45,7 +45,7 @@ for kv in filter(None, a.opts.split(",")):
     k, v = kv.split("=")
     assert L.bp_cs_set_option(h, k.encode(), int(v)) == 0, L.bp_cs_last_error(h)
 for kern in [int(k) for k in a.kernels.split(",")]:
-    assert L.bp_cs_set_option(h, b"kernel", kern) == 0
+    assert L.bp_cs_set_option(h, b"fat_terms", kern) == 0
     for _ in range(3):
         assert L.bp_cs_check_async(h, ctypes.c_void_p(out.data_ptr())) == 0, L.bp_cs_last_error(h)
     torch.cuda.synchronize()
@@ -57,8 +57,8 @@ for kern in [int(k) for k in a.kernels.split(",")]:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     used = ctypes.c_int64()
-    L.bp_cs_get_option(h, b"last_kernel", ctypes.byref(used))
-    print(json.dumps({"kernel_req": kern, "staged_used": used.value, "field": a.field, "rows": rows, "nnz": nnz, "t": a.t, "n_vars": n_in + n_aux,
+    L.bp_cs_get_option(h, b"fat_rows", ctypes.byref(used))
+    print(json.dumps({"fat_terms": kern, "fat_rows": used.value, "field": a.field, "rows": rows, "nnz": nnz, "t": a.t, "n_vars": n_in + n_aux,
                       "ms": round(ms, 4), "constraints_per_s": rows / ms * 1e3, "terms_per_s": nnz / ms * 1e3,
                       "alg_GBps": alg_bytes / ms / 1e6, "first_bad": int(out.item()), "gen_s": round(gen_s, 2)}), flush=True)
 L.bp_cs_free(h)
