@@ -1,0 +1,46 @@
+//! `extern "C"` twin of include/bp_r1cs.h (keep in sync with BP_ABI_VERSION = 1).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct bp_cs {
+    _private: [u8; 0],
+}
+
+pub const BP_OK: c_int = 0;
+pub const BP_E_CUDA: c_int = -1;
+pub const BP_E_OOM: c_int = -2;
+pub const BP_E_RANGE: c_int = -3;
+pub const BP_E_STATE: c_int = -4;
+pub const BP_E_ARG: c_int = -5;
+
+pub const BP_FIELD_BLS12_381_FR: c_int = 0;
+pub const BP_FIELD_PALLAS_FR: c_int = 1;
+pub const BP_FIELD_VESTA_FR: c_int = 2;
+pub const BP_COL_AUX: u32 = 0x8000_0000;
+
+extern "C" {
+    pub fn bp_abi_version() -> c_int;
+    pub fn bp_cs_new(field: c_int, device: c_int, reserve_rows: u64, reserve_nnz: u64, reserve_vars: u64, out: *mut *mut bp_cs) -> c_int;
+    pub fn bp_cs_free(cs: *mut bp_cs);
+    pub fn bp_cs_last_error(cs: *const bp_cs) -> *const c_char;
+    pub fn bp_cs_alloc(cs: *mut bp_cs, is_aux: c_int, vals_le: *const u64, n: u64, first_index: *mut u64) -> c_int;
+    pub fn bp_cs_set(cs: *mut bp_cs, is_aux: c_int, idx: u64, v: *const u64) -> c_int;
+    pub fn bp_cs_get(cs: *mut bp_cs, is_aux: c_int, idx: u64, v: *mut u64) -> c_int;
+    pub fn bp_cs_set_range(cs: *mut bp_cs, is_aux: c_int, first: u64, n: u64, vals_le: *const u64) -> c_int;
+    pub fn bp_cs_witness(cs: *mut bp_cs, is_aux: c_int, first: u64, n: u64, out_le: *mut u64) -> c_int;
+    pub fn bp_cs_enforce(cs: *mut bp_cs, n_rows: u64, lens: *const u32, cols: *const u32, coeffs_le: *const u64) -> c_int;
+    pub fn bp_cs_counts(cs: *mut bp_cs, n_inputs: *mut u64, n_aux: *mut u64, n_rows: *mut u64, nnz: *mut u64) -> c_int;
+    pub fn bp_cs_first_unsatisfied(cs: *mut bp_cs, row: *mut i64) -> c_int;
+    pub fn bp_cs_check_async(cs: *mut bp_cs, dev_result: *mut i64) -> c_int;
+    pub fn bp_cs_eval(cs: *mut bp_cs, az: *mut u64, bz: *mut u64, cz: *mut u64) -> c_int;
+    pub fn bp_cs_eval_async(cs: *mut bp_cs, dev_az: *mut u64, dev_bz: *mut u64, dev_cz: *mut u64) -> c_int;
+    pub fn bp_cs_eval_lc(cs: *mut bp_cs, cols: *const u32, coeffs_le: *const u64, n_terms: u32, out: *mut u64) -> c_int;
+    pub fn bp_cs_set_stream(cs: *mut bp_cs, cuda_stream: *mut c_void) -> c_int;
+    pub fn bp_cs_set_row_base(cs: *mut bp_cs, row_base: u64) -> c_int;
+    pub fn bp_cs_sync(cs: *mut bp_cs) -> c_int;
+    pub fn bp_cs_set_option(cs: *mut bp_cs, key: *const c_char, value: i64) -> c_int;
+    pub fn bp_cs_get_option(cs: *mut bp_cs, key: *const c_char, value: *mut i64) -> c_int;
+    pub fn bp_cs_synth_rows(cs: *mut bp_cs, seed: u64, t: u32, n_vars: u64, n_inputs: u64, row0: u64, n_rows: u64) -> c_int;
+    pub fn bp_cs_synth_witness(cs: *mut bp_cs, seed: u64, n_vars: u64, n_inputs: u64) -> c_int;
+}

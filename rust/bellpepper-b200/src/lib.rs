@@ -1,0 +1,294 @@
+//! `B200ConstraintSystem<Scalar>`: a drop-in for `bellpepper_core::test_cs::TestConstraintSystem` whose witness and
+//! constraint matrices live in GPU memory and whose `which_is_unsatisfied` / `is_satisfied` run as CUDA kernels.
+//!
+//! Names, namespaces, closures and `LinearCombination` construction stay in Rust exactly as in the reference
+//! (crates/bellpepper-core/src/util_cs/test_cs.rs:377-447); only flat data crosses the C ABI:
+//!   * `alloc`/`alloc_input`  -> value pushed to a pending buffer, flushed with `bp_cs_alloc`
+//!   * `enforce`              -> the three LCs flattened (`iter_inputs` then `iter_aux`, lc.rs:162-170) into
+//!                               (tagged u32 column, 32-byte little-endian `to_repr()`) and flushed with `bp_cs_enforce`
+//!   * `which_is_unsatisfied` -> `bp_cs_first_unsatisfied`, row mapped back to its path
+//!
+//! NOT COMPILED in this repository (no Rust toolchain in the build image); kept in sync with include/bp_r1cs.h.
+pub mod ffi;
+
+use std::collections::HashMap;
+use std::ffi::CStr;
+use std::marker::PhantomData;
+
+use bellpepper_core::{ConstraintSystem, Index, LinearCombination, SynthesisError, Variable};
+use ff::PrimeField;
+
+/// Which of the three supported scalar fields `Scalar` is (checked against `Scalar::MODULUS` at construction).
+pub trait B200Field: PrimeField {
+    const FIELD_ID: i32;
+}
+
+#[derive(Debug)]
+enum NamedObject {
+    Constraint(usize),
+    Var(Variable),
+    Namespace,
+}
+
+pub struct B200ConstraintSystem<Scalar: B200Field> {
+    h: *mut ffi::bp_cs,
+    named_objects: HashMap<String, NamedObject>,
+    current_namespace: Vec<String>,
+    constraint_paths: Vec<String>,
+    input_names: Vec<String>,
+    aux_names: Vec<String>,
+    // pending (not yet flushed) data
+    pend_vals: [Vec<u64>; 2],
+    count: [u64; 2],
+    lens: Vec<u32>,
+    cols: Vec<u32>,
+    coeffs: Vec<u64>,
+    _s: PhantomData<Scalar>,
+}
+
+// The handle is thread-compatible (no TLS, every call selects its device): `ConstraintSystem: Send` holds.
+unsafe impl<Scalar: B200Field> Send for B200ConstraintSystem<Scalar> {}
+
+fn repr_to_limbs<S: PrimeField>(s: &S, out: &mut Vec<u64>) {
+    let repr = s.to_repr(); // canonical little-endian 32 bytes (test_cs.rs:108-111 reverses it for big-endian)
+    for chunk in repr.as_ref().chunks_exact(8) {
+        out.push(u64::from_le_bytes(chunk.try_into().unwrap()));
+    }
+}
+
+fn compute_path(ns: &[String], this: &str) -> String {
+    assert!(!this.chars().any(|a| a == '/'), "'/' is not allowed in names");
+    if ns.is_empty() {
+        return this.to_string();
+    }
+    format!("{}/{}", ns.join("/"), this)
+}
+
+impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
+    pub fn new_on(device: i32) -> Self {
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { ffi::bp_cs_new(Scalar::FIELD_ID, device, 0, 0, 0, &mut h) };
+        assert_eq!(rc, ffi::BP_OK, "bp_cs_new failed ({rc}): no CUDA device? there is no CPU fallback");
+        let mut named_objects = HashMap::new();
+        named_objects.insert("ONE".into(), NamedObject::Var(Self::one()));
+        Self {
+            h,
+            named_objects,
+            current_namespace: vec![],
+            constraint_paths: vec![],
+            input_names: vec!["ONE".into()],
+            aux_names: vec![],
+            pend_vals: [vec![], vec![]],
+            count: [1, 0],
+            lens: vec![],
+            cols: vec![],
+            coeffs: vec![],
+            _s: PhantomData,
+        }
+    }
+
+    fn check(&self, rc: i32) {
+        if rc != ffi::BP_OK {
+            let msg = unsafe { CStr::from_ptr(ffi::bp_cs_last_error(self.h)) }.to_string_lossy().into_owned();
+            panic!("bp_r1cs error {rc}: {msg}"); // BP_E_RANGE at check time == the reference's slice-index panic
+        }
+    }
+
+    pub fn flush(&mut self) {
+        for k in 0..2 {
+            if !self.pend_vals[k].is_empty() {
+                let n = (self.pend_vals[k].len() / 4) as u64;
+                let mut first = 0u64;
+                let rc = unsafe { ffi::bp_cs_alloc(self.h, k as i32, self.pend_vals[k].as_ptr(), n, &mut first) };
+                self.check(rc);
+                self.pend_vals[k].clear();
+            }
+        }
+        if !self.lens.is_empty() {
+            let rc = unsafe {
+                ffi::bp_cs_enforce(self.h, (self.lens.len() / 3) as u64, self.lens.as_ptr(), self.cols.as_ptr(), self.coeffs.as_ptr())
+            };
+            self.check(rc);
+            self.lens.clear();
+            self.cols.clear();
+            self.coeffs.clear();
+        }
+    }
+
+    fn push_lc(&mut self, lc: &LinearCombination<Scalar>) {
+        let mut n = 0u32;
+        for (i, c) in lc.iter_inputs() {
+            self.cols.push(*i as u32);
+            repr_to_limbs(c, &mut self.coeffs);
+            n += 1;
+        }
+        for (i, c) in lc.iter_aux() {
+            self.cols.push(*i as u32 | ffi::BP_COL_AUX);
+            repr_to_limbs(c, &mut self.coeffs);
+            n += 1;
+        }
+        self.lens.push(n);
+    }
+
+    fn set_named_obj(&mut self, path: String, to: NamedObject) {
+        assert!(!self.named_objects.contains_key(&path), "tried to create object at existing path: {}", path);
+        self.named_objects.insert(path, to);
+    }
+
+    /// test_cs.rs:239-253
+    pub fn which_is_unsatisfied(&mut self) -> Option<&str> {
+        self.flush();
+        let mut row = 0i64;
+        let rc = unsafe { ffi::bp_cs_first_unsatisfied(self.h, &mut row) };
+        self.check(rc);
+        if row < 0 { None } else { Some(&self.constraint_paths[row as usize]) }
+    }
+
+    /// test_cs.rs:255-264
+    pub fn is_satisfied(&mut self) -> bool {
+        match self.which_is_unsatisfied() {
+            Some(b) => {
+                println!("fail: {:?}", b);
+                false
+            }
+            None => true,
+        }
+    }
+
+    pub fn num_constraints(&self) -> usize { self.constraint_paths.len() }
+    pub fn num_inputs(&self) -> usize { self.input_names.len() }
+
+    fn var_at(&self, path: &str) -> Variable {
+        match self.named_objects.get(path) {
+            Some(NamedObject::Var(v)) => *v,
+            Some(e) => panic!("tried to access path `{}`, but `{:?}` exists there (not a variable)", path, e),
+            _ => panic!("no variable exists at path: {}", path),
+        }
+    }
+
+    /// test_cs.rs:270-282
+    pub fn set(&mut self, path: &str, to: Scalar) {
+        let (is_aux, idx) = match self.var_at(path).get_unchecked() {
+            Index::Input(i) => (0, i),
+            Index::Aux(i) => (1, i),
+        };
+        self.flush();
+        let mut v = Vec::with_capacity(4);
+        repr_to_limbs(&to, &mut v);
+        let rc = unsafe { ffi::bp_cs_set(self.h, is_aux, idx as u64, v.as_ptr()) };
+        self.check(rc);
+    }
+
+    /// test_cs.rs:311-323
+    pub fn get(&mut self, path: &str) -> Scalar {
+        let (is_aux, idx) = match self.var_at(path).get_unchecked() {
+            Index::Input(i) => (0, i),
+            Index::Aux(i) => (1, i),
+        };
+        self.flush();
+        let mut v = [0u64; 4];
+        let rc = unsafe { ffi::bp_cs_get(self.h, is_aux, idx as u64, v.as_mut_ptr()) };
+        self.check(rc);
+        let mut repr = Scalar::Repr::default();
+        for (dst, limb) in repr.as_mut().chunks_exact_mut(8).zip(v.iter()) {
+            dst.copy_from_slice(&limb.to_le_bytes());
+        }
+        Option::from(Scalar::from_repr(repr)).expect("device returned a canonical element")
+    }
+}
+
+impl<Scalar: B200Field> Drop for B200ConstraintSystem<Scalar> {
+    fn drop(&mut self) {
+        unsafe { ffi::bp_cs_free(self.h) }
+    }
+}
+
+impl<Scalar: B200Field> ConstraintSystem<Scalar> for B200ConstraintSystem<Scalar> {
+    type Root = Self;
+
+    fn new() -> Self {
+        Self::new_on(0)
+    }
+
+    fn alloc<F, A, AR>(&mut self, annotation: A, f: F) -> Result<Variable, SynthesisError>
+    where
+        F: FnOnce() -> Result<Scalar, SynthesisError>,
+        A: FnOnce() -> AR,
+        AR: Into<String>,
+    {
+        let index = self.count[1] as usize;
+        let path = compute_path(&self.current_namespace, &annotation().into());
+        let value = f()?; // an Err leaves no variable behind (test_cs.rs:388)
+        repr_to_limbs(&value, &mut self.pend_vals[1]);
+        self.count[1] += 1;
+        self.aux_names.push(path.clone());
+        let var = Variable::new_unchecked(Index::Aux(index));
+        self.set_named_obj(path, NamedObject::Var(var));
+        Ok(var)
+    }
+
+    fn alloc_input<F, A, AR>(&mut self, annotation: A, f: F) -> Result<Variable, SynthesisError>
+    where
+        F: FnOnce() -> Result<Scalar, SynthesisError>,
+        A: FnOnce() -> AR,
+        AR: Into<String>,
+    {
+        let index = self.count[0] as usize;
+        let path = compute_path(&self.current_namespace, &annotation().into());
+        let value = f()?;
+        repr_to_limbs(&value, &mut self.pend_vals[0]);
+        self.count[0] += 1;
+        self.input_names.push(path.clone());
+        let var = Variable::new_unchecked(Index::Input(index));
+        self.set_named_obj(path, NamedObject::Var(var));
+        Ok(var)
+    }
+
+    fn enforce<A, AR, LA, LB, LC>(&mut self, annotation: A, a: LA, b: LB, c: LC)
+    where
+        A: FnOnce() -> AR,
+        AR: Into<String>,
+        LA: FnOnce(LinearCombination<Scalar>) -> LinearCombination<Scalar>,
+        LB: FnOnce(LinearCombination<Scalar>) -> LinearCombination<Scalar>,
+        LC: FnOnce(LinearCombination<Scalar>) -> LinearCombination<Scalar>,
+    {
+        let path = compute_path(&self.current_namespace, &annotation().into());
+        let index = self.constraint_paths.len();
+        self.set_named_obj(path.clone(), NamedObject::Constraint(index));
+        let a = a(LinearCombination::zero());
+        let b = b(LinearCombination::zero());
+        let c = c(LinearCombination::zero());
+        self.push_lc(&a);
+        self.push_lc(&b);
+        self.push_lc(&c);
+        self.constraint_paths.push(path);
+        if self.cols.len() >= (1 << 20) {
+            self.flush();
+        }
+    }
+
+    fn push_namespace<NR, N>(&mut self, name_fn: N)
+    where
+        NR: Into<String>,
+        N: FnOnce() -> NR,
+    {
+        let name = name_fn().into();
+        let path = compute_path(&self.current_namespace, &name);
+        self.set_named_obj(path, NamedObject::Namespace);
+        self.current_namespace.push(name);
+    }
+
+    fn pop_namespace(&mut self) {
+        assert!(self.current_namespace.pop().is_some());
+    }
+
+    fn get_root(&mut self) -> &mut Self::Root {
+        self
+    }
+}
+
+#[cfg(test)]
+mod tests {
+    // Mirrors crates/bellpepper-core/src/util_cs/test_cs.rs:472-510 and the sha256 KATs; `impl B200Field for
+    // blstrs::Scalar { const FIELD_ID: i32 = 0; }` lives in the test module of a build that has blstrs.
+}
