@@ -6,6 +6,8 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
 #include <cstdarg>
@@ -15,6 +17,7 @@
 #include <string>
 
 #include "kernels.cuh"
+#include "staged.cuh"
 
 namespace {
 
@@ -43,7 +46,9 @@ struct bp_cs {
     DevBuf row_ptr, cols, vals, inputs, aux;
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
     DevBuf fat_rows;           // plan: rows handled by check_fat_rows (+ one u32 counter at the end)
+    DevBuf row_kind;           // plan: one RowKind byte per row
     uint64_t fat_terms = 96;   // rows with more terms than this go to the warp-per-row kernel
+    int64_t fat_ctas_per_sm = 8;  // grid of check_fat_rows = sm_count * this
     int64_t kernels_mask = 3;  // measurement aid: bit 0 = launch check_rows, bit 1 = launch check_fat_rows
     int64_t variant = -1;      // < 0: the default kernel configuration; >= 0: an experimental variant id (see launch_check)
     bool plan_valid = false;
@@ -145,7 +150,7 @@ CsrView view(const bp_cs* h) {
     m.n_rows = (uint32_t)h->n_rows;
     m.n_inputs = (uint32_t)h->n_inputs;
     m.n_aux = (uint32_t)h->n_aux;
-    m.fat_terms = (uint32_t)h->fat_terms;
+    m.fat_terms = (uint32_t)std::min<uint64_t>(h->fat_terms, kStageCap);  // the staged kernel cannot hold a larger row
     m.row_base = h->row_base;
     return m;
 }
@@ -207,7 +212,28 @@ int check_err_word(bp_cs* h, const char* what) {
     return BP_OK;
 }
 
-// (Re)build the fat-row list when rows or the threshold changed.
+constexpr int kVStaged = kVMagSkip | kVBitRow;
+
+template <int F> cudaError_t launch_thin_staged(bp_cs* h, const CsrView& m, const CheckOut& o) {
+    check_rows_staged<F, kVStaged, 5><<<h->sm_count * 5, 128, 0, h->stream>>>(m, o);
+    return cudaGetLastError();
+}
+
+template <int F> cudaError_t launch_fat_staged(bp_cs* h, const CsrView& m, const CheckOut& o, const uint32_t* fat, const uint32_t* n_fat) {
+    cudaError_t e = cudaFuncSetAttribute(check_fat_rows_staged<F, kVStaged, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFatStageSmem);
+    if (e != cudaSuccess) return e;
+    check_fat_rows_staged<F, kVStaged, 3><<<h->sm_count * 3, 128, kFatStageSmem, h->stream>>>(m, o, fat, n_fat);
+    return cudaGetLastError();
+}
+
+struct IsFatRow {
+    const uint32_t* row_ptr;
+    uint32_t fat_terms;
+    __host__ __device__ bool operator()(uint32_t row) const { return row_ptr[3 * (size_t)row + 3] - row_ptr[3 * (size_t)row] > fat_terms; }
+};
+
+// (Re)build the fat-row list when rows or the threshold changed.  The list is in ascending row order (stable
+// selection): warps that run at the same time then work on neighbouring rows, whose operands share cache lines.
 int ensure_plan(bp_cs* h) {
     if (h->plan_valid) return BP_OK;
     int rc = ensure(h, h->fat_rows, ((size_t)h->n_rows + 1) * 4, 0);
@@ -215,8 +241,16 @@ int ensure_plan(bp_cs* h) {
     uint32_t* cnt = (uint32_t*)h->fat_rows.p + h->n_rows;
     CU(h, cudaMemsetAsync(cnt, 0, 4, h->stream));
     if (h->n_rows) {
-        collect_fat_rows<<<grid_for(h, h->n_rows, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (uint32_t)h->n_rows,
-                                                                                 (uint32_t)h->fat_terms, (uint32_t*)h->fat_rows.p, cnt);
+        IsFatRow pred{(const uint32_t*)h->row_ptr.p, (uint32_t)std::min<uint64_t>(h->fat_terms, kStageCap)};
+        cub::CountingInputIterator<uint32_t> rows_begin(0);
+        size_t tmp_bytes = 0;
+        CU(h, cub::DeviceSelect::If(nullptr, tmp_bytes, rows_begin, (uint32_t*)h->fat_rows.p, cnt, (int)h->n_rows, pred, h->stream));
+        if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
+        CU(h, cub::DeviceSelect::If(h->scan_tmp.p, tmp_bytes, rows_begin, (uint32_t*)h->fat_rows.p, cnt, (int)h->n_rows, pred, h->stream));
+        if ((rc = ensure(h, h->row_kind, (size_t)h->n_rows, 0)) != BP_OK) return rc;
+        classify_rows<<<grid_for(h, h->n_rows, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p,
+                                                                              (const uint4*)h->vals.p, (uint32_t)h->n_rows, pred.fat_terms,
+                                                                              (uint8_t*)h->row_kind.p);
         h->launches++;
         CU(h, cudaGetLastError());
     }
@@ -242,18 +276,33 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
     const int grid = grid_for(h, h->n_rows, block, 16);
     const uint32_t* fat = (const uint32_t*)h->fat_rows.p;
     const uint32_t* n_fat = fat + h->n_rows;
-    const int fat_grid = h->sm_count * 8;
+    const int fat_grid = h->sm_count * (int)h->fat_ctas_per_sm;
     // (VT, MBT): feature bits / min blocks per SM of the thread-per-row kernel; (VF, MBF): of the warp-per-row kernel.
 #define BP_LAUNCH(EMITF, VT, MBT, VF, MBF)                                                                                                     \
     do {                                                                                                                                       \
         if (h->kernels_mask & 1) DISPATCH_FIELD(h, (check_rows<F, EMITF, VT, MBT><<<grid, block, 0, h->stream>>>(m, o, h->fc)));                \
         if (h->kernels_mask & 2) DISPATCH_FIELD(h, (check_fat_rows<F, EMITF, VF, MBF><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat))); \
     } while (0)
+    // staged variants (staged.cuh): TS = thread-per-row kernel staged, FS = warp-per-row kernel staged
+#define BP_LAUNCH_STAGED(TS, FS)                                                                                                \
+    do {                                                                                                                        \
+        cudaError_t le = cudaSuccess;                                                                                           \
+        if (h->kernels_mask & 1) {                                                                                              \
+            if (TS) { DISPATCH_FIELD(h, (le = launch_thin_staged<F>(h, m, o))); }                                                \
+            else { DISPATCH_FIELD(h, (check_rows<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); }         \
+        }                                                                                                                       \
+        if (le == cudaSuccess && (h->kernels_mask & 2)) {                                                                       \
+            if (FS) { DISPATCH_FIELD(h, (le = launch_fat_staged<F>(h, m, o, fat, n_fat))); }                                     \
+            else { DISPATCH_FIELD(h, (check_fat_rows<F, false, kVStaged, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat))); } \
+        }                                                                                                                       \
+        CU(h, le);                                                                                                              \
+    } while (0)
     if (emit) {
         BP_LAUNCH(true, 0, 4, 0, 4);
     } else {
         // default configuration by instance statistics: product-heavy instances park az/bz in shared memory
-        const int64_t variant = h->variant >= 0 ? h->variant : (2 * h->n_gen > h->nnz ? -2 : -1);
+        // -2: product-heavy (synthetic): generic kernel with az/bz parked; -1 -> 42: plain-row kernel first
+        const int64_t variant = h->variant >= 0 ? h->variant : (2 * h->n_gen > h->nnz ? -2 : (h->variant == -3 ? -1 : 42));
         switch (variant) {
 #ifdef BP_EXPERIMENTAL_VARIANTS
             case 0: BP_LAUNCH(false, 0, 4, 0, 4); break;
@@ -266,11 +315,32 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             case 10: BP_LAUNCH(false, kVMagSkip | kVBitRow, 6, kVMagSkip | kVBitRow, 6); break;
             case 14: BP_LAUNCH(false, 0, 6, 0, 6); break;
 #endif
+            case 30: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
+            case 31: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged, 5><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
+            case 32: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged, 4><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
+            case 33: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged | kVPark, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
+            case 34: DISPATCH_FIELD(h, (check_rows_fused2<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
+            case 35: DISPATCH_FIELD(h, (check_rows_fused2<F, false, kVStaged, 5><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
+            case 36: DISPATCH_FIELD(h, (check_rows_fused2<F, false, kVStaged, 4><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
+            case 40: case 41: case 42: {  // plain-row kernel + generic kernel on the remaining rows + fat kernel
+                uint8_t* kind = (uint8_t*)h->row_kind.p;
+                if (h->kernels_mask & 1) {
+                    if (variant == 40) { DISPATCH_FIELD(h, (check_rows_plain<F, 8><<<h->sm_count * 16, block, 0, h->stream>>>(m, o, kind))); }
+                    if (variant == 41) { DISPATCH_FIELD(h, (check_rows_plain<F, 6><<<h->sm_count * 12, block, 0, h->stream>>>(m, o, kind))); }
+                    if (variant == 42) { DISPATCH_FIELD(h, (check_rows_plain<F, 10><<<h->sm_count * 20, block, 0, h->stream>>>(m, o, kind))); }
+                    DISPATCH_FIELD(h, (check_rows<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc, kind)));
+                }
+                if (h->kernels_mask & 2) { DISPATCH_FIELD(h, (check_fat_rows<F, false, kVStaged, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat))); }
+            } break;
+            case 20: BP_LAUNCH_STAGED(true, false); break;
+            case 21: BP_LAUNCH_STAGED(false, true); break;
+            case 22: BP_LAUNCH_STAGED(true, true); break;
             case -2: BP_LAUNCH(false, kVMagSkip | kVBitRow | kVPark, 6, kVMagSkip | kVBitRow, 4); break;  // product-heavy instances
             default: BP_LAUNCH(false, kVMagSkip | kVBitRow, 6, kVMagSkip | kVBitRow, 4); break;          // measured best on gadget circuits
         }
     }
 #undef BP_LAUNCH
+#undef BP_LAUNCH_STAGED
     h->launches += 2;
     CU(h, cudaGetLastError());
     return BP_OK;
@@ -337,7 +407,7 @@ void bp_cs_free(bp_cs* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->scan_tmp, &h->scratch, &h->fat_rows})
+    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->scan_tmp, &h->scratch, &h->fat_rows, &h->row_kind})
         if (b->p) cudaFree(b->p);
     if (h->d_result) cudaFree(h->d_result);
     if (h->h_pinned_small) cudaFreeHost(h->h_pinned_small);
@@ -375,6 +445,11 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
     if (!h || !key) return BP_E_ARG;
     if (!std::strcmp(key, "variant")) {
         h->variant = v;
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "fat_ctas_per_sm")) {
+        if (v < 1 || v > 32) return fail(h, BP_E_ARG, "fat_ctas_per_sm out of range");
+        h->fat_ctas_per_sm = v;
         return BP_OK;
     }
     if (!std::strcmp(key, "kernels_mask")) {

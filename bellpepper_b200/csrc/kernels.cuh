@@ -58,6 +58,14 @@ struct CheckOut {
     uint4* cz;
 };
 
+// Plan: what kind of row is it (one byte per row, built by classify_rows)?
+enum RowKind : uint8_t {
+    kRowGeneric = 0,   // check_rows (full arithmetic)
+    kRowPlain = 1,     // every term is a small-coefficient class and sum|c| of C is <= 5: check_rows_plain can decide it
+    kRowFat = 2,       // check_fat_rows
+    kRowDeferred = 3   // a plain row whose VALUES needed the full product this time: check_rows picks it up and resets it
+};
+
 __device__ __forceinline__ void ld8(uint32_t* x, const uint4* p) {
     const uint4 lo = __ldg(p), hi = __ldg(p + 1);
     x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w;
@@ -280,12 +288,17 @@ __device__ __forceinline__ void publish_first_bad(uint32_t my_bad, const CsrView
 
 // ---- K1 / K2, thin rows: one thread per constraint -------------------------------------------------------------------
 template <int F, bool EMIT, int V, int MB>
-__global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, FieldConsts fc) {
+__global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, FieldConsts fc, uint8_t* __restrict__ kind = nullptr) {
     constexpr bool PIPE = (V & kVPipe) != 0, PARK = (V & kVPark) != 0;
     __shared__ uint32_t s_az[PARK ? 8 : 1][128], s_bz[PARK ? 8 : 1][128];
     uint32_t my_bad = 0xffffffffu;
     unsigned int my_err = 0;
     for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < m.n_rows; row += gridDim.x * blockDim.x) {
+        if (kind) {  // rows already decided by check_rows_plain (or owned by check_fat_rows) are not ours
+            const uint8_t kd = kind[row];
+            if (kd == kRowPlain || kd == kRowFat) continue;
+            if (kd == kRowDeferred) kind[row] = kRowPlain;  // picked up: back to its static kind for the next check
+        }
         const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
                        p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
         if (p3 - p0 > m.fat_terms) continue;  // check_fat_rows does it
@@ -328,6 +341,119 @@ __global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, Fie
             }
         }
         if (!row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, gen, mag) && row < my_bad) my_bad = row;
+    }
+    publish_first_bad(my_bad, m, o, my_err);
+}
+
+// ---- plan: what kind of row is it? -------------------------------------------------------------------------------------
+
+__global__ void classify_rows(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, const uint4* __restrict__ vals,
+                              uint32_t n_rows, uint32_t fat_terms, uint8_t* __restrict__ kind) {
+    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+        const uint32_t p0 = row_ptr[3 * (size_t)row], p2 = row_ptr[3 * (size_t)row + 2], p3 = row_ptr[3 * (size_t)row + 3];
+        uint8_t k = kRowPlain;
+        if (p3 - p0 > fat_terms) {
+            k = kRowFat;
+        } else {
+            uint32_t mag_c = 0;
+            for (uint32_t t = p0; t < p3 && k == kRowPlain; ++t) {
+                const uint32_t cls = (__ldg(cols + t) >> kColClsShift) & 7u;
+                if (cls == kClsGen) k = kRowGeneric;
+                if (t >= p2) {
+                    if (cls == kClsP1 || cls == kClsM1) mag_c += 1;
+                    else if (cls == kClsP2 || cls == kClsM2) mag_c += 2;
+                    else if (cls == kClsPS || cls == kClsMS) {
+                        const uint32_t sm = __ldg(reinterpret_cast<const uint32_t*>(vals + 2 * (size_t)t));
+                        mag_c += sm > 8u ? 8u : sm;
+                    }
+                    if (mag_c > 5u) k = kRowGeneric;
+                }
+            }
+        }
+        kind[row] = k;
+    }
+}
+
+// Fold the plain terms [k0,k1) into a 9-limb accumulator (sum < 8p by construction of the row kind).
+template <int F>
+__device__ __forceinline__ void fold_plain(uint32_t* acc /*9*/, uint32_t k0, uint32_t k1, const CsrView& m, unsigned int& err, uint32_t& mag) {
+#pragma unroll 1
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t col = __ldg(m.cols + k);
+        const uint32_t cls = (col >> kColClsShift) & 7u;
+        if (cls == kClsZero) continue;
+        const uint32_t idx = col & kColIdxMask;
+        const bool is_aux = (col & kColAux) != 0;
+        if (idx >= (is_aux ? m.n_aux : m.n_inputs)) { err = 1; continue; }
+        uint32_t w[8];
+        ld8(w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx);
+        if (cls == kClsM1 || cls == kClsM2 || cls == kClsMS) {
+            uint32_t n[8];
+            neg_mod<F>(n, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = n[i];
+        }
+        if (cls == kClsP1 || cls == kClsM1) {
+            acc_add8<9>(acc, w);
+            mag += 1;
+        } else if (cls == kClsP2 || cls == kClsM2) {
+            acc_add8<9>(acc, w);
+            acc_add8<9>(acc, w);
+            mag += 2;
+        } else {
+            const uint32_t sm = __ldg(reinterpret_cast<const uint32_t*>(m.vals + 2 * (size_t)k));
+            acc_mad_small<9>(acc, w, sm);
+            mag += sm > 8u ? 8u : sm;
+        }
+    }
+}
+
+template <int F> __device__ __forceinline__ void finish_plain(uint32_t* out /*8*/, const uint32_t* acc /*9*/, uint32_t mag) {
+    if (mag <= 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = acc[i];
+    } else {
+        reduce_8p<F>(out, acc);
+    }
+}
+
+// ---- K1, plain rows: additions only.  Small register footprint -> 8 CTAs/SM; rows whose values need the full product
+// (neither Az nor Bz is 0/1) are handed to check_rows through the kind byte.
+template <int F, int MB>
+__global__ void __launch_bounds__(128, MB) check_rows_plain(CsrView m, CheckOut o, uint8_t* __restrict__ kind) {
+    uint32_t my_bad = 0xffffffffu;
+    unsigned int my_err = 0;
+    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < m.n_rows; row += gridDim.x * blockDim.x) {
+        if (kind[row] != kRowPlain) continue;
+        const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
+                       p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
+        uint32_t acc[9], az[8], bz[8];
+        uint32_t mag = 0;
+        zeron<9>(acc);
+        fold_plain<F>(acc, p0, p1, m, my_err, mag);
+        finish_plain<F>(az, acc, mag);
+        mag = 0;
+        zeron<9>(acc);
+        fold_plain<F>(acc, p1, p2, m, my_err, mag);
+        finish_plain<F>(bz, acc, mag);
+        const uint32_t sa = small01(az), sb = small01(bz);
+        if (sa == 2u && sb == 2u) {  // needs Az*Bz: not ours
+            kind[row] = kRowDeferred;
+            continue;
+        }
+        mag = 0;
+        zeron<9>(acc);
+        fold_plain<F>(acc, p2, p3, m, my_err, mag);  // < 5p by the row kind
+        const bool zero = (sa == 0u) || (sb == 0u);
+        uint32_t prod[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) prod[i] = zero ? 0u : (sa == 1u ? bz[i] : az[i]);
+        acc_add8<9>(acc, prod);  // < 5p + 2p
+        uint32_t r[8], nz = 0;
+        reduce_8p<F>(r, acc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nz |= r[i];
+        if (nz != 0 && row < my_bad) my_bad = row;
     }
     publish_first_bad(my_bad, m, o, my_err);
 }
@@ -408,6 +534,196 @@ __global__ void __launch_bounds__(128, MB) check_fat_rows(CsrView m, CheckOut o,
             }
         }
         if (!row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, any_gen, mag) && row < my_bad) my_bad = row;
+    }
+    publish_first_bad(my_bad, m, o, my_err);
+}
+
+// One fat row by the whole warp, outlined so that its register needs do not leak into the thin path's allocation.
+// Returns (to every lane) whether the row is satisfied; emits canonical Az/Bz/Cz from lane 0 when asked to.
+template <int F, bool EMIT, int V>
+__device__ __noinline__ bool fat_row_by_warp(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t frow, const CsrView& m,
+                                             const CheckOut& o, const FieldConsts& fc, unsigned int* err_out) {
+    unsigned int err = 0;
+    uint32_t acc[17], az[8], bz[8];
+    uint32_t any_gen, mag;
+    warp_fold_lc<F, 9, false>(acc, q0, q1, m, err, any_gen, mag);
+    finish_ab<F, (V & kVMagSkip) != 0>(az, acc, any_gen, mag);
+    warp_fold_lc<F, 9, false>(acc, q1, q2, m, err, any_gen, mag);
+    finish_ab<F, (V & kVMagSkip) != 0>(bz, acc, any_gen, mag);
+    warp_fold_lc<F, 17, false>(acc, q2, q3, m, err, any_gen, mag);
+    if (EMIT && (threadIdx.x & 31u) == 0) {
+        uint32_t v[8];
+        if (o.cz) {
+            finish_c_canonical<F>(v, acc, fc);
+            st8(o.cz + 2 * (size_t)frow, v);
+        }
+        if (o.az) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = az[i];
+            canon_ab<F>(v);
+            st8(o.az + 2 * (size_t)frow, v);
+        }
+        if (o.bz) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = bz[i];
+            canon_ab<F>(v);
+            st8(o.bz + 2 * (size_t)frow, v);
+        }
+    }
+    *err_out |= err;
+    return row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, any_gen, mag);
+}
+
+// One thin row by its own thread, outlined for the same reason as fat_row_by_warp.  Returns "satisfied".
+template <int F, bool EMIT, int V>
+__device__ __noinline__ bool thin_row_by_thread(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t row, const CsrView& m,
+                                                const CheckOut& o, const FieldConsts& fc, unsigned int* err_out) {
+    unsigned int err = 0;
+    uint32_t acc[17], az[8], bz[8];
+    uint32_t gen = 0, mag = 0;
+    zeron<17>(acc);
+    fold_range<F, 9, 1, false>(acc, p0, p1, m, err, gen, mag);
+    finish_ab<F, (V & kVMagSkip) != 0>(az, acc, gen, mag);
+    gen = 0; mag = 0;
+    zeron<17>(acc);
+    fold_range<F, 9, 1, false>(acc, p1, p2, m, err, gen, mag);
+    finish_ab<F, (V & kVMagSkip) != 0>(bz, acc, gen, mag);
+    gen = 0; mag = 0;
+    zeron<17>(acc);
+    fold_range<F, 17, 1, false>(acc, p2, p3, m, err, gen, mag);
+    if (EMIT) {
+        uint32_t v[8];
+        if (o.cz) {
+            finish_c_canonical<F>(v, acc, fc);
+            st8(o.cz + 2 * (size_t)row, v);
+        }
+        if (o.az) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = az[i];
+            canon_ab<F>(v);
+            st8(o.az + 2 * (size_t)row, v);
+        }
+        if (o.bz) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = bz[i];
+            canon_ab<F>(v);
+            st8(o.bz + 2 * (size_t)row, v);
+        }
+    }
+    *err_out |= err;
+    return row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, gen, mag);
+}
+
+// ---- K1 / K2, fused: thin rows by their own thread, fat rows by the whole warp, in the SAME pass over the rows --------
+// A separate fat-row kernel gathers from a witness region that has long left the caches (measured: L2 hit 8 %, and it
+// runs at the HBM random-access rate); handled in place, a fat row finds its operands in L2/L1 because the neighbouring
+// thin rows have just touched the same variables.  A warp owns 32 consecutive rows: each lane evaluates its row if it is
+// thin; then the lanes that hold a fat row are served one after the other by all 32 lanes together.
+template <int F, bool EMIT, int V, int MB>
+__global__ void __launch_bounds__(128, MB) check_rows_fused(CsrView m, CheckOut o, FieldConsts fc) {
+    constexpr bool PARK = (V & kVPark) != 0;
+    __shared__ uint32_t s_az[PARK ? 8 : 1][128], s_bz[PARK ? 8 : 1][128];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t my_bad = 0xffffffffu;
+    unsigned int my_err = 0;
+    const uint32_t n_blocks = (m.n_rows + 31u) / 32u;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n_blocks; blk += n_warps) {
+        const uint32_t row = blk * 32u + lane;
+        const bool live = row < m.n_rows;
+        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+        if (live) {
+            p0 = __ldg(m.row_ptr + 3 * (size_t)row);
+            p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1);
+            p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2);
+            p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
+        }
+        const bool fat = live && (p3 - p0 > m.fat_terms);
+        if (live && !fat) {
+            uint32_t acc[17], az[8], bz[8];
+            uint32_t gen = 0, mag = 0;
+            zeron<17>(acc);
+            fold_range<F, 9, 1, false>(acc, p0, p1, m, my_err, gen, mag);
+            finish_ab<F, (V & kVMagSkip) != 0>(az, acc, gen, mag);
+            if (PARK) park8(s_az, az);
+            gen = 0; mag = 0;
+            zeron<17>(acc);
+            fold_range<F, 9, 1, false>(acc, p1, p2, m, my_err, gen, mag);
+            finish_ab<F, (V & kVMagSkip) != 0>(bz, acc, gen, mag);
+            if (PARK) park8(s_bz, bz);
+            gen = 0; mag = 0;
+            zeron<17>(acc);
+            fold_range<F, 17, 1, false>(acc, p2, p3, m, my_err, gen, mag);
+            if (PARK) {
+                unpark8(az, s_az);
+                unpark8(bz, s_bz);
+            }
+            if (EMIT) {
+                uint32_t v[8];
+                if (o.cz) {
+                    finish_c_canonical<F>(v, acc, fc);
+                    st8(o.cz + 2 * (size_t)row, v);
+                }
+                if (o.az) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = az[i];
+                    canon_ab<F>(v);
+                    st8(o.az + 2 * (size_t)row, v);
+                }
+                if (o.bz) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = bz[i];
+                    canon_ab<F>(v);
+                    st8(o.bz + 2 * (size_t)row, v);
+                }
+            }
+            if (!row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, gen, mag) && row < my_bad) my_bad = row;
+        }
+        // fat rows of this block: the whole warp serves them one at a time
+        uint32_t fat_mask = __ballot_sync(0xffffffffu, fat);
+        while (fat_mask) {
+            const int src = __ffs(fat_mask) - 1;
+            fat_mask &= fat_mask - 1;
+            const uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src),
+                           q2 = __shfl_sync(0xffffffffu, p2, src), q3 = __shfl_sync(0xffffffffu, p3, src);
+            const uint32_t frow = blk * 32u + (uint32_t)src;
+            if (!fat_row_by_warp<F, EMIT, V>(q0, q1, q2, q3, frow, m, o, fc, &my_err) && frow < my_bad) my_bad = frow;
+        }
+    }
+    publish_first_bad(my_bad, m, o, my_err);
+}
+
+// Same as check_rows_fused with BOTH paths outlined: the kernel body is only the dispatcher.
+template <int F, bool EMIT, int V, int MB>
+__global__ void __launch_bounds__(128, MB) check_rows_fused2(CsrView m, CheckOut o, FieldConsts fc) {
+    uint32_t my_bad = 0xffffffffu;
+    unsigned int my_err = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_blocks = (m.n_rows + 31u) / 32u;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n_blocks; blk += n_warps) {
+        const uint32_t row = blk * 32u + lane;
+        const bool live = row < m.n_rows;
+        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+        if (live) {
+            p0 = __ldg(m.row_ptr + 3 * (size_t)row);
+            p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1);
+            p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2);
+            p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
+        }
+        const bool fat = live && (p3 - p0 > m.fat_terms);
+        if (live && !fat) {
+            if (!thin_row_by_thread<F, EMIT, V>(p0, p1, p2, p3, row, m, o, fc, &my_err) && row < my_bad) my_bad = row;
+        }
+        uint32_t fat_mask = __ballot_sync(0xffffffffu, fat);
+        while (fat_mask) {
+            const int src = __ffs(fat_mask) - 1;
+            fat_mask &= fat_mask - 1;
+            const uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src),
+                           q2 = __shfl_sync(0xffffffffu, p2, src), q3 = __shfl_sync(0xffffffffu, p3, src);
+            const uint32_t frow = blk * 32u + (uint32_t)src;
+            if (!fat_row_by_warp<F, EMIT, V>(q0, q1, q2, q3, frow, m, o, fc, &my_err) && frow < my_bad) my_bad = frow;
+        }
     }
     publish_first_bad(my_bad, m, o, my_err);
 }

@@ -181,7 +181,9 @@ def sha256_chain_host_csr(field: int, blocks: int):
 def sha256_chain_into_new_handle(field: int, device: int, blocks: int, rank: int = 0, world: int = 1):
     """BASELINE configs[1]: sha256 gadget over `blocks` chained compression blocks, rows of this rank's block range
     streamed into a fresh device handle.  Returns (bp_cs handle as c_void_p, info); the caller frees via `info['tcs']`."""
-    b0, b1 = rank * blocks // world, (rank + 1) * blocks // world
+    from .sharding import split_range
+
+    b0, b1 = split_range(blocks, rank, world)
     per_block_rows, per_block_terms, per_block_vars = 26400, 170000, 26500
     t = Tcs(field, device, named=False,
             reserve=((b1 - b0) * per_block_rows + 4096, (b1 - b0) * per_block_terms + 65536, blocks * per_block_vars + 4096))

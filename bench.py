@@ -113,11 +113,12 @@ def build_workload(L, ffi, name, rank, world, device):
     info = {"field": field}
     t0 = time.time()
     if kind == "synthetic":
+        from bellpepper_b200.sharding import split_range
+
         n_rows_total = 1 << prm["log_rows"]
         n_vars = n_rows_total
         t = prm["t"]
-        r0 = rank * n_rows_total // world
-        r1 = (rank + 1) * n_rows_total // world
+        r0, r1 = split_range(n_rows_total, rank, world)
         n = r1 - r0
         rc = L.bp_cs_new(field, device, n, int(n * 3 * t * 1.01) + 4096, n_vars, ctypes.byref(h))
         assert rc == 0, f"bp_cs_new -> {rc} (no CUDA device? there is no CPU path)"
@@ -163,7 +164,8 @@ def cpu_reference_rate(name, sample_rows_log2, threads, steps=1, warmup=0):
         n = lens.size // 3
         inst = c_api.Instance(field, lens, cols, coeffs, inputs, aux)
         sample = f"first {blocks} blocks ({n} rows) of {name}"
-    threads = threads or lib().bpo_max_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; bpo_check sets its own team size)
+    threads = threads or max(lib().bpo_max_threads(), len(os.sched_getaffinity(0)))
     for _ in range(warmup):
         inst.check(threads, False)
     t0 = time.perf_counter()
@@ -230,6 +232,7 @@ def main():
     import torch.distributed as dist
 
     from bellpepper_b200 import ffi
+    from bellpepper_b200.sharding import reduce_first_unsatisfied
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
     torch.cuda.set_device(local_rank)
@@ -254,8 +257,7 @@ def main():
     def step_device():
         rc = L.bp_cs_check_async(h, ctypes.c_void_p(result.data_ptr()))
         assert rc == 0, L.bp_cs_last_error(h)
-        if world > 1:
-            dist.all_reduce(result, op=dist.ReduceOp.MIN)
+        reduce_first_unsatisfied(result, world)  # NCCL MIN all-reduce of the global first-unsatisfied row (no-op at N=1)
 
     def barrier():
         if world > 1:

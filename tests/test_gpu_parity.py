@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 from gpu_util import Handle  # noqa: E402
 
 FIDS = sorted(FIELDS)
-KERNELS = [96, 8]  # fat_terms: default split, and "almost every row through the warp-per-row kernel"
+# (fat_terms, variant): default split / nearly every row through the warp-per-row kernel, x direct (-1) / warp-staged (22) kernels
+KERNELS = [(96, -1), (8, -1), (96, -3), (8, 22), (96, 40)]
 
 
 @pytest.mark.parametrize("fid", FIDS)
@@ -24,7 +25,8 @@ def test_host_ingested_synthetic_matches_oracle(fid, kernel, t, n_vars, n_rows):
     inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
     bad, az_r, bz_r, cz_r = inst.eval(2)
     with Handle(fid) as h:
-        h.opt("fat_terms", kernel)
+        h.opt("fat_terms", kernel[0])
+        h.opt("variant", kernel[1])
         h.load_instance(lens, cols, coeffs, inputs, aux)
         assert h.counts() == (inputs.shape[0], aux.shape[0], n_rows, cols.size)
         assert h.first_unsatisfied() == bad
@@ -51,7 +53,8 @@ def test_device_generator_matches_oracle_recipe(fid):
         az, bz, cz = h.eval(n_rows)
         assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
         for kernel in KERNELS:
-            h.opt("fat_terms", kernel)
+            h.opt("fat_terms", kernel[0])
+            h.opt("variant", kernel[1])
             assert h.first_unsatisfied() == bad
 
 
@@ -87,7 +90,8 @@ def test_satisfiable_then_flip_first_failure(fid, kernel):
     assert inst.check(2, False) == -1
     rng = random.Random(99 + fid)
     with Handle(fid) as h:
-        h.opt("fat_terms", kernel)
+        h.opt("fat_terms", kernel[0])
+        h.opt("variant", kernel[1])
         h.load_instance(lens, cols, coeffs, inputs, aux)
         assert h.first_unsatisfied() == -1
         for _ in range(6):  # flip-and-recheck (boolean.rs:783-787, num.rs:753-762): no matrix re-upload
@@ -155,7 +159,8 @@ def test_ragged_empty_and_fat_rows(kernel):
     inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
     bad, az_r, bz_r, cz_r = inst.eval(2)
     with Handle(fid) as h:
-        h.opt("fat_terms", kernel)
+        h.opt("fat_terms", kernel[0])
+        h.opt("variant", kernel[1])
         # ingest in three uneven batches
         first = ctypes.c_uint64()
         h.ok(h.L.bp_cs_alloc(h.h, 0, inputs[1:].ctypes.data, 2, ctypes.byref(first)))
