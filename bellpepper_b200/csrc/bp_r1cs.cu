@@ -17,7 +17,6 @@
 #include <string>
 
 #include "kernels.cuh"
-#include "staged.cuh"
 
 namespace {
 
@@ -44,16 +43,22 @@ struct bp_cs {
     uint64_t n_rows = 0, nnz = 0, n_inputs = 0, n_aux = 0, row_base = 0;
     uint64_t n_gen = 0;  // terms that need a full 256x256 product (drives the kernel-configuration heuristic)
     DevBuf row_ptr, cols, vals, inputs, aux;
+    DevBuf inputs_s, aux_s;    // witness shadows (u32 per element, kernels.cuh: shadow_of)
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
+    DevBuf u8_stage;           // packed witness uploads land here before widen_u8
+    DevBuf row_meta;           // plan: lengths + RowKind per row
     DevBuf fat_rows;           // plan: rows handled by check_fat_rows (+ one u32 counter at the end)
-    DevBuf row_kind;           // plan: one RowKind byte per row
+    DevBuf gen_rows;           // plan: rows of kind Generic when the instance also has plain rows (+ counter)
+    DevBuf deferred;           // per check: plain rows check_small handed to check_rows
+    uint64_t n_fat_rows = 0, n_gen_rows = 0, n_plain_rows = 0;  // plan statistics (host copies)
     uint64_t fat_terms = 96;   // rows with more terms than this go to the warp-per-row kernel
     int64_t fat_ctas_per_sm = 8;  // grid of check_fat_rows = sm_count * this
-    int64_t kernels_mask = 3;  // measurement aid: bit 0 = launch check_rows, bit 1 = launch check_fat_rows
-    int64_t variant = -1;      // < 0: the default kernel configuration; >= 0: an experimental variant id (see launch_check)
+    int64_t kernels_mask = 3;  // measurement aid: bit 0 = launch the thin-row kernels, bit 1 = launch check_fat_rows
+    int64_t variant = -1;      // < 0: default; >= 0: bit 0 = no small-row kernel, bit 1 = no shadows in the fat kernel, bit 2 = park az/bz
     bool plan_valid = false;
     long long* d_result = nullptr;  // [0] first_bad
-    unsigned int* d_err = nullptr;
+    unsigned int* d_err = nullptr;  // [0] err word, [1] GEN-term counter of the last ingest call
+    uint32_t* d_ndef = nullptr;     // number of rows in `deferred`
     void* h_pinned_small = nullptr;  // 64 B: [0,32) element, [32,40) first_bad, [40,44) err word, [48,56) tiny row_ptr
     void* h_stage[kNumStage] = {nullptr, nullptr};
     cudaEvent_t stage_ev[kNumStage] = {nullptr, nullptr};
@@ -147,10 +152,13 @@ CsrView view(const bp_cs* h) {
     m.vals = (const uint4*)h->vals.p;
     m.inputs = (const uint4*)h->inputs.p;
     m.aux = (const uint4*)h->aux.p;
+    m.inputs_s = (const uint32_t*)h->inputs_s.p;
+    m.aux_s = (const uint32_t*)h->aux_s.p;
+    m.row_meta = (const uint32_t*)h->row_meta.p;
     m.n_rows = (uint32_t)h->n_rows;
     m.n_inputs = (uint32_t)h->n_inputs;
     m.n_aux = (uint32_t)h->n_aux;
-    m.fat_terms = (uint32_t)std::min<uint64_t>(h->fat_terms, kStageCap);  // the staged kernel cannot hold a larger row
+    m.fat_terms = (uint32_t)h->fat_terms;
     m.row_base = h->row_base;
     return m;
 }
@@ -212,56 +220,68 @@ int check_err_word(bp_cs* h, const char* what) {
     return BP_OK;
 }
 
-constexpr int kVStaged = kVMagSkip | kVBitRow;
+constexpr int kVDefault = kVMagSkip | kVBitRow;
 
-template <int F> cudaError_t launch_thin_staged(bp_cs* h, const CsrView& m, const CheckOut& o) {
-    check_rows_staged<F, kVStaged, 5><<<h->sm_count * 5, 128, 0, h->stream>>>(m, o);
-    return cudaGetLastError();
-}
-
-template <int F> cudaError_t launch_fat_staged(bp_cs* h, const CsrView& m, const CheckOut& o, const uint32_t* fat, const uint32_t* n_fat) {
-    cudaError_t e = cudaFuncSetAttribute(check_fat_rows_staged<F, kVStaged, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFatStageSmem);
-    if (e != cudaSuccess) return e;
-    check_fat_rows_staged<F, kVStaged, 3><<<h->sm_count * 3, 128, kFatStageSmem, h->stream>>>(m, o, fat, n_fat);
-    return cudaGetLastError();
-}
-
-struct IsFatRow {
-    const uint32_t* row_ptr;
-    uint32_t fat_terms;
-    __host__ __device__ bool operator()(uint32_t row) const { return row_ptr[3 * (size_t)row + 3] - row_ptr[3 * (size_t)row] > fat_terms; }
+struct RowKindIs {
+    const uint32_t* meta;
+    uint32_t kind;
+    __host__ __device__ bool operator()(uint32_t row) const { return (meta[row] >> 24) == kind; }
 };
 
-// (Re)build the fat-row list when rows or the threshold changed.  The list is in ascending row order (stable
-// selection): warps that run at the same time then work on neighbouring rows, whose operands share cache lines.
+// Ascending list of the rows whose kind is `kind` (stable selection: warps that run at the same time then work on
+// neighbouring rows, whose operands share cache lines).  list has room for `expect` rows + the counter word.
+int select_rows(bp_cs* h, DevBuf& list, uint32_t kind, uint64_t expect) {
+    int rc = ensure(h, list, ((size_t)expect + 1) * 4, 0);
+    if (rc != BP_OK) return rc;
+    uint32_t* cnt = (uint32_t*)list.p + expect;
+    CU(h, cudaMemsetAsync(cnt, 0, 4, h->stream));
+    if (!expect) return BP_OK;
+    RowKindIs pred{(const uint32_t*)h->row_meta.p, kind};
+    cub::CountingInputIterator<uint32_t> rows_begin(0);
+    size_t tmp_bytes = 0;
+    CU(h, cub::DeviceSelect::If(nullptr, tmp_bytes, rows_begin, (uint32_t*)list.p, cnt, (int)h->n_rows, pred, h->stream));
+    if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
+    CU(h, cub::DeviceSelect::If(h->scan_tmp.p, tmp_bytes, rows_begin, (uint32_t*)list.p, cnt, (int)h->n_rows, pred, h->stream));
+    return BP_OK;
+}
+
+// (Re)build the plan when rows or the threshold changed: row_meta, the per-kind counts, the fat / generic row lists and the
+// deferred-row buffer.
 int ensure_plan(bp_cs* h) {
     if (h->plan_valid) return BP_OK;
-    int rc = ensure(h, h->fat_rows, ((size_t)h->n_rows + 1) * 4, 0);
-    if (rc != BP_OK) return rc;
-    uint32_t* cnt = (uint32_t*)h->fat_rows.p + h->n_rows;
-    CU(h, cudaMemsetAsync(cnt, 0, 4, h->stream));
+    h->n_fat_rows = h->n_gen_rows = h->n_plain_rows = 0;
     if (h->n_rows) {
-        IsFatRow pred{(const uint32_t*)h->row_ptr.p, (uint32_t)std::min<uint64_t>(h->fat_terms, kStageCap)};
-        cub::CountingInputIterator<uint32_t> rows_begin(0);
-        size_t tmp_bytes = 0;
-        CU(h, cub::DeviceSelect::If(nullptr, tmp_bytes, rows_begin, (uint32_t*)h->fat_rows.p, cnt, (int)h->n_rows, pred, h->stream));
-        if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
-        CU(h, cub::DeviceSelect::If(h->scan_tmp.p, tmp_bytes, rows_begin, (uint32_t*)h->fat_rows.p, cnt, (int)h->n_rows, pred, h->stream));
-        if ((rc = ensure(h, h->row_kind, (size_t)h->n_rows, 0)) != BP_OK) return rc;
-        classify_rows<<<grid_for(h, h->n_rows, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p,
-                                                                              (const uint4*)h->vals.p, (uint32_t)h->n_rows, pred.fat_terms,
-                                                                              (uint8_t*)h->row_kind.p);
+        const uint32_t n = (uint32_t)h->n_rows;
+        int rc = ensure(h, h->row_meta, (size_t)n * 4, 0);
+        if (rc != BP_OK) return rc;
+        if ((rc = ensure(h, h->scratch, 16, 0)) != BP_OK) return rc;
+        uint32_t* d_cnt = (uint32_t*)h->scratch.p;
+        CU(h, cudaMemsetAsync(d_cnt, 0, 12, h->stream));
+        build_row_meta<<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p,
+                                                                       (const uint4*)h->vals.p, n, (uint32_t)h->fat_terms,
+                                                                       (uint32_t*)h->row_meta.p, d_cnt);
         h->launches++;
         CU(h, cudaGetLastError());
+        uint32_t* hc = (uint32_t*)((char*)h->h_pinned_small + 48);
+        CU(h, cudaMemcpyAsync(hc, d_cnt, 12, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->n_gen_rows = hc[kRowGeneric];
+        h->n_plain_rows = hc[kRowPlain];
+        h->n_fat_rows = hc[kRowFat];
+        if ((rc = select_rows(h, h->fat_rows, kRowFat, h->n_fat_rows)) != BP_OK) return rc;
+        // the generic list is only needed when the thin rows are split between check_small and check_rows
+        if ((rc = select_rows(h, h->gen_rows, kRowGeneric, h->n_plain_rows ? h->n_gen_rows : 0)) != BP_OK) return rc;
+        if ((rc = ensure(h, h->deferred, std::max<size_t>((size_t)h->n_plain_rows * 4, 4), 0)) != BP_OK) return rc;
     }
     h->plan_valid = true;
     return BP_OK;
 }
 
-// Launch K1/K2 on the handle's stream: result init, thread-per-row kernel, warp-per-row kernel for the fat rows.
-// Emit mode when any of az/bz/cz is set.
+// Launch K1/K2 on the handle's stream.  Emit mode (any of az/bz/cz set): the full-width kernels over every row.
+// Check mode: result init; check_small over the plain rows (integer arithmetic on the shadows); check_rows over the generic
+// rows and whatever check_small deferred; check_fat_rows (warp per row) over the fat rows.
 int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4* cz) {
-    init_result<<<1, 1, 0, h->stream>>>(dev_first_bad, h->d_err);
+    init_result<<<1, 1, 0, h->stream>>>(dev_first_bad, h->d_err, h->d_ndef);
     h->launches++;
     if (h->n_rows == 0) {
         CU(h, cudaGetLastError());
@@ -275,36 +295,25 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
     const int block = 128;
     const int grid = grid_for(h, h->n_rows, block, 16);
     const uint32_t* fat = (const uint32_t*)h->fat_rows.p;
-    const uint32_t* n_fat = fat + h->n_rows;
-    const int fat_grid = h->sm_count * (int)h->fat_ctas_per_sm;
+    const uint32_t* n_fat = fat + h->n_fat_rows;
+    const int fat_grid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * (uint64_t)h->fat_ctas_per_sm);
     // (VT, MBT): feature bits / min blocks per SM of the thread-per-row kernel; (VF, MBF): of the warp-per-row kernel.
 #define BP_LAUNCH(EMITF, VT, MBT, VF, MBF)                                                                                                     \
     do {                                                                                                                                       \
-        if (h->kernels_mask & 1) DISPATCH_FIELD(h, (check_rows<F, EMITF, VT, MBT><<<grid, block, 0, h->stream>>>(m, o, h->fc)));                \
-        if (h->kernels_mask & 2) DISPATCH_FIELD(h, (check_fat_rows<F, EMITF, VF, MBF><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat))); \
-    } while (0)
-    // staged variants (staged.cuh): TS = thread-per-row kernel staged, FS = warp-per-row kernel staged
-#define BP_LAUNCH_STAGED(TS, FS)                                                                                                \
-    do {                                                                                                                        \
-        cudaError_t le = cudaSuccess;                                                                                           \
-        if (h->kernels_mask & 1) {                                                                                              \
-            if (TS) { DISPATCH_FIELD(h, (le = launch_thin_staged<F>(h, m, o))); }                                                \
-            else { DISPATCH_FIELD(h, (check_rows<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); }         \
-        }                                                                                                                       \
-        if (le == cudaSuccess && (h->kernels_mask & 2)) {                                                                       \
-            if (FS) { DISPATCH_FIELD(h, (le = launch_fat_staged<F>(h, m, o, fat, n_fat))); }                                     \
-            else { DISPATCH_FIELD(h, (check_fat_rows<F, false, kVStaged, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat))); } \
-        }                                                                                                                       \
-        CU(h, le);                                                                                                              \
+        if (h->kernels_mask & 1) {                                                                                                             \
+            DISPATCH_FIELD(h, (check_rows<F, EMITF, VT, MBT><<<grid, block, 0, h->stream>>>(m, o, h->fc)));                                     \
+            h->launches++;                                                                                                                     \
+        }                                                                                                                                      \
+        if ((h->kernels_mask & 2) && h->n_fat_rows) {                                                                                          \
+            DISPATCH_FIELD(h, (check_fat_rows<F, EMITF, VF, MBF><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));                 \
+            h->launches++;                                                                                                                     \
+        }                                                                                                                                      \
     } while (0)
     if (emit) {
         BP_LAUNCH(true, 0, 4, 0, 4);
-    } else {
-        // default configuration by instance statistics: product-heavy instances park az/bz in shared memory
-        // -2: product-heavy (synthetic): generic kernel with az/bz parked; -1 -> 42: plain-row kernel first
-        const int64_t variant = h->variant >= 0 ? h->variant : (2 * h->n_gen > h->nnz ? -2 : (h->variant == -3 ? -1 : 42));
-        switch (variant) {
+    } else if (h->variant >= 100) {
 #ifdef BP_EXPERIMENTAL_VARIANTS
+        switch (h->variant - 100) {
             case 0: BP_LAUNCH(false, 0, 4, 0, 4); break;
             case 1: BP_LAUNCH(false, kVMagSkip, 4, kVMagSkip, 4); break;
             case 2: BP_LAUNCH(false, kVMagSkip | kVBitRow, 4, kVMagSkip | kVBitRow, 4); break;
@@ -312,36 +321,49 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             case 4: BP_LAUNCH(false, kVMagSkip | kVPrefetch, 4, kVMagSkip, 4); break;
             case 5: BP_LAUNCH(false, kVMagSkip | kVPipe, 5, kVMagSkip | kVPipe, 5); break;
             case 8: BP_LAUNCH(false, kVMagSkip | kVPark, 6, kVMagSkip | kVPark, 6); break;
-            case 10: BP_LAUNCH(false, kVMagSkip | kVBitRow, 6, kVMagSkip | kVBitRow, 6); break;
             case 14: BP_LAUNCH(false, 0, 6, 0, 6); break;
+            default: return fail(h, BP_E_ARG, "unknown experimental variant");
+        }
+#else
+        return fail(h, BP_E_ARG, "experimental variants need a build with BP_EXPERIMENTAL_VARIANTS=1");
 #endif
-            case 30: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
-            case 31: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged, 5><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
-            case 32: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged, 4><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
-            case 33: DISPATCH_FIELD(h, (check_rows_fused<F, false, kVStaged | kVPark, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
-            case 34: DISPATCH_FIELD(h, (check_rows_fused2<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
-            case 35: DISPATCH_FIELD(h, (check_rows_fused2<F, false, kVStaged, 5><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
-            case 36: DISPATCH_FIELD(h, (check_rows_fused2<F, false, kVStaged, 4><<<grid, block, 0, h->stream>>>(m, o, h->fc))); break;
-            case 40: case 41: case 42: {  // plain-row kernel + generic kernel on the remaining rows + fat kernel
-                uint8_t* kind = (uint8_t*)h->row_kind.p;
-                if (h->kernels_mask & 1) {
-                    if (variant == 40) { DISPATCH_FIELD(h, (check_rows_plain<F, 8><<<h->sm_count * 16, block, 0, h->stream>>>(m, o, kind))); }
-                    if (variant == 41) { DISPATCH_FIELD(h, (check_rows_plain<F, 6><<<h->sm_count * 12, block, 0, h->stream>>>(m, o, kind))); }
-                    if (variant == 42) { DISPATCH_FIELD(h, (check_rows_plain<F, 10><<<h->sm_count * 20, block, 0, h->stream>>>(m, o, kind))); }
-                    DISPATCH_FIELD(h, (check_rows<F, false, kVStaged, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc, kind)));
+    } else {
+        const int64_t v = h->variant < 0 ? 0 : h->variant;
+        const bool use_small = !(v & 1) && h->n_plain_rows > 0;
+        const bool fat_shadow = !(v & 2);
+        // product-heavy instances (synthetic) park az/bz in shared memory while C is folded
+        const bool park = (v & 4) || (h->variant < 0 && 2 * h->n_gen > h->nnz);
+        if (h->kernels_mask & 1) {
+            if (use_small) {
+                const int sgrid = (int)std::min<uint64_t>((h->n_rows + kSmallThreads - 1) / kSmallThreads, (uint64_t)h->sm_count * 6);
+                check_small<<<sgrid, kSmallThreads, 0, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
+                h->launches++;
+                const uint32_t* gl = (const uint32_t*)h->gen_rows.p;
+                const int lgrid = grid_for(h, h->n_gen_rows + h->n_plain_rows, block, 16);
+                if (park) {
+                    DISPATCH_FIELD(h, (check_rows<F, false, kVDefault | kVPark, 6, true><<<lgrid, block, 0, h->stream>>>(
+                                          m, o, h->fc, gl, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
+                } else {
+                    DISPATCH_FIELD(h, (check_rows<F, false, kVDefault, 6, true><<<lgrid, block, 0, h->stream>>>(
+                                          m, o, h->fc, gl, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
                 }
-                if (h->kernels_mask & 2) { DISPATCH_FIELD(h, (check_fat_rows<F, false, kVStaged, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat))); }
-            } break;
-            case 20: BP_LAUNCH_STAGED(true, false); break;
-            case 21: BP_LAUNCH_STAGED(false, true); break;
-            case 22: BP_LAUNCH_STAGED(true, true); break;
-            case -2: BP_LAUNCH(false, kVMagSkip | kVBitRow | kVPark, 6, kVMagSkip | kVBitRow, 4); break;  // product-heavy instances
-            default: BP_LAUNCH(false, kVMagSkip | kVBitRow, 6, kVMagSkip | kVBitRow, 4); break;          // measured best on gadget circuits
+                h->launches++;
+            } else {
+                if (park) { DISPATCH_FIELD(h, (check_rows<F, false, kVDefault | kVPark, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); }
+                else { DISPATCH_FIELD(h, (check_rows<F, false, kVDefault, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); }
+                h->launches++;
+            }
+        }
+        if ((h->kernels_mask & 2) && h->n_fat_rows) {
+            if (fat_shadow) {
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));
+            } else {
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));
+            }
+            h->launches++;
         }
     }
 #undef BP_LAUNCH
-#undef BP_LAUNCH_STAGED
-    h->launches += 2;
     CU(h, cudaGetLastError());
     return BP_OK;
 }
@@ -376,9 +398,10 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BP_E_CUDA);
     h->stream = h->own_stream;
-    if (cudaMalloc(&h->d_result, 16) != cudaSuccess) return bail(BP_E_OOM);
+    if (cudaMalloc(&h->d_result, 32) != cudaSuccess) return bail(BP_E_OOM);
     h->d_err = (unsigned int*)(h->d_result + 1);
-    if (cudaMemset(h->d_result, 0, 16) != cudaSuccess) return bail(BP_E_CUDA);
+    h->d_ndef = (uint32_t*)(h->d_result + 2);
+    if (cudaMemset(h->d_result, 0, 32) != cudaSuccess) return bail(BP_E_CUDA);
     if (cudaMallocHost(&h->h_pinned_small, 64) != cudaSuccess) return bail(BP_E_OOM);
     for (int s = 0; s < kNumStage; ++s) {
         if (cudaMallocHost(&h->h_stage[s], kStageBytes) != cudaSuccess) return bail(BP_E_OOM);
@@ -389,8 +412,8 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     const uint64_t one[4] = {1, 0, 0, 0};
     uint64_t idx = 0;
     size_t rv = (size_t)std::max<uint64_t>(reserve_vars, 1);
-    if (ensure(h, h->inputs, std::max<size_t>(32 * 1024, 32), 0) != BP_OK) return bail(BP_E_OOM);
-    if (reserve_vars && ensure(h, h->aux, rv * 32, 0) != BP_OK) return bail(BP_E_OOM);
+    if (ensure(h, h->inputs, 32 * 1024, 0) != BP_OK || ensure(h, h->inputs_s, 4 * 1024, 0) != BP_OK) return bail(BP_E_OOM);
+    if (reserve_vars && (ensure(h, h->aux, rv * 32, 0) != BP_OK || ensure(h, h->aux_s, rv * 4, 0) != BP_OK)) return bail(BP_E_OOM);
     if (reserve_rows && ensure(h, h->row_ptr, (3 * (size_t)reserve_rows + 1) * 4, 0) != BP_OK) return bail(BP_E_OOM);
     if (reserve_nnz) {
         if (ensure(h, h->cols, (size_t)reserve_nnz * 4, 0) != BP_OK) return bail(BP_E_OOM);
@@ -407,7 +430,8 @@ void bp_cs_free(bp_cs* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->scan_tmp, &h->scratch, &h->fat_rows, &h->row_kind})
+    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->inputs_s, &h->aux_s, &h->scan_tmp, &h->scratch, &h->u8_stage,
+                      &h->row_meta, &h->fat_rows, &h->gen_rows, &h->deferred})
         if (b->p) cudaFree(b->p);
     if (h->d_result) cudaFree(h->d_result);
     if (h->h_pinned_small) cudaFreeHost(h->h_pinned_small);
@@ -471,11 +495,17 @@ int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
     if (!std::strcmp(key, "launches")) { *v = h->launches; return BP_OK; }
     if (!std::strcmp(key, "gen_terms")) { *v = (int64_t)h->n_gen; return BP_OK; }
     if (!std::strcmp(key, "sm_count")) { *v = h->sm_count; return BP_OK; }
-    if (!std::strcmp(key, "fat_rows")) {  // number of rows the warp-per-row kernel handles (builds the plan if needed)
+    // plan statistics (build the plan if needed): rows per kernel
+    if (!std::strcmp(key, "fat_rows") || !std::strcmp(key, "plain_rows") || !std::strcmp(key, "generic_rows")) {
         CU(h, cudaSetDevice(h->device));
         int rc = ensure_plan(h);
         if (rc != BP_OK) return rc;
-        CU(h, cudaMemcpyAsync(h->h_pinned_small, (uint32_t*)h->fat_rows.p + h->n_rows, 4, cudaMemcpyDeviceToHost, h->stream));
+        *v = (int64_t)(key[0] == 'f' ? h->n_fat_rows : (key[0] == 'p' ? h->n_plain_rows : h->n_gen_rows));
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "deferred_rows")) {  // plain rows the last check handed to the full-width kernel
+        CU(h, cudaSetDevice(h->device));
+        CU(h, cudaMemcpyAsync(h->h_pinned_small, h->d_ndef, 4, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
         uint32_t n;
         std::memcpy(&n, h->h_pinned_small, 4);
@@ -500,15 +530,17 @@ int bp_cs_alloc(bp_cs* h, int is_aux, const uint64_t* vals, uint64_t n, uint64_t
     DevBuf& b = is_aux ? h->aux : h->inputs;
     uint64_t& cnt = is_aux ? h->n_aux : h->n_inputs;
     if (cnt + n >= 0x80000000ull) return fail(h, BP_E_RANGE, "more than 2^31-1 variables in one index space");
+    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
     int rc = ensure(h, b, (size_t)(cnt + n) * 32, (size_t)cnt * 32);
     if (rc != BP_OK) return rc;
+    if ((rc = ensure(h, bs, (size_t)(cnt + n) * 4, (size_t)cnt * 4)) != BP_OK) return rc;
     if (n) {
         rc = clear_err(h);
         if (rc != BP_OK) return rc;
         rc = upload(h, (char*)b.p + cnt * 32, vals, (size_t)n * 32);
         if (rc != BP_OK) return rc;
         DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>(
-                              (const uint4*)((char*)b.p + cnt * 32), n, h->d_err)));
+                              (const uint4*)((char*)b.p + cnt * 32), n, h->d_err, (uint32_t*)bs.p + cnt)));
         h->launches++;
         CU(h, cudaGetLastError());
         rc = check_err_word(h, "bp_cs_alloc");
@@ -527,6 +559,7 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
                                                    (unsigned long long)n, (unsigned long long)cnt);
     if (!n) return BP_OK;
     DevBuf& b = is_aux ? h->aux : h->inputs;
+    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, vals);
     if (e != cudaSuccess) (void)cudaGetLastError();
@@ -544,20 +577,67 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
             }
             if (!lt) return fail(h, BP_E_RANGE, "bp_cs_set_range: element %llu is not canonical (>= p)", (unsigned long long)i);
         }
-        return upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32);
+        int rc = clear_err(h);
+        if (rc != BP_OK) return rc;
+        if ((rc = upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32)) != BP_OK) return rc;
+        DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>(  // refreshes the shadows
+                              (const uint4*)((char*)b.p + first * 32), n, h->d_err, (uint32_t*)bs.p + first)));
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return BP_OK;
     }
     // bulk witness refresh: copy at link speed, validate on the device (on BP_E_RANGE the range's contents are unspecified)
     int rc = clear_err(h);
     if (rc != BP_OK) return rc;
     if ((rc = upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32)) != BP_OK) return rc;
     DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint4*)((char*)b.p + first * 32), n,
-                                                                                          h->d_err)));
+                                                                                          h->d_err, (uint32_t*)bs.p + first)));
     h->launches++;
     CU(h, cudaGetLastError());
     return check_err_word(h, "bp_cs_set_range");
 }
 
 int bp_cs_set(bp_cs* h, int is_aux, uint64_t idx, const uint64_t v[4]) { return bp_cs_set_range(h, is_aux, idx, 1, v); }
+
+// bytes -> device staging -> widen_u8 into elements [first, first+n) of the index space (capacity already ensured)
+static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals) {
+    int rc = ensure(h, h->u8_stage, (size_t)n, 0);
+    if (rc != BP_OK) return rc;
+    if ((rc = upload(h, h->u8_stage.p, vals, (size_t)n)) != BP_OK) return rc;
+    DevBuf& b = is_aux ? h->aux : h->inputs;
+    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
+    widen_u8<<<grid_for(h, 2 * n, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p, n, (uint4*)((char*)b.p + first * 32),
+                                                                 (uint32_t*)bs.p + first);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_cs_alloc_u8(bp_cs* h, int is_aux, const uint8_t* vals, uint64_t n, uint64_t* first_index) {
+    if (!h || (!vals && n)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    DevBuf& b = is_aux ? h->aux : h->inputs;
+    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
+    uint64_t& cnt = is_aux ? h->n_aux : h->n_inputs;
+    if (cnt + n >= 0x80000000ull) return fail(h, BP_E_RANGE, "more than 2^31-1 variables in one index space");
+    int rc = ensure(h, b, (size_t)(cnt + n) * 32, (size_t)cnt * 32);
+    if (rc != BP_OK) return rc;
+    if ((rc = ensure(h, bs, (size_t)(cnt + n) * 4, (size_t)cnt * 4)) != BP_OK) return rc;
+    if (n && (rc = widen_into(h, is_aux, cnt, n, vals)) != BP_OK) return rc;
+    if (first_index) *first_index = cnt;
+    cnt += n;
+    return BP_OK;
+}
+
+int bp_cs_set_range_u8(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals) {
+    if (!h || (!vals && n)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
+    if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "set_range_u8 [%llu,+%llu) exceeds %llu", (unsigned long long)first,
+                                                   (unsigned long long)n, (unsigned long long)cnt);
+    if (!n) return BP_OK;
+    return widen_into(h, is_aux, first, n, vals);
+}
 
 int bp_cs_witness(bp_cs* h, int is_aux, uint64_t first, uint64_t n, uint64_t* out) {
     if (!h || (!out && n)) return BP_E_ARG;
@@ -756,8 +836,10 @@ int bp_cs_synth_witness(bp_cs* h, uint64_t seed, uint64_t n_vars, uint64_t n_inp
     int rc;
     if ((rc = ensure(h, h->inputs, (size_t)n_inputs * 32, 0)) != BP_OK) return rc;
     if ((rc = ensure(h, h->aux, (size_t)std::max<uint64_t>(n_vars - n_inputs, 1) * 32, 0)) != BP_OK) return rc;
-    DISPATCH_FIELD(h, (synth_witness<F><<<grid_for(h, n_vars, 256, 8), 256, 0, h->stream>>>((uint4*)h->inputs.p, (uint4*)h->aux.p, seed,
-                                                                                          n_vars, n_inputs)));
+    if ((rc = ensure(h, h->inputs_s, (size_t)n_inputs * 4, 0)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->aux_s, (size_t)std::max<uint64_t>(n_vars - n_inputs, 1) * 4, 0)) != BP_OK) return rc;
+    DISPATCH_FIELD(h, (synth_witness<F><<<grid_for(h, n_vars, 256, 8), 256, 0, h->stream>>>(
+                          (uint4*)h->inputs.p, (uint4*)h->aux.p, (uint32_t*)h->inputs_s.p, (uint32_t*)h->aux_s.p, seed, n_vars, n_inputs)));
     h->launches++;
     CU(h, cudaGetLastError());
     h->n_inputs = n_inputs;

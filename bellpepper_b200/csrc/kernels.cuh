@@ -43,6 +43,9 @@ struct CsrView {
     const uint4* __restrict__ vals;
     const uint4* __restrict__ inputs;
     const uint4* __restrict__ aux;
+    const uint32_t* __restrict__ inputs_s;  // witness shadows: the value when it is < 2^24, else kShadowBig
+    const uint32_t* __restrict__ aux_s;
+    const uint32_t* __restrict__ row_meta;  // plan: |A| | |B|<<8 | |C|<<16 | RowKind<<24   (lengths 255,0,0 = not encodable)
     uint32_t n_rows;
     uint32_t n_inputs;
     uint32_t n_aux;
@@ -58,13 +61,27 @@ struct CheckOut {
     uint4* cz;
 };
 
-// Plan: what kind of row is it (one byte per row, built by classify_rows)?
-enum RowKind : uint8_t {
-    kRowGeneric = 0,   // check_rows (full arithmetic)
-    kRowPlain = 1,     // every term is a small-coefficient class and sum|c| of C is <= 5: check_rows_plain can decide it
-    kRowFat = 2,       // check_fat_rows
-    kRowDeferred = 3   // a plain row whose VALUES needed the full product this time: check_rows picks it up and resets it
+// Plan: what kind of row is it (top byte of row_meta, built by build_row_meta)?
+enum RowKind : uint32_t {
+    kRowGeneric = 0,  // check_rows (full arithmetic)
+    kRowPlain = 1,    // every term has a small-coefficient class, sum|c| <= 7 in A and in B, <= 5 in C, every length <= 254:
+                      // check_small decides it from the witness shadows when every value it touches is small
+    kRowFat = 2       // check_fat_rows
 };
+constexpr uint32_t kMetaNoLens = 255u;
+constexpr uint32_t kSmallCap = 512;  // words per staging buffer of check_small; a plain row has at most this many terms
+
+// Witness shadow: a second, 4-byte copy of every witness element, maintained wherever the witness is written.
+// Gadget circuits (sha256, blake2s, boolean, uint32) have bit- or byte-valued witnesses; a row whose operands are all
+// small is decided in 64-bit integer arithmetic from 4-byte gathers, and a full-width coefficient times a small value is
+// one 1x8 product instead of 8x8.  The shortcut is taken on VALUES: any element >= 2^24 sends its rows down the
+// full-width path, so every witness gets the verdict of the general arithmetic.
+constexpr uint32_t kSmallBits = 24;
+constexpr uint32_t kShadowBig = 0xffffffffu;
+__host__ __device__ __forceinline__ uint32_t shadow_of(const uint32_t* x /*8*/) {
+    const uint32_t hi = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
+    return (hi == 0u && x[0] < (1u << kSmallBits)) ? x[0] : kShadowBig;
+}
 
 __device__ __forceinline__ void ld8(uint32_t* x, const uint4* p) {
     const uint4 lo = __ldg(p), hi = __ldg(p + 1);
@@ -139,6 +156,7 @@ constexpr int kVMagSkip = 2;   // plain A/B sums below 2p are used unreduced
 constexpr int kVBitRow = 4;    // rows whose Az or Bz is 0/1 (and C is plain) are decided without any multiplication
 constexpr int kVPark = 8;      // az / bz wait in shared memory while C is folded (fewer live registers)
 constexpr int kVPrefetch = 16; // L1 prefetch of every witness line of the row before the first term is folded
+constexpr int kVShadow = 32;   // warp-per-row kernel: use the witness shadows (small operand => 1x8 product / integer add)
 
 // Terms k0, k0+STEP, ... < k1.  STEP = 1 for the thread-per-row kernel, 32 for a lane of the warp-per-row kernel.
 template <int F, int RIPPLE, uint32_t STEP, bool PIPE>
@@ -287,18 +305,19 @@ __device__ __forceinline__ void publish_first_bad(uint32_t my_bad, const CsrView
 }
 
 // ---- K1 / K2, thin rows: one thread per constraint -------------------------------------------------------------------
-template <int F, bool EMIT, int V, int MB>
-__global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, FieldConsts fc, uint8_t* __restrict__ kind = nullptr) {
+// LIST: the rows to do are list_a[0..n_a) (static: the plan's generic rows) followed by list_b[0..*n_b) (dynamic: plain
+// rows that check_small deferred because an operand was not small); otherwise every row that is not fat.
+template <int F, bool EMIT, int V, int MB, bool LIST = false>
+__global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, FieldConsts fc, const uint32_t* __restrict__ list_a = nullptr,
+                                                      uint32_t n_a = 0, const uint32_t* __restrict__ list_b = nullptr,
+                                                      const uint32_t* __restrict__ n_b = nullptr) {
     constexpr bool PIPE = (V & kVPipe) != 0, PARK = (V & kVPark) != 0;
     __shared__ uint32_t s_az[PARK ? 8 : 1][128], s_bz[PARK ? 8 : 1][128];
     uint32_t my_bad = 0xffffffffu;
     unsigned int my_err = 0;
-    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < m.n_rows; row += gridDim.x * blockDim.x) {
-        if (kind) {  // rows already decided by check_rows_plain (or owned by check_fat_rows) are not ours
-            const uint8_t kd = kind[row];
-            if (kd == kRowPlain || kd == kRowFat) continue;
-            if (kd == kRowDeferred) kind[row] = kRowPlain;  // picked up: back to its static kind for the next check
-        }
+    const uint32_t n_todo = LIST ? n_a + *n_b : m.n_rows;
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n_todo; it += gridDim.x * blockDim.x) {
+        const uint32_t row = LIST ? (it < n_a ? __ldg(list_a + it) : list_b[it - n_a]) : it;
         const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
                        p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
         if (p3 - p0 > m.fat_terms) continue;  // check_fat_rows does it
@@ -345,115 +364,278 @@ __global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, Fie
     publish_first_bad(my_bad, m, o, my_err);
 }
 
-// ---- plan: what kind of row is it? -------------------------------------------------------------------------------------
-
-__global__ void classify_rows(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, const uint4* __restrict__ vals,
-                              uint32_t n_rows, uint32_t fat_terms, uint8_t* __restrict__ kind) {
+// ---- plan: row_meta (lengths + kind), one thread per row ------------------------------------------------------------
+__global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, const uint4* __restrict__ vals,
+                               uint32_t n_rows, uint32_t fat_terms, uint32_t* __restrict__ row_meta, uint32_t* __restrict__ counts /*3*/) {
+    uint32_t n_kind[3] = {0, 0, 0};
     for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
-        const uint32_t p0 = row_ptr[3 * (size_t)row], p2 = row_ptr[3 * (size_t)row + 2], p3 = row_ptr[3 * (size_t)row + 3];
-        uint8_t k = kRowPlain;
+        const uint32_t p0 = row_ptr[3 * (size_t)row], p1 = row_ptr[3 * (size_t)row + 1], p2 = row_ptr[3 * (size_t)row + 2],
+                       p3 = row_ptr[3 * (size_t)row + 3];
+        const uint32_t la = p1 - p0, lb = p2 - p1, lc = p3 - p2;
+        const bool enc = la < kMetaNoLens && lb < kMetaNoLens && lc < kMetaNoLens;
+        uint32_t k = kRowPlain;
         if (p3 - p0 > fat_terms) {
             k = kRowFat;
+        } else if (!enc || p3 - p0 > kSmallCap) {
+            k = kRowGeneric;
         } else {
-            uint32_t mag_c = 0;
+            uint32_t mag[3] = {0, 0, 0};
             for (uint32_t t = p0; t < p3 && k == kRowPlain; ++t) {
                 const uint32_t cls = (__ldg(cols + t) >> kColClsShift) & 7u;
+                const int lc_i = t < p1 ? 0 : (t < p2 ? 1 : 2);
                 if (cls == kClsGen) k = kRowGeneric;
-                if (t >= p2) {
-                    if (cls == kClsP1 || cls == kClsM1) mag_c += 1;
-                    else if (cls == kClsP2 || cls == kClsM2) mag_c += 2;
-                    else if (cls == kClsPS || cls == kClsMS) {
-                        const uint32_t sm = __ldg(reinterpret_cast<const uint32_t*>(vals + 2 * (size_t)t));
-                        mag_c += sm > 8u ? 8u : sm;
-                    }
-                    if (mag_c > 5u) k = kRowGeneric;
+                else if (cls == kClsP1 || cls == kClsM1) mag[lc_i] += 1;
+                else if (cls == kClsP2 || cls == kClsM2) mag[lc_i] += 2;
+                else if (cls == kClsPS || cls == kClsMS) {
+                    const uint32_t sm = __ldg(reinterpret_cast<const uint32_t*>(vals + 2 * (size_t)t));
+                    mag[lc_i] += sm > 8u ? 8u : sm;
                 }
+                if (mag[0] > 7u || mag[1] > 7u || mag[2] > 5u) k = kRowGeneric;
             }
         }
-        kind[row] = k;
+        row_meta[row] = (enc ? (la | (lb << 8) | (lc << 16)) : kMetaNoLens) | (k << 24);
+        n_kind[0] += k == kRowGeneric;
+        n_kind[1] += k == kRowPlain;
+        n_kind[2] += k == kRowFat;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // all threads are back together here
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, n_kind[i]);
+        if ((threadIdx.x & 31u) == 0 && tot) atomicAdd(counts + i, tot);
     }
 }
 
-// Fold the plain terms [k0,k1) into a 9-limb accumulator (sum < 8p by construction of the row kind).
-template <int F>
-__device__ __forceinline__ void fold_plain(uint32_t* acc /*9*/, uint32_t k0, uint32_t k1, const CsrView& m, unsigned int& err, uint32_t& mag) {
+// ---- K1, plain rows with small operands: 64-bit integer arithmetic on the witness shadows ---------------------------------
+// A warp owns 32 consecutive rows.  Lane l reads row_meta[row0+l] (coalesced); a shuffle scan turns the lengths into term
+// offsets; the terms of the block are then handled TERM-parallel -- lane-contiguous column words (coalesced), one 4-byte
+// shadow gather each, all of a round's loads in flight together -- and each term's signed contribution c*w is parked in
+// shared memory; finally lane l sums its own row's three ranges and tests  Az*Bz + sum_C(-c)w == 0  as integers
+// (|Az|,|Bz| < 2^27, |Cz| < 2^27: nothing wraps, and |X| < p so X = 0 mod p iff X = 0).
+// A row with an operand that is not small is appended to `deferred` and decided by check_rows<LIST>.
+constexpr int kSmallThreads = 256;
+constexpr int32_t kPoison = (int32_t)0x80000000;
+
+__device__ __forceinline__ uint32_t ldg_early(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+// TMA bulk copy global -> shared (bytes and both addresses multiples of 16), completion on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+
+// A term's contribution from the shadows, in two branch-free halves so that the gathers of several terms are issued
+// back to back (a branch between two gathers makes the second wait for the first).
+//   small_gather : column word -> shadow of its variable (index 0 of the inputs, i.e. ONE, stands in for "no load needed")
+//   small_value  : signed contribution c*w, kPoison when the operand is not small or the coefficient is full-width
+__device__ __forceinline__ uint32_t small_gather(uint32_t col, const CsrView& m, unsigned int& err) {
+    const uint32_t cls = (col >> kColClsShift) & 7u;
+    const uint32_t idx = col & kColIdxMask;
+    const bool is_aux = (col & kColAux) != 0;
+    const bool oob = idx >= (is_aux ? m.n_aux : m.n_inputs);
+    const bool skip = oob || cls == kClsZero;
+    if (oob && cls != kClsZero) err = 1;
+    const uint32_t* p = (is_aux && !skip) ? m.aux_s : m.inputs_s;
+    return __ldg(p + (skip ? 0u : idx));
+}
+__device__ __forceinline__ int32_t small_value(uint32_t col, uint32_t s, uint32_t k, const CsrView& m) {
+    const uint32_t cls = (col >> kColClsShift) & 7u;
+    // multiplier by class: GEN 0, P1 +1, M1 -1, P2 +2, M2 -2, PS +s, MS -s, ZERO 0  (one sign-extended nibble each)
+    uint32_t mult = (uint32_t)(((int32_t)(0x0F1E2F10u << (28u - 4u * cls))) >> 28);
+    if (cls == kClsPS || cls == kClsMS) mult *= __ldg(reinterpret_cast<const uint32_t*>(m.vals + 2 * (size_t)k));  // rare
+    const int32_t v = (int32_t)(mult * s);
+    return cls == kClsZero ? 0 : ((cls == kClsGen || s == kShadowBig) ? kPoison : v);
+}
+
+// Sum of n staged contributions; returns true when one of them was poisoned (operand not small, or a GEN coefficient).
+__device__ __forceinline__ bool small_sum(const int32_t* st, uint32_t n, int32_t& sum) {
+    bool bad = false;
+    int32_t a = 0;
 #pragma unroll 1
-    for (uint32_t k = k0; k < k1; ++k) {
-        const uint32_t col = __ldg(m.cols + k);
-        const uint32_t cls = (col >> kColClsShift) & 7u;
-        if (cls == kClsZero) continue;
-        const uint32_t idx = col & kColIdxMask;
-        const bool is_aux = (col & kColAux) != 0;
-        if (idx >= (is_aux ? m.n_aux : m.n_inputs)) { err = 1; continue; }
-        uint32_t w[8];
-        ld8(w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx);
-        if (cls == kClsM1 || cls == kClsM2 || cls == kClsMS) {
-            uint32_t n[8];
-            neg_mod<F>(n, w);
+    for (uint32_t j = 0; j < n; ++j) {
+        const int32_t v = st[j];
+        bad |= (v == kPoison);
+        a += v;
+    }
+    sum = a;
+    return bad;
+}
+
+// buf[0..nt) holds column words (FROM_SMEM) or is filled from cols[k0..k0+nt): replace every word by its contribution.
+// Term-parallel: lane-contiguous words, four rounds of shadow gathers in flight per lane.
+template <bool FROM_SMEM>
+__device__ __forceinline__ void small_stage(uint32_t* buf, uint32_t nt, uint32_t k0, const CsrView& m, unsigned int& err) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t t0 = 0; t0 < nt; t0 += 128u) {
+        uint32_t col[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = n[i];
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t t = t0 + 32u * j + lane;
+            col[j] = t < nt ? (FROM_SMEM ? buf[t] : __ldg(m.cols + k0 + t)) : (kClsZero << kColClsShift);
         }
-        if (cls == kClsP1 || cls == kClsM1) {
-            acc_add8<9>(acc, w);
-            mag += 1;
-        } else if (cls == kClsP2 || cls == kClsM2) {
-            acc_add8<9>(acc, w);
-            acc_add8<9>(acc, w);
-            mag += 2;
-        } else {
-            const uint32_t sm = __ldg(reinterpret_cast<const uint32_t*>(m.vals + 2 * (size_t)k));
-            acc_mad_small<9>(acc, w, sm);
-            mag += sm > 8u ? 8u : sm;
+        uint32_t sh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh[j] = small_gather(col[j], m, err);
+        int32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = small_value(col[j], sh[j], k0 + t0 + 32u * j + lane, m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t t = t0 + 32u * j + lane;
+            if (t < nt) buf[t] = (uint32_t)v[j];
         }
     }
 }
 
-template <int F> __device__ __forceinline__ void finish_plain(uint32_t* out /*8*/, const uint32_t* acc /*9*/, uint32_t mag) {
-    if (mag <= 2) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) out[i] = acc[i];
-    } else {
-        reduce_8p<F>(out, acc);
+// Row phase: the lane's row (if `mine`) has its contributions at q[0 .. la+lb+lc).  Deferred rows are appended warp-aggregated.
+__device__ __forceinline__ void small_rows(const int32_t* q, bool mine, uint32_t la, uint32_t lb, uint32_t lc, uint32_t row, uint32_t& my_bad,
+                                           uint32_t* __restrict__ deferred, uint32_t* __restrict__ n_deferred) {
+    const uint32_t lane = threadIdx.x & 31u;
+    bool defer = false;
+    if (mine) {
+        int32_t a, b, c;
+        bool bad = small_sum(q, la, a);
+        bad |= small_sum(q + la, lb, b);
+        bad |= small_sum(q + la + lb, lc, c);
+        if (bad) defer = true;
+        else if ((long long)a * (long long)b + (long long)c != 0ll && row < my_bad) my_bad = row;
+    }
+    const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
+    if (dmask) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(n_deferred, (uint32_t)__popc(dmask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (defer) deferred[base + (uint32_t)__popc(dmask & ((1u << lane) - 1u))] = row;
     }
 }
 
-// ---- K1, plain rows: additions only.  Small register footprint -> 8 CTAs/SM; rows whose values need the full product
-// (neither Az nor Bz is 0/1) are handed to check_rows through the kind byte.
-template <int F, int MB>
-__global__ void __launch_bounds__(128, MB) check_rows_plain(CsrView m, CheckOut o, uint8_t* __restrict__ kind) {
+// Per-warp software pipeline over the warp's blocks b, b+W, b+2W, ...:
+//   two blocks ahead   the block's term range [row_ptr[96b'], row_ptr[96(b'+1)]) is loaded into registers,
+//   one block ahead    its column words are brought into shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier,
+//                      double-buffered) and its row_meta word is loaded into a register,
+//   current block      scan of the lengths -> term offsets, contributions in place of the column words, row sums.
+// Only the shadow gathers of the current block are exposed latency.  A block whose range does not fit the buffer (it
+// contains a fat row) is read with plain loads in groups of rows that fit.
+__global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, CheckOut o, uint32_t* __restrict__ deferred,
+                                                                uint32_t* __restrict__ n_deferred) {
+    __shared__ __align__(16) uint32_t s_buf[kSmallThreads / 32][2][kSmallCap];
+    __shared__ __align__(8) unsigned long long s_bar[kSmallThreads / 32][2];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    if (lane == 0) {
+        mbar_init(&s_bar[wib][0], 1);
+        mbar_init(&s_bar[wib][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     uint32_t my_bad = 0xffffffffu;
     unsigned int my_err = 0;
-    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < m.n_rows; row += gridDim.x * blockDim.x) {
-        if (kind[row] != kRowPlain) continue;
-        const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
-                       p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
-        uint32_t acc[9], az[8], bz[8];
-        uint32_t mag = 0;
-        zeron<9>(acc);
-        fold_plain<F>(acc, p0, p1, m, my_err, mag);
-        finish_plain<F>(az, acc, mag);
-        mag = 0;
-        zeron<9>(acc);
-        fold_plain<F>(acc, p1, p2, m, my_err, mag);
-        finish_plain<F>(bz, acc, mag);
-        const uint32_t sa = small01(az), sb = small01(bz);
-        if (sa == 2u && sb == 2u) {  // needs Az*Bz: not ours
-            kind[row] = kRowDeferred;
-            continue;
+    const uint32_t n_blocks = (m.n_rows + 31u) / 32u;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t b0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    // (volatile: issued HERE, one iteration before they are needed, not sunk to their first use)
+    auto range_lo = [&](uint32_t b) { return ldg_early(m.row_ptr + 96 * (size_t)b); };
+    auto range_hi = [&](uint32_t b) { return ldg_early(m.row_ptr + 3 * (size_t)min(32u * (b + 1u), m.n_rows)); };
+    auto load_meta = [&](uint32_t b) { return 32u * b + lane < m.n_rows ? ldg_early(m.row_meta + 32u * b + lane) : (kRowGeneric << 24); };
+    // copy the words [kb & ~3, roundup4(ke)) of cols into a stage; false when they do not fit
+    auto issue_copy = [&](uint32_t kb, uint32_t ke, uint32_t stage) {
+        const uint32_t w0 = kb & ~3u, w1 = (ke + 3u) & ~3u;
+        if (w1 - w0 > kSmallCap) return false;
+        if (ke > kb && lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our generic-proxy accesses of the stage are done
+            bulk_g2s(s_buf[wib][stage], m.cols + w0, (w1 - w0) * 4u, &s_bar[wib][stage]);
         }
-        mag = 0;
-        zeron<9>(acc);
-        fold_plain<F>(acc, p2, p3, m, my_err, mag);  // < 5p by the row kind
-        const bool zero = (sa == 0u) || (sb == 0u);
-        uint32_t prod[8];
+        return true;
+    };
+
+    if (b0 >= n_blocks) {  // (keeps publish_first_bad's barriers uniform)
+        publish_first_bad(my_bad, m, o, my_err);
+        return;
+    }
+    // prologue: block b0 staged, block b0+W's range in registers
+    uint32_t kb_cur = range_lo(b0), ke_cur = range_hi(b0);
+    uint32_t meta_cur = load_meta(b0);
+    bool copied_cur = issue_copy(kb_cur, ke_cur, 0);
+    uint32_t kb_nxt = 0, ke_nxt = 0;
+    if (b0 + n_warps < n_blocks) { kb_nxt = range_lo(b0 + n_warps); ke_nxt = range_hi(b0 + n_warps); }
+    uint32_t it = 0, phase = 0;  // phase bit s: parity the next wait on stage s expects (copies and waits pair up per stage)
+    for (uint32_t blk = b0; blk < n_blocks; blk += n_warps, ++it) {
+        const uint32_t stage = it & 1u;
+        const uint32_t b_nxt = blk + n_warps, b_nn = blk + 2u * n_warps;
+        // 1. loads for the blocks ahead (consumed in the next iteration)
+        uint32_t meta_nxt = kRowGeneric << 24, kb_nn = 0, ke_nn = 0;
+        if (b_nxt < n_blocks) meta_nxt = load_meta(b_nxt);
+        if (b_nn < n_blocks) { kb_nn = range_lo(b_nn); ke_nn = range_hi(b_nn); }
+        // 2. the next block's column words: the other stage is free (its rows were finished before the last __syncwarp)
+        bool copied_nxt = false;
+        if (b_nxt < n_blocks) copied_nxt = issue_copy(kb_nxt, ke_nxt, stage ^ 1u);
+        // 3. the current block
+        const uint32_t row0 = blk * 32u, row = row0 + lane;
+        const uint32_t la = meta_cur & 255u, lb = (meta_cur >> 8) & 255u, lc = (meta_cur >> 16) & 255u, kind = meta_cur >> 24;
+        const bool noenc = la == kMetaNoLens;
+        const uint32_t noenc_mask = __ballot_sync(0xffffffffu, noenc);
+        const bool any_plain = __ballot_sync(0xffffffffu, kind == kRowPlain) != 0u;
+        uint32_t nt = la + lb + lc;
+        if (noenc && any_plain) nt = __ldg(m.row_ptr + 3 * (size_t)row + 3) - __ldg(m.row_ptr + 3 * (size_t)row);
+        uint32_t incl = nt;  // inclusive scan of the term counts
 #pragma unroll
-        for (int i = 0; i < 8; ++i) prod[i] = zero ? 0u : (sa == 1u ? bz[i] : az[i]);
-        acc_add8<9>(acc, prod);  // < 5p + 2p
-        uint32_t r[8], nz = 0;
-        reduce_8p<F>(r, acc);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) nz |= r[i];
-        if (nz != 0 && row < my_bad) my_bad = row;
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const uint32_t off = incl - nt;
+        uint32_t* buf = s_buf[wib][stage];
+        if (copied_cur) {
+            if (ke_cur > kb_cur) {
+                mbar_wait(&s_bar[wib][stage], (phase >> stage) & 1u);
+                phase ^= 1u << stage;
+            }
+            if (any_plain) {
+                uint32_t* terms = buf + (kb_cur & 3u);
+                small_stage<true>(terms, ke_cur - kb_cur, kb_cur, m, my_err);
+                __syncwarp();
+                small_rows(reinterpret_cast<const int32_t*>(terms) + off, kind == kRowPlain, la, lb, lc, row, my_bad, deferred, n_deferred);
+            }
+        } else if (any_plain) {
+            uint32_t done = 0;
+            while (done < 32u) {
+                const uint32_t rest = noenc_mask >> done;
+                if (rest & 1u) { ++done; continue; }
+                const uint32_t stop = rest ? done + (uint32_t)__ffs((int)rest) - 1u : 32u;  // first lane we cannot stage
+                const uint32_t base_off = __shfl_sync(0xffffffffu, off, done);
+                const bool fits = lane >= done && lane < stop && (incl - base_off) <= kSmallCap;
+                const uint32_t r = max(1u, (uint32_t)__popc(__ballot_sync(0xffffffffu, fits)));
+                const uint32_t nt_g = min(kSmallCap, __shfl_sync(0xffffffffu, incl, done + r - 1u) - base_off);
+                small_stage<false>(buf, nt_g, kb_cur + base_off, m, my_err);
+                __syncwarp();
+                // (a generic row longer than the buffer can only be the single row of its group: it is not plain, nobody reads it)
+                small_rows(reinterpret_cast<const int32_t*>(buf) + (off - base_off), lane >= done && lane < done + r && kind == kRowPlain, la,
+                           lb, lc, row, my_bad, deferred, n_deferred);
+                __syncwarp();  // the buffer is reused by the next group
+                done += r;
+            }
+        }
+        __syncwarp();  // every lane is done with this stage before it is refilled
+        // 4. rotate
+        kb_cur = kb_nxt; ke_cur = ke_nxt; meta_cur = meta_nxt; copied_cur = copied_nxt;
+        kb_nxt = kb_nn; ke_nxt = ke_nn;
     }
     publish_first_bad(my_bad, m, o, my_err);
 }
@@ -469,16 +651,166 @@ __device__ __forceinline__ void warp_sum17(uint32_t* acc) {
     }
 }
 
-// One LC [k0,k1) by a whole warp: lanes stride the terms (two terms' loads in flight per lane), then the partial sums
-// are combined.  Every lane returns with the total, the "a full product was folded" flag and the plain magnitude.
-template <int F, int RIPPLE, bool PIPE>
+// Small positive / negative plain contributions of one lane to a C LC, kept as integers until the LC ends:
+//   sum_pos = sum mag*w (class P*),   sum_neg = sum mag*w and cnt = sum mag (class M*: the term is mag*(p - w)).
+struct SmallSums {
+    uint64_t pos_lo = 0, neg_lo = 0, cnt = 0;
+    uint32_t pos_hi = 0, neg_hi = 0;
+    uint32_t used = 0;
+};
+
+// acc (17 limbs) += pos + cnt*p - neg      (cnt*p >= neg because every w < p)
+template <int F> __device__ __forceinline__ void fold_small_sums(uint32_t* acc, const SmallSums& ss) {
+    uint32_t t[12];
+    zeron<12>(t);
+    uint32_t pl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pl[i] = PL<F>(i);
+    acc_mad_small<12>(t, pl, (uint32_t)ss.cnt);
+    acc_mad_small<11>(t + 1, pl, (uint32_t)(ss.cnt >> 32));
+    uint32_t x[12];
+    zeron<12>(x);
+    x[0] = (uint32_t)ss.neg_lo; x[1] = (uint32_t)(ss.neg_lo >> 32); x[2] = ss.neg_hi;
+    (void)subn<12>(t, t, x);
+    x[0] = (uint32_t)ss.pos_lo; x[1] = (uint32_t)(ss.pos_lo >> 32); x[2] = ss.pos_hi;
+    (void)addn<12>(t, t, x);
+    uint32_t c = addn<12>(acc, acc, t);
+#pragma unroll
+    for (int i = 12; i < 17; ++i) {
+        const uint32_t v = acc[i] + c;
+        c = v < c ? 1u : 0u;
+        acc[i] = v;
+    }
+}
+
+// One lane's terms k0, k0+32, ... < k1 of a fat LC, with the witness shadows: a small operand turns a full-width
+// coefficient into a 1x8 product and a plain coefficient into two 64-bit additions; anything else takes the general path.
+// IS_C: C LCs take every class; A/B LCs only their GEN terms (a plain A/B LC has at most 7 non-zero terms and a value
+// bound the general path maintains).
+// Is term (col, shadow) one the shadow pass cannot take?  (operand not small; or a plain term of an A/B LC)
+template <bool IS_C> __device__ __forceinline__ bool shadow_slow(uint32_t cls, uint32_t sh) {
+    return cls != kClsZero && (sh == kShadowBig || (!IS_C && cls != kClsGen));
+}
+
+constexpr int kFatU = 8;  // terms per lane and round in the shadow pass of the warp-per-row kernel
+struct FatStage {
+    uint4 c[kFatU][2][32];  // [term of the round][half][lane]: conflict-free 16-byte accesses
+};
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+// Pass 1 over a lane's terms k0, k0+32, ... < k1: everything whose operand is small.  Products go to a 10-limb
+// accumulator (c*s < 2^280, so 2^40 of them fit), plain terms to `ss`.  Returns true when a term was left for pass 2.
+// kFatU terms per lane and round: their column words (coalesced), then their shadows (4-byte gathers), then the
+// coefficients of the terms that need one (operand not zero; cp.async straight into shared memory, no registers held)
+// are each fetched together, so a round costs three memory round trips for 256 terms of the warp.
+template <int F, bool IS_C>
+__device__ __forceinline__ bool fold_lane_shadow(uint32_t* acc10, uint32_t k0, uint32_t k1, const CsrView& m, FatStage& fs, unsigned int& err,
+                                                 uint32_t& gen, SmallSums& ss) {
+    const uint32_t lane = threadIdx.x & 31u;
+    bool any_slow = false;
+#pragma unroll 1
+    for (uint32_t kb = k0; kb < k1; kb += 32u * kFatU) {
+        uint32_t col[kFatU], sh[kFatU];
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) col[j] = kb + 32u * j < k1 ? __ldg(m.cols + kb + 32u * j) : (kClsZero << kColClsShift);
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) {  // branch-free: the gathers are issued back to back
+            const uint32_t idx = col[j] & kColIdxMask;
+            if (idx >= ((col[j] & kColAux) ? m.n_aux : m.n_inputs) && ((col[j] >> kColClsShift) & 7u) != kClsZero) {
+                err = 1;
+                col[j] = kClsZero << kColClsShift;  // reported; contributes nothing
+            }
+            sh[j] = small_gather(col[j], m, err);
+        }
+        uint32_t need_c = 0;
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) {
+            const uint32_t cls = (col[j] >> kColClsShift) & 7u;
+            if (shadow_slow<IS_C>(cls, sh[j])) { any_slow = true; continue; }
+            if (cls == kClsGen) {
+                gen = 1;
+                if (sh[j] != 0u) {
+                    need_c |= 1u << j;
+                    const uint4* src = m.vals + 2 * (size_t)(kb + 32u * j);
+                    cp_async16(&fs.c[j][0][lane], src);
+                    cp_async16(&fs.c[j][1][lane], src + 1);
+                }
+            }
+        }
+        cp_async_wait_all();  // each lane reads back only what it copied itself: no cross-lane hazard
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) {
+            const uint32_t cls = (col[j] >> kColClsShift) & 7u;
+            if ((need_c >> j) & 1u) {
+                uint32_t c[8];
+                const uint4 lo = fs.c[j][0][lane], hi = fs.c[j][1][lane];
+                c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w;
+                c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
+                acc_mad_small<10>(acc10, c, sh[j]);
+            } else if (IS_C && cls != kClsZero && cls != kClsGen && sh[j] != kShadowBig && sh[j] != 0u) {
+                uint32_t mg = (cls == kClsP1 || cls == kClsM1) ? 1u : 2u;
+                if (cls >= kClsPS) mg = __ldg(reinterpret_cast<const uint32_t*>(m.vals + 2 * (size_t)(kb + 32u * j)));
+                const uint64_t v = (uint64_t)mg * sh[j];
+                if (cls == kClsP1 || cls == kClsP2 || cls == kClsPS) {
+                    ss.pos_lo += v;
+                    ss.pos_hi += ss.pos_lo < v ? 1u : 0u;
+                } else {
+                    ss.neg_lo += v;
+                    ss.neg_hi += ss.neg_lo < v ? 1u : 0u;
+                    ss.cnt += mg;
+                }
+                ss.used = 1;
+            }
+        }
+    }
+    return any_slow;
+}
+
+// Pass 2 (only when pass 1 left something): the terms pass 1 skipped, by the general path.
+template <int F, int RIPPLE, bool IS_C>
+__device__ __forceinline__ void fold_lane_slow(uint32_t* acc, uint32_t k0, uint32_t k1, const CsrView& m, unsigned int& err, uint32_t& gen,
+                                               uint32_t& mag) {
+#pragma unroll 1
+    for (uint32_t k = k0; k < k1; k += 32u) {
+        const uint32_t col = __ldg(m.cols + k);
+        const uint32_t cls = (col >> kColClsShift) & 7u;
+        if (cls == kClsZero) continue;
+        const uint32_t idx = col & kColIdxMask;
+        const bool is_aux = (col & kColAux) != 0;
+        if (idx >= (is_aux ? m.n_aux : m.n_inputs)) continue;  // reported by pass 1
+        if (!shadow_slow<IS_C>(cls, __ldg((is_aux ? m.aux_s : m.inputs_s) + idx))) continue;
+        TermW t;
+        t.cls = cls;
+        ld8(t.w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx);
+        apply_term<F, RIPPLE>(acc, t, k, m, gen, mag);
+    }
+}
+
+// One LC [k0,k1) by a whole warp: lanes stride the terms, then the partial sums are combined.  Every lane returns with
+// the total, the "a full product was folded" flag and the plain magnitude.  SH: use the witness shadows.
+template <int F, int RIPPLE, bool PIPE, bool SH = false>
 __device__ __forceinline__ void warp_fold_lc(uint32_t* acc, uint32_t k0, uint32_t k1, const CsrView& m, unsigned int& err, uint32_t& any_gen,
-                                             uint32_t& mag) {
+                                             uint32_t& mag, FatStage* fs = nullptr) {
     const uint32_t lane = threadIdx.x & 31u;
     zeron<17>(acc);
     uint32_t g = 0, mg = 0;
     if (k1 - k0 <= 4) {  // short LC: lane 0 alone
         if (lane == 0) fold_range<F, RIPPLE, 1, false>(acc, k0, k1, m, err, g, mg);
+    } else if (SH) {
+        SmallSums ss;
+        uint32_t acc10[10];
+        zeron<10>(acc10);
+        const bool any_slow = fold_lane_shadow<F, RIPPLE == 17>(acc10, k0 + lane, k1, m, *fs, err, g, ss);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) acc[i] = acc10[i];
+        if (ss.used) {
+            fold_small_sums<F>(acc, ss);
+            mg = 8;  // the sum is no longer a small multiple of p: the row takes the general test
+        }
+        if (any_slow) fold_lane_slow<F, 17, RIPPLE == 17>(acc, k0 + lane, k1, m, err, g, mg);
     } else {
         fold_range<F, 17, 32, PIPE>(acc, k0 + lane, k1, m, err, g, mg);
     }
@@ -491,8 +823,10 @@ __device__ __forceinline__ void warp_fold_lc(uint32_t* acc, uint32_t k0, uint32_
 template <int F, bool EMIT, int V, int MB>
 __global__ void __launch_bounds__(128, MB) check_fat_rows(CsrView m, CheckOut o, FieldConsts fc, const uint32_t* __restrict__ fat_rows,
                                                           const uint32_t* __restrict__ n_fat) {
-    constexpr bool PIPE = (V & kVPipe) != 0, PARK = (V & kVPark) != 0;
+    constexpr bool PIPE = (V & kVPipe) != 0, PARK = (V & kVPark) != 0, SH = (V & kVShadow) != 0;
     __shared__ uint32_t s_az[PARK ? 8 : 1][128], s_bz[PARK ? 8 : 1][128];
+    __shared__ FatStage s_fs[SH ? 4 : 1];
+    FatStage* fs = &s_fs[SH ? (threadIdx.x >> 5) : 0];
     uint32_t my_bad = 0xffffffffu;
     unsigned int my_err = 0;
     const uint32_t n = *n_fat;
@@ -503,13 +837,13 @@ __global__ void __launch_bounds__(128, MB) check_fat_rows(CsrView m, CheckOut o,
                        p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
         uint32_t acc[17], az[8], bz[8];
         uint32_t any_gen, mag;
-        warp_fold_lc<F, 9, PIPE>(acc, p0, p1, m, my_err, any_gen, mag);
+        warp_fold_lc<F, 9, PIPE, SH>(acc, p0, p1, m, my_err, any_gen, mag, fs);
         finish_ab<F, (V & kVMagSkip) != 0>(az, acc, any_gen, mag);
         if (PARK) park8(s_az, az);
-        warp_fold_lc<F, 9, PIPE>(acc, p1, p2, m, my_err, any_gen, mag);
+        warp_fold_lc<F, 9, PIPE, SH>(acc, p1, p2, m, my_err, any_gen, mag, fs);
         finish_ab<F, (V & kVMagSkip) != 0>(bz, acc, any_gen, mag);
         if (PARK) park8(s_bz, bz);
-        warp_fold_lc<F, 17, PIPE>(acc, p2, p3, m, my_err, any_gen, mag);
+        warp_fold_lc<F, 17, PIPE, SH>(acc, p2, p3, m, my_err, any_gen, mag, fs);
         if (PARK) {
             unpark8(az, s_az);
             unpark8(bz, s_bz);
@@ -538,207 +872,10 @@ __global__ void __launch_bounds__(128, MB) check_fat_rows(CsrView m, CheckOut o,
     publish_first_bad(my_bad, m, o, my_err);
 }
 
-// One fat row by the whole warp, outlined so that its register needs do not leak into the thin path's allocation.
-// Returns (to every lane) whether the row is satisfied; emits canonical Az/Bz/Cz from lane 0 when asked to.
-template <int F, bool EMIT, int V>
-__device__ __noinline__ bool fat_row_by_warp(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t frow, const CsrView& m,
-                                             const CheckOut& o, const FieldConsts& fc, unsigned int* err_out) {
-    unsigned int err = 0;
-    uint32_t acc[17], az[8], bz[8];
-    uint32_t any_gen, mag;
-    warp_fold_lc<F, 9, false>(acc, q0, q1, m, err, any_gen, mag);
-    finish_ab<F, (V & kVMagSkip) != 0>(az, acc, any_gen, mag);
-    warp_fold_lc<F, 9, false>(acc, q1, q2, m, err, any_gen, mag);
-    finish_ab<F, (V & kVMagSkip) != 0>(bz, acc, any_gen, mag);
-    warp_fold_lc<F, 17, false>(acc, q2, q3, m, err, any_gen, mag);
-    if (EMIT && (threadIdx.x & 31u) == 0) {
-        uint32_t v[8];
-        if (o.cz) {
-            finish_c_canonical<F>(v, acc, fc);
-            st8(o.cz + 2 * (size_t)frow, v);
-        }
-        if (o.az) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = az[i];
-            canon_ab<F>(v);
-            st8(o.az + 2 * (size_t)frow, v);
-        }
-        if (o.bz) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = bz[i];
-            canon_ab<F>(v);
-            st8(o.bz + 2 * (size_t)frow, v);
-        }
-    }
-    *err_out |= err;
-    return row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, any_gen, mag);
-}
-
-// One thin row by its own thread, outlined for the same reason as fat_row_by_warp.  Returns "satisfied".
-template <int F, bool EMIT, int V>
-__device__ __noinline__ bool thin_row_by_thread(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t row, const CsrView& m,
-                                                const CheckOut& o, const FieldConsts& fc, unsigned int* err_out) {
-    unsigned int err = 0;
-    uint32_t acc[17], az[8], bz[8];
-    uint32_t gen = 0, mag = 0;
-    zeron<17>(acc);
-    fold_range<F, 9, 1, false>(acc, p0, p1, m, err, gen, mag);
-    finish_ab<F, (V & kVMagSkip) != 0>(az, acc, gen, mag);
-    gen = 0; mag = 0;
-    zeron<17>(acc);
-    fold_range<F, 9, 1, false>(acc, p1, p2, m, err, gen, mag);
-    finish_ab<F, (V & kVMagSkip) != 0>(bz, acc, gen, mag);
-    gen = 0; mag = 0;
-    zeron<17>(acc);
-    fold_range<F, 17, 1, false>(acc, p2, p3, m, err, gen, mag);
-    if (EMIT) {
-        uint32_t v[8];
-        if (o.cz) {
-            finish_c_canonical<F>(v, acc, fc);
-            st8(o.cz + 2 * (size_t)row, v);
-        }
-        if (o.az) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = az[i];
-            canon_ab<F>(v);
-            st8(o.az + 2 * (size_t)row, v);
-        }
-        if (o.bz) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = bz[i];
-            canon_ab<F>(v);
-            st8(o.bz + 2 * (size_t)row, v);
-        }
-    }
-    *err_out |= err;
-    return row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, gen, mag);
-}
-
-// ---- K1 / K2, fused: thin rows by their own thread, fat rows by the whole warp, in the SAME pass over the rows --------
-// A separate fat-row kernel gathers from a witness region that has long left the caches (measured: L2 hit 8 %, and it
-// runs at the HBM random-access rate); handled in place, a fat row finds its operands in L2/L1 because the neighbouring
-// thin rows have just touched the same variables.  A warp owns 32 consecutive rows: each lane evaluates its row if it is
-// thin; then the lanes that hold a fat row are served one after the other by all 32 lanes together.
-template <int F, bool EMIT, int V, int MB>
-__global__ void __launch_bounds__(128, MB) check_rows_fused(CsrView m, CheckOut o, FieldConsts fc) {
-    constexpr bool PARK = (V & kVPark) != 0;
-    __shared__ uint32_t s_az[PARK ? 8 : 1][128], s_bz[PARK ? 8 : 1][128];
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t my_bad = 0xffffffffu;
-    unsigned int my_err = 0;
-    const uint32_t n_blocks = (m.n_rows + 31u) / 32u;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n_blocks; blk += n_warps) {
-        const uint32_t row = blk * 32u + lane;
-        const bool live = row < m.n_rows;
-        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        if (live) {
-            p0 = __ldg(m.row_ptr + 3 * (size_t)row);
-            p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1);
-            p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2);
-            p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
-        }
-        const bool fat = live && (p3 - p0 > m.fat_terms);
-        if (live && !fat) {
-            uint32_t acc[17], az[8], bz[8];
-            uint32_t gen = 0, mag = 0;
-            zeron<17>(acc);
-            fold_range<F, 9, 1, false>(acc, p0, p1, m, my_err, gen, mag);
-            finish_ab<F, (V & kVMagSkip) != 0>(az, acc, gen, mag);
-            if (PARK) park8(s_az, az);
-            gen = 0; mag = 0;
-            zeron<17>(acc);
-            fold_range<F, 9, 1, false>(acc, p1, p2, m, my_err, gen, mag);
-            finish_ab<F, (V & kVMagSkip) != 0>(bz, acc, gen, mag);
-            if (PARK) park8(s_bz, bz);
-            gen = 0; mag = 0;
-            zeron<17>(acc);
-            fold_range<F, 17, 1, false>(acc, p2, p3, m, my_err, gen, mag);
-            if (PARK) {
-                unpark8(az, s_az);
-                unpark8(bz, s_bz);
-            }
-            if (EMIT) {
-                uint32_t v[8];
-                if (o.cz) {
-                    finish_c_canonical<F>(v, acc, fc);
-                    st8(o.cz + 2 * (size_t)row, v);
-                }
-                if (o.az) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = az[i];
-                    canon_ab<F>(v);
-                    st8(o.az + 2 * (size_t)row, v);
-                }
-                if (o.bz) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = bz[i];
-                    canon_ab<F>(v);
-                    st8(o.bz + 2 * (size_t)row, v);
-                }
-            }
-            if (!row_satisfied<F, (V & kVBitRow) != 0>(acc, az, bz, gen, mag) && row < my_bad) my_bad = row;
-        }
-        // fat rows of this block: the whole warp serves them one at a time
-        uint32_t fat_mask = __ballot_sync(0xffffffffu, fat);
-        while (fat_mask) {
-            const int src = __ffs(fat_mask) - 1;
-            fat_mask &= fat_mask - 1;
-            const uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src),
-                           q2 = __shfl_sync(0xffffffffu, p2, src), q3 = __shfl_sync(0xffffffffu, p3, src);
-            const uint32_t frow = blk * 32u + (uint32_t)src;
-            if (!fat_row_by_warp<F, EMIT, V>(q0, q1, q2, q3, frow, m, o, fc, &my_err) && frow < my_bad) my_bad = frow;
-        }
-    }
-    publish_first_bad(my_bad, m, o, my_err);
-}
-
-// Same as check_rows_fused with BOTH paths outlined: the kernel body is only the dispatcher.
-template <int F, bool EMIT, int V, int MB>
-__global__ void __launch_bounds__(128, MB) check_rows_fused2(CsrView m, CheckOut o, FieldConsts fc) {
-    uint32_t my_bad = 0xffffffffu;
-    unsigned int my_err = 0;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_blocks = (m.n_rows + 31u) / 32u;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n_blocks; blk += n_warps) {
-        const uint32_t row = blk * 32u + lane;
-        const bool live = row < m.n_rows;
-        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        if (live) {
-            p0 = __ldg(m.row_ptr + 3 * (size_t)row);
-            p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1);
-            p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2);
-            p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
-        }
-        const bool fat = live && (p3 - p0 > m.fat_terms);
-        if (live && !fat) {
-            if (!thin_row_by_thread<F, EMIT, V>(p0, p1, p2, p3, row, m, o, fc, &my_err) && row < my_bad) my_bad = row;
-        }
-        uint32_t fat_mask = __ballot_sync(0xffffffffu, fat);
-        while (fat_mask) {
-            const int src = __ffs(fat_mask) - 1;
-            fat_mask &= fat_mask - 1;
-            const uint32_t q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src),
-                           q2 = __shfl_sync(0xffffffffu, p2, src), q3 = __shfl_sync(0xffffffffu, p3, src);
-            const uint32_t frow = blk * 32u + (uint32_t)src;
-            if (!fat_row_by_warp<F, EMIT, V>(q0, q1, q2, q3, frow, m, o, fc, &my_err) && frow < my_bad) my_bad = frow;
-        }
-    }
-    publish_first_bad(my_bad, m, o, my_err);
-}
-
-// List the rows that belong to check_fat_rows (order is irrelevant: the result is a minimum).
-__global__ void collect_fat_rows(const uint32_t* __restrict__ row_ptr, uint32_t n_rows, uint32_t fat_terms, uint32_t* fat_rows,
-                                 uint32_t* n_fat) {
-    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
-        if (row_ptr[3 * (size_t)row + 3] - row_ptr[3 * (size_t)row] > fat_terms) fat_rows[atomicAdd(n_fat, 1u)] = row;
-    }
-}
-
-__global__ void init_result(long long* first_bad, unsigned int* err) {
+__global__ void init_result(long long* first_bad, unsigned int* err, uint32_t* n_deferred) {
     *first_bad = 0x7fffffffffffffffLL;
     *err = 0;
+    if (n_deferred) *n_deferred = 0;
 }
 
 // ---- K3: ingest conversion ------------------------------------------------------------------------------------------------
@@ -819,11 +956,28 @@ __global__ void convert_terms(uint4* vals, uint32_t* cols, const uint32_t* __res
     }
 }
 
-template <int F> __global__ void validate_canonical(const uint4* __restrict__ v, uint64_t n, unsigned int* err) {
+// Witness upload: value < p check, and the 4-byte shadow of every element.
+template <int F> __global__ void validate_canonical(const uint4* __restrict__ v, uint64_t n, unsigned int* err, uint32_t* __restrict__ shadow) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t x[8];
         ld8(x, v + 2 * i);
         if (!is_canonical<F>(x)) atomicOr(err, 2u);
+        shadow[i] = shadow_of(x);
+    }
+}
+
+// Packed witness upload (bp_cs_alloc_u8 / bp_cs_set_range_u8): element i = bytes[i], widened to the canonical 32-byte form
+// and to its shadow.  Two lanes write one element (16 bytes each) so that a warp stores 512 contiguous bytes.
+__global__ void widen_u8(const uint8_t* __restrict__ bytes, uint64_t n, uint4* __restrict__ out, uint32_t* __restrict__ shadow) {
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < 2 * n; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = j >> 1;
+        const uint32_t b = bytes[i];
+        if (j & 1) {
+            out[j] = make_uint4(0, 0, 0, 0);
+        } else {
+            out[j] = make_uint4(b, 0, 0, 0);
+            shadow[i] = b;
+        }
     }
 }
 
@@ -901,7 +1055,7 @@ __global__ void synth_fill(uint32_t* cols, uint4* vals, const uint32_t* __restri
 }
 
 template <int F>
-__global__ void synth_witness(uint4* inputs, uint4* aux, uint64_t seed, uint64_t n_vars, uint64_t n_inputs) {
+__global__ void synth_witness(uint4* inputs, uint4* aux, uint32_t* inputs_s, uint32_t* aux_s, uint64_t seed, uint64_t n_vars, uint64_t n_inputs) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_vars; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t v[8];
         if (i == 0) {
@@ -911,6 +1065,7 @@ __global__ void synth_witness(uint4* inputs, uint4* aux, uint64_t seed, uint64_t
             sm_sample<F>(sm_key(seed, 4, i, 0), v);
         }
         st8((i < n_inputs ? inputs + 2 * i : aux + 2 * (i - n_inputs)), v);
+        *(i < n_inputs ? inputs_s + i : aux_s + (i - n_inputs)) = shadow_of(v);
     }
 }
 

@@ -25,6 +25,8 @@ SIGNATURES = {
     "bp_cs_free": (None, [vp]),
     "bp_cs_last_error": (ctypes.c_char_p, [vp]),
     "bp_cs_alloc": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_uint64, u64p]),
+    "bp_cs_alloc_u8": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_uint64, u64p]),
+    "bp_cs_set_range_u8": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp]),
     "bp_cs_set": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, vp]),
     "bp_cs_get": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, vp]),
     "bp_cs_set_range": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp]),

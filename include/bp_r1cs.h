@@ -70,6 +70,12 @@ int bp_abi_version(void);
  * to one index space; *first_index receives the index of the first appended element. */
 int bp_cs_alloc(bp_cs* cs, int is_aux, const uint64_t* vals_le, uint64_t n, uint64_t* first_index);
 
+/* Packed form of bp_cs_alloc for witnesses whose values fit one byte: element i = vals[i] (0..255).  Gadget
+ * circuits allocate almost nothing but AllocatedBit values (boolean.rs:68-97: `alloc(|| .., || Ok(if b {ONE} else
+ * {ZERO}))`), so the Rust wrapper's staging buffer holds one byte per such value instead of 32 and flushes it here;
+ * a value that does not fit (rare) is patched afterwards with bp_cs_set.  Same index assignment as bp_cs_alloc. */
+int bp_cs_alloc_u8(bp_cs* cs, int is_aux, const uint8_t* vals, uint64_t n, uint64_t* first_index);
+
 /* set (test_cs.rs:270-282): overwrite one element.  get (test_cs.rs:311-323). */
 int bp_cs_set(bp_cs* cs, int is_aux, uint64_t idx, const uint64_t v[4]);
 int bp_cs_get(bp_cs* cs, int is_aux, uint64_t idx, uint64_t v[4]);
@@ -77,6 +83,9 @@ int bp_cs_get(bp_cs* cs, int is_aux, uint64_t idx, uint64_t v[4]);
 /* Bulk overwrite of an existing range [first, first+n): SizedWitness::generate_witness_into
  * (witness_cs.rs:12, 28-40) writing into the slices returned by allocate_empty. */
 int bp_cs_set_range(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, const uint64_t* vals_le);
+
+/* Packed form of bp_cs_set_range (see bp_cs_alloc_u8). */
+int bp_cs_set_range_u8(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals);
 
 /* scalar_inputs / scalar_aux (test_cs.rs:180-189), inputs_slice / aux_slice (witness_cs.rs:195-201). */
 int bp_cs_witness(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, uint64_t* out_le);
@@ -120,8 +129,11 @@ int bp_cs_set_stream(bp_cs* cs, void* cuda_stream);
 int bp_cs_set_row_base(bp_cs* cs, uint64_t row_base);
 /* Block until all enqueued work of this handle is complete. */
 int bp_cs_sync(bp_cs* cs);
-/* Tuning / introspection knobs: "fat_terms" (rows with more terms use the warp-per-row kernel; default 96),
- * read-only: "launches" (kernels launched so far), "fat_rows", "sm_count". */
+/* Tuning / introspection knobs: "fat_terms" (rows with more terms use the warp-per-row kernel; default 96);
+ * "variant" (-1 = default; else bit 0: no small-operand kernel, bit 1: no witness shadows in the warp-per-row kernel,
+ * bit 2: park A.w/B.w in shared memory -- every variant returns the same results, the parity tests run them all);
+ * read-only: "launches" (kernels launched so far), "plain_rows" / "generic_rows" / "fat_rows" (rows per kernel),
+ * "deferred_rows" (plain rows the last check sent to the full-width kernel), "gen_terms", "sm_count". */
 int bp_cs_set_option(bp_cs* cs, const char* key, int64_t value);
 int bp_cs_get_option(bp_cs* cs, const char* key, int64_t* value);
 

@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 from gpu_util import Handle  # noqa: E402
 
 FIDS = sorted(FIELDS)
-# (fat_terms, variant): default split / nearly every row through the warp-per-row kernel, x direct (-1) / warp-staged (22) kernels
-KERNELS = [(96, -1), (8, -1), (96, -3), (8, 22), (96, 40)]
+# (fat_terms, variant): default split / nearly every row through the warp-per-row kernel, x the kernel variants of
+# bp_cs_set_option("variant"): -1 default, bit 0 no small-operand kernel, bit 1 no shadows in the fat kernel, bit 2 park
+KERNELS = [(96, -1), (8, -1), (96, 1), (8, 3), (96, 4), (8, 2)]
 
 
 @pytest.mark.parametrize("fid", FIDS)
@@ -175,6 +176,144 @@ def test_ragged_empty_and_fat_rows(kernel):
         assert h.first_unsatisfied() == bad
         az, bz, cz = h.eval(700)
         assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
+
+
+def _gadget_like_instance(fid, seed, n_rows, n_aux, big_every):
+    """Rows shaped like boolean / uint32 gadget constraints (coefficients +-1, +-2, small, 0; 2^k in the fat rows) over a
+    witness of small values, with every `big_every`-th element a full-width field element and some at the 2^24 boundary.
+    About half of the rows are made to hold by solving for a fresh C variable."""
+    p = FIELDS[fid].p
+    rng = random.Random(seed)
+    small = [0, 1, 1, 0, 255, 65535, 3, 2]
+    edge = [(1 << 24) - 1, (1 << 24), (1 << 24) + 1]
+    aux = []
+    for i in range(n_aux):
+        if big_every and i % big_every == big_every - 1:
+            aux.append(rng.randrange(p))
+        else:
+            aux.append(rng.choice(edge) if rng.random() < 0.02 else rng.choice(small))
+    inputs = [1, 5, 0]
+    coef_small = [1, 1, 1, p - 1, p - 1, 2, p - 2, 3, p - 3, 0, 5, p - 7]
+
+    def val(col):
+        return aux[col & 0x7FFFFFFF] if col & 0x80000000 else inputs[col]
+
+    def lc(n, coefs, bound):
+        idx = sorted(rng.sample(range(bound), n)) if n else []
+        out = [(i | 0x80000000, rng.choice(coefs)) for i in idx]
+        if n and rng.random() < 0.3:
+            out = [(rng.randrange(len(inputs)), rng.choice(coefs))] + out
+        return out
+
+    rows = []
+    for r in range(n_rows):
+        bound = len(aux)
+        kind = rng.randrange(10)
+        if kind == 0:
+            a, b = lc(rng.randrange(120, 400), [1 << rng.randrange(0, 250) for _ in range(8)], bound), [(0, 1)]  # MultiEq-like
+        elif kind == 1:
+            a, b = lc(rng.randrange(0, 4), coef_small + [rng.randrange(p)], bound), lc(rng.randrange(0, 3), coef_small, bound)
+        else:
+            a, b = lc(rng.randrange(0, 5), coef_small, bound), lc(rng.randrange(0, 4), coef_small, bound)
+        c = lc(rng.randrange(0, 4) if kind else rng.randrange(100, 300), coef_small if kind else [1 << rng.randrange(0, 40) for _ in range(6)] + [p - 1],
+               bound)
+        if rng.random() < 0.55:  # make the row hold: append a fresh variable with coefficient +-1 to C
+            az = sum(cf * val(col) for col, cf in a) % p
+            bz = sum(cf * val(col) for col, cf in b) % p
+            cz = sum(cf * val(col) for col, cf in c) % p
+            v = (az * bz - cz) % p
+            sign = 1 if v < p // 2 else p - 1  # keeps the solved value small when the operands are
+            aux.append((v * sign) % p)
+            c = c + [((len(aux) - 1) | 0x80000000, sign)]
+        rows.append((a, b, c))
+    lens, cols, coeffs = [], [], []
+    for a, b, c in rows:
+        for l in (a, b, c):
+            lens.append(len(l))
+            cols += [x for x, _ in l]
+            coeffs += [v for _, v in l]
+    return (np.asarray(lens, np.uint32), np.asarray(cols, np.uint32), c_api.ints_to_limbs(coeffs), c_api.ints_to_limbs(inputs),
+            c_api.ints_to_limbs(aux), rows)
+
+
+@pytest.mark.parametrize("fid", FIDS)
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("big_every", [0, 5, 1])
+def test_small_operand_rows_match_oracle(fid, kernel, big_every):
+    """The integer path on the witness shadows (check_small, shadow path of check_fat_rows) against the oracle: small and
+    full-width operands mixed, values on both sides of the 2^24 boundary, holding and failing rows, then witness edits."""
+    p = FIELDS[fid].p
+    n_rows = 2500
+    lens, cols, coeffs, inputs, aux, rows = _gadget_like_instance(fid, 1000 * fid + big_every, n_rows, 3000, big_every)
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    bad, az_r, bz_r, cz_r = inst.eval(2)
+    with Handle(fid) as h:
+        h.opt("fat_terms", kernel[0])
+        h.opt("variant", kernel[1])
+        h.load_instance(lens, cols, coeffs, inputs, aux)
+        assert h.first_unsatisfied() == bad
+        if kernel[1] in (-1, 4, 2):
+            assert h.opt("plain_rows") > n_rows // 5
+            if big_every == 0:
+                assert 0 < h.opt("deferred_rows") < h.opt("plain_rows") // 2  # only rows touching a value >= 2^24
+        az, bz, cz = h.eval(n_rows)
+        assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
+        # make every failing row hold one after the other is too slow; instead repair the first few and re-check
+        rng = random.Random(7)
+        for _ in range(8):
+            row = inst.check(2, True)
+            assert h.first_unsatisfied() == row
+            if row < 0:
+                break
+            a, b, c = rows[row]
+            # overwrite a random variable of the row with a random small or big value: verdicts must keep agreeing
+            terms = [t for t in a + b + c if t[0] & 0x80000000]
+            if not terms:
+                break
+            col = rng.choice(terms)[0]
+            new = rng.choice([0, 1, (1 << 24) - 1, 1 << 24, rng.randrange(p)])
+            v = c_api.ints_to_limbs([new])
+            h.ok(h.L.bp_cs_set(h.h, 1, col & 0x7FFFFFFF, v.ctypes.data))
+            inst.set(True, col & 0x7FFFFFFF, new)
+        assert h.first_unsatisfied() == inst.check(2, True)
+
+
+@pytest.mark.parametrize("fid", FIDS)
+def test_packed_u8_witness_equals_full_width(fid):
+    """bp_cs_alloc_u8 / bp_cs_set_range_u8 give the same system as the 32-byte calls."""
+    rng = random.Random(3 + fid)
+    n = 5000
+    vals = np.asarray([rng.choice([0, 1, 1, 0, 255, 7]) for _ in range(n)], np.uint8)
+    full = c_api.ints_to_limbs([int(v) for v in vals])
+    lens, cols, coeffs, inputs, _, _ = _gadget_like_instance(fid, 77, 1500, n, 0)
+    with Handle(fid) as h1, Handle(fid) as h2:
+        first = ctypes.c_uint64()
+        h1.ok(h1.L.bp_cs_alloc(h1.h, 0, inputs[1:].ctypes.data, 2, ctypes.byref(first)))
+        h2.ok(h2.L.bp_cs_alloc(h2.h, 0, inputs[1:].ctypes.data, 2, ctypes.byref(first)))
+        n_aux_total = int((cols[cols >= 0x80000000] & 0x7FFFFFFF).max()) + 1
+        pad = np.zeros(n_aux_total - n, np.uint8)
+        h1.ok(h1.L.bp_cs_alloc(h1.h, 1, full.ctypes.data, n, ctypes.byref(first)))
+        pad_full = c_api.ints_to_limbs([0] * pad.size)
+        h1.ok(h1.L.bp_cs_alloc(h1.h, 1, pad_full.ctypes.data, pad.size, ctypes.byref(first)))
+        h2.ok(h2.L.bp_cs_alloc_u8(h2.h, 1, vals.ctypes.data, n, ctypes.byref(first)))
+        assert first.value == 0
+        h2.ok(h2.L.bp_cs_alloc_u8(h2.h, 1, pad.ctypes.data, pad.size, ctypes.byref(first)))
+        assert first.value == n
+        for h in (h1, h2):
+            h.ok(h.L.bp_cs_enforce(h.h, lens.size // 3, lens.ctypes.data, cols.ctypes.data, coeffs.ctypes.data))
+        got = np.zeros((n, 4), np.uint64)
+        h2.ok(h2.L.bp_cs_witness(h2.h, 1, 0, n, got.ctypes.data))
+        assert (got == full).all()
+        assert h1.first_unsatisfied() == h2.first_unsatisfied()
+        a1, a2 = h1.eval(lens.size // 3), h2.eval(lens.size // 3)
+        assert all((x == y).all() for x, y in zip(a1, a2))
+        # overwrite a range, packed vs full-width
+        new = np.asarray([rng.choice([0, 1, 200]) for _ in range(1000)], np.uint8)
+        h2.ok(h2.L.bp_cs_set_range_u8(h2.h, 1, 100, 1000, new.ctypes.data))
+        new_full = c_api.ints_to_limbs([int(v) for v in new])
+        h1.ok(h1.L.bp_cs_set_range(h1.h, 1, 100, 1000, new_full.ctypes.data))
+        assert h1.first_unsatisfied() == h2.first_unsatisfied()
+        assert h2.L.bp_cs_set_range_u8(h2.h, 1, n_aux_total - 1, 2, new.ctypes.data) == -3
 
 
 def test_errors_and_empty_system():
