@@ -43,7 +43,9 @@ struct bp_cs {
     uint64_t n_rows = 0, nnz = 0, n_inputs = 0, n_aux = 0, row_base = 0;
     uint64_t n_gen = 0;  // terms that need a full 256x256 product (drives the kernel-configuration heuristic)
     DevBuf row_ptr, cols, vals, inputs, aux;
-    DevBuf inputs_s, aux_s;    // witness shadows (u32 per element, kernels.cuh: shadow_of)
+    DevBuf shadow;             // witness shadows (u32 per element, kernels.cuh: shadow_of): inputs at [0, n_inputs), aux at
+    uint64_t shadow_aux_off = 1u << 16;  // [shadow_aux_off, +n_aux): one array, so that a column word maps to one 32-bit index
+    bool cols_in_range = true; // plan: every column index of every row exists (checked when the plan is built)
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
     DevBuf u8_stage;           // packed witness uploads land here before widen_u8
     DevBuf row_meta;           // plan: lengths + RowKind per row
@@ -122,6 +124,43 @@ int ensure(bp_cs* h, DevBuf& b, size_t need, size_t keep) {
     return BP_OK;
 }
 
+uint32_t* shadow_ptr(bp_cs* h, int is_aux) { return (uint32_t*)h->shadow.p + (is_aux ? h->shadow_aux_off : 0); }
+
+// Room for `need_in` input and `need_aux` aux shadows, keeping the current contents.  The aux region starts at a fixed
+// offset; outgrowing the input region (rare: circuits have few public inputs) moves it.
+int ensure_shadow(bp_cs* h, uint64_t need_in, uint64_t need_aux) {
+    uint64_t off = h->shadow_aux_off;
+    while (need_in > off) off *= 4;
+    if (off + need_aux >= 0xffffffffull) return fail(h, BP_E_RANGE, "too many variables for one handle");
+    const size_t have = h->shadow.cap / 4;
+    if (off == h->shadow_aux_off && off + need_aux <= have) return BP_OK;
+    size_t aux_cap = std::max<size_t>(need_aux, have > h->shadow_aux_off ? (have - h->shadow_aux_off) * 3 / 2 : 0);
+    size_t bytes = ((off + aux_cap) * 4 + 255) & ~size_t(255);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        bytes = ((off + need_aux) * 4 + 255) & ~size_t(255);
+        e = cudaMalloc(&np, bytes);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, BP_E_OOM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    if (h->shadow.p) {
+        if (h->n_inputs) CU(h, cudaMemcpyAsync(np, h->shadow.p, h->n_inputs * 4, cudaMemcpyDeviceToDevice, h->stream));
+        if (h->n_aux)
+            CU(h, cudaMemcpyAsync((uint32_t*)np + off, (uint32_t*)h->shadow.p + h->shadow_aux_off, h->n_aux * 4, cudaMemcpyDeviceToDevice,
+                                  h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaFree(h->shadow.p));
+    }
+    h->shadow.p = np;
+    h->shadow.cap = bytes;
+    h->shadow_aux_off = off;
+    return BP_OK;
+}
+
 // 2^k mod p on the host, with the same limb code the device uses.
 template <int F> void pow2_mod_p(int k, uint32_t* out) {
     uint32_t x[8] = {1, 0, 0, 0, 0, 0, 0, 0};
@@ -152,8 +191,8 @@ CsrView view(const bp_cs* h) {
     m.vals = (const uint4*)h->vals.p;
     m.inputs = (const uint4*)h->inputs.p;
     m.aux = (const uint4*)h->aux.p;
-    m.inputs_s = (const uint32_t*)h->inputs_s.p;
-    m.aux_s = (const uint32_t*)h->aux_s.p;
+    m.shadow = (const uint32_t*)h->shadow.p;
+    m.aux_off = (uint32_t)h->shadow_aux_off;
     m.row_meta = (const uint32_t*)h->row_meta.p;
     m.n_rows = (uint32_t)h->n_rows;
     m.n_inputs = (uint32_t)h->n_inputs;
@@ -252,22 +291,23 @@ int ensure_plan(bp_cs* h) {
     h->n_fat_rows = h->n_gen_rows = h->n_plain_rows = 0;
     if (h->n_rows) {
         const uint32_t n = (uint32_t)h->n_rows;
-        int rc = ensure(h, h->row_meta, (size_t)n * 4, 0);
+        int rc = ensure(h, h->row_meta, ((size_t)n + 1) * 4, 0);
         if (rc != BP_OK) return rc;
         if ((rc = ensure(h, h->scratch, 16, 0)) != BP_OK) return rc;
         uint32_t* d_cnt = (uint32_t*)h->scratch.p;
-        CU(h, cudaMemsetAsync(d_cnt, 0, 12, h->stream));
-        build_row_meta<<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p,
-                                                                       (const uint4*)h->vals.p, n, (uint32_t)h->fat_terms,
+        CU(h, cudaMemsetAsync(d_cnt, 0, 16, h->stream));
+        build_row_meta<<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p, n,
+                                                                       (uint32_t)h->fat_terms, (uint32_t)h->n_inputs, (uint32_t)h->n_aux,
                                                                        (uint32_t*)h->row_meta.p, d_cnt);
         h->launches++;
         CU(h, cudaGetLastError());
         uint32_t* hc = (uint32_t*)((char*)h->h_pinned_small + 48);
-        CU(h, cudaMemcpyAsync(hc, d_cnt, 12, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
         h->n_gen_rows = hc[kRowGeneric];
         h->n_plain_rows = hc[kRowPlain];
         h->n_fat_rows = hc[kRowFat];
+        h->cols_in_range = hc[3] == 0;  // (rows with a column that does not exist are generic: check_rows reports them)
         if ((rc = select_rows(h, h->fat_rows, kRowFat, h->n_fat_rows)) != BP_OK) return rc;
         // the generic list is only needed when the thin rows are split between check_small and check_rows
         if ((rc = select_rows(h, h->gen_rows, kRowGeneric, h->n_plain_rows ? h->n_gen_rows : 0)) != BP_OK) return rc;
@@ -335,8 +375,10 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
         const bool park = (v & 4) || (h->variant < 0 && 2 * h->n_gen > h->nnz);
         if (h->kernels_mask & 1) {
             if (use_small) {
-                const int sgrid = (int)std::min<uint64_t>((h->n_rows + kSmallThreads - 1) / kSmallThreads, (uint64_t)h->sm_count * 6);
-                check_small<<<sgrid, kSmallThreads, 0, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
+                const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;  // one warp per block of rows
+                const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 4);
+                CU(h, cudaFuncSetAttribute(check_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
+                check_small<<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
                 h->launches++;
                 const uint32_t* gl = (const uint32_t*)h->gen_rows.p;
                 const int lgrid = grid_for(h, h->n_gen_rows + h->n_plain_rows, block, 16);
@@ -412,8 +454,9 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     const uint64_t one[4] = {1, 0, 0, 0};
     uint64_t idx = 0;
     size_t rv = (size_t)std::max<uint64_t>(reserve_vars, 1);
-    if (ensure(h, h->inputs, 32 * 1024, 0) != BP_OK || ensure(h, h->inputs_s, 4 * 1024, 0) != BP_OK) return bail(BP_E_OOM);
-    if (reserve_vars && (ensure(h, h->aux, rv * 32, 0) != BP_OK || ensure(h, h->aux_s, rv * 4, 0) != BP_OK)) return bail(BP_E_OOM);
+    if (ensure(h, h->inputs, 32 * 1024, 0) != BP_OK) return bail(BP_E_OOM);
+    if (reserve_vars && ensure(h, h->aux, rv * 32, 0) != BP_OK) return bail(BP_E_OOM);
+    if (ensure_shadow(h, 1, reserve_vars) != BP_OK) return bail(BP_E_OOM);
     if (reserve_rows && ensure(h, h->row_ptr, (3 * (size_t)reserve_rows + 1) * 4, 0) != BP_OK) return bail(BP_E_OOM);
     if (reserve_nnz) {
         if (ensure(h, h->cols, (size_t)reserve_nnz * 4, 0) != BP_OK) return bail(BP_E_OOM);
@@ -430,7 +473,7 @@ void bp_cs_free(bp_cs* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->inputs_s, &h->aux_s, &h->scan_tmp, &h->scratch, &h->u8_stage,
+    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->shadow, &h->scan_tmp, &h->scratch, &h->u8_stage,
                       &h->row_meta, &h->fat_rows, &h->gen_rows, &h->deferred})
         if (b->p) cudaFree(b->p);
     if (h->d_result) cudaFree(h->d_result);
@@ -530,17 +573,16 @@ int bp_cs_alloc(bp_cs* h, int is_aux, const uint64_t* vals, uint64_t n, uint64_t
     DevBuf& b = is_aux ? h->aux : h->inputs;
     uint64_t& cnt = is_aux ? h->n_aux : h->n_inputs;
     if (cnt + n >= 0x80000000ull) return fail(h, BP_E_RANGE, "more than 2^31-1 variables in one index space");
-    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
     int rc = ensure(h, b, (size_t)(cnt + n) * 32, (size_t)cnt * 32);
     if (rc != BP_OK) return rc;
-    if ((rc = ensure(h, bs, (size_t)(cnt + n) * 4, (size_t)cnt * 4)) != BP_OK) return rc;
+    if ((rc = ensure_shadow(h, h->n_inputs + (is_aux ? 0 : n), h->n_aux + (is_aux ? n : 0))) != BP_OK) return rc;
     if (n) {
         rc = clear_err(h);
         if (rc != BP_OK) return rc;
         rc = upload(h, (char*)b.p + cnt * 32, vals, (size_t)n * 32);
         if (rc != BP_OK) return rc;
         DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>(
-                              (const uint4*)((char*)b.p + cnt * 32), n, h->d_err, (uint32_t*)bs.p + cnt)));
+                              (const uint4*)((char*)b.p + cnt * 32), n, h->d_err, shadow_ptr(h, is_aux) + cnt)));
         h->launches++;
         CU(h, cudaGetLastError());
         rc = check_err_word(h, "bp_cs_alloc");
@@ -559,7 +601,6 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
                                                    (unsigned long long)n, (unsigned long long)cnt);
     if (!n) return BP_OK;
     DevBuf& b = is_aux ? h->aux : h->inputs;
-    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, vals);
     if (e != cudaSuccess) (void)cudaGetLastError();
@@ -581,7 +622,7 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
         if (rc != BP_OK) return rc;
         if ((rc = upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32)) != BP_OK) return rc;
         DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>(  // refreshes the shadows
-                              (const uint4*)((char*)b.p + first * 32), n, h->d_err, (uint32_t*)bs.p + first)));
+                              (const uint4*)((char*)b.p + first * 32), n, h->d_err, shadow_ptr(h, is_aux) + first)));
         h->launches++;
         CU(h, cudaGetLastError());
         return BP_OK;
@@ -591,7 +632,7 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
     if (rc != BP_OK) return rc;
     if ((rc = upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32)) != BP_OK) return rc;
     DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint4*)((char*)b.p + first * 32), n,
-                                                                                          h->d_err, (uint32_t*)bs.p + first)));
+                                                                                          h->d_err, shadow_ptr(h, is_aux) + first)));
     h->launches++;
     CU(h, cudaGetLastError());
     return check_err_word(h, "bp_cs_set_range");
@@ -605,9 +646,8 @@ static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const ui
     if (rc != BP_OK) return rc;
     if ((rc = upload(h, h->u8_stage.p, vals, (size_t)n)) != BP_OK) return rc;
     DevBuf& b = is_aux ? h->aux : h->inputs;
-    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
     widen_u8<<<grid_for(h, 2 * n, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p, n, (uint4*)((char*)b.p + first * 32),
-                                                                 (uint32_t*)bs.p + first);
+                                                                 shadow_ptr(h, is_aux) + first);
     h->launches++;
     CU(h, cudaGetLastError());
     return BP_OK;
@@ -617,12 +657,11 @@ int bp_cs_alloc_u8(bp_cs* h, int is_aux, const uint8_t* vals, uint64_t n, uint64
     if (!h || (!vals && n)) return BP_E_ARG;
     CU(h, cudaSetDevice(h->device));
     DevBuf& b = is_aux ? h->aux : h->inputs;
-    DevBuf& bs = is_aux ? h->aux_s : h->inputs_s;
     uint64_t& cnt = is_aux ? h->n_aux : h->n_inputs;
     if (cnt + n >= 0x80000000ull) return fail(h, BP_E_RANGE, "more than 2^31-1 variables in one index space");
     int rc = ensure(h, b, (size_t)(cnt + n) * 32, (size_t)cnt * 32);
     if (rc != BP_OK) return rc;
-    if ((rc = ensure(h, bs, (size_t)(cnt + n) * 4, (size_t)cnt * 4)) != BP_OK) return rc;
+    if ((rc = ensure_shadow(h, h->n_inputs + (is_aux ? 0 : n), h->n_aux + (is_aux ? n : 0))) != BP_OK) return rc;
     if (n && (rc = widen_into(h, is_aux, cnt, n, vals)) != BP_OK) return rc;
     if (first_index) *first_index = cnt;
     cnt += n;
@@ -836,14 +875,15 @@ int bp_cs_synth_witness(bp_cs* h, uint64_t seed, uint64_t n_vars, uint64_t n_inp
     int rc;
     if ((rc = ensure(h, h->inputs, (size_t)n_inputs * 32, 0)) != BP_OK) return rc;
     if ((rc = ensure(h, h->aux, (size_t)std::max<uint64_t>(n_vars - n_inputs, 1) * 32, 0)) != BP_OK) return rc;
-    if ((rc = ensure(h, h->inputs_s, (size_t)n_inputs * 4, 0)) != BP_OK) return rc;
-    if ((rc = ensure(h, h->aux_s, (size_t)std::max<uint64_t>(n_vars - n_inputs, 1) * 4, 0)) != BP_OK) return rc;
+    h->n_inputs = h->n_aux = 0;  // the witness is REPLACED: nothing to carry over when the shadows move
+    if ((rc = ensure_shadow(h, n_inputs, n_vars - n_inputs)) != BP_OK) return rc;
     DISPATCH_FIELD(h, (synth_witness<F><<<grid_for(h, n_vars, 256, 8), 256, 0, h->stream>>>(
-                          (uint4*)h->inputs.p, (uint4*)h->aux.p, (uint32_t*)h->inputs_s.p, (uint32_t*)h->aux_s.p, seed, n_vars, n_inputs)));
+                          (uint4*)h->inputs.p, (uint4*)h->aux.p, shadow_ptr(h, 0), shadow_ptr(h, 1), seed, n_vars, n_inputs)));
     h->launches++;
     CU(h, cudaGetLastError());
     h->n_inputs = n_inputs;
     h->n_aux = n_vars - n_inputs;
+    h->plan_valid = false;  // the plan vouches for column ranges
     return BP_OK;
 }
 

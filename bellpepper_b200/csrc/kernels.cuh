@@ -43,8 +43,8 @@ struct CsrView {
     const uint4* __restrict__ vals;
     const uint4* __restrict__ inputs;
     const uint4* __restrict__ aux;
-    const uint32_t* __restrict__ inputs_s;  // witness shadows: the value when it is < 2^24, else kShadowBig
-    const uint32_t* __restrict__ aux_s;
+    const uint32_t* __restrict__ shadow;    // witness shadows (the value when it is < 2^24, else kShadowBig): inputs at
+    uint32_t aux_off;                       // [0, n_inputs), aux at [aux_off, aux_off + n_aux)
     const uint32_t* __restrict__ row_meta;  // plan: |A| | |B|<<8 | |C|<<16 | RowKind<<24   (lengths 255,0,0 = not encodable)
     uint32_t n_rows;
     uint32_t n_inputs;
@@ -69,7 +69,7 @@ enum RowKind : uint32_t {
     kRowFat = 2       // check_fat_rows
 };
 constexpr uint32_t kMetaNoLens = 255u;
-constexpr uint32_t kSmallCap = 512;  // words per staging buffer of check_small; a plain row has at most this many terms
+constexpr uint32_t kSmallCap = 768;  // words per staging buffer of check_small; a plain row has at most this many terms
 
 // Witness shadow: a second, 4-byte copy of every witness element, maintained wherever the witness is written.
 // Gadget circuits (sha256, blake2s, boolean, uint32) have bit- or byte-valued witnesses; a row whose operands are all
@@ -365,9 +365,10 @@ __global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, Fie
 }
 
 // ---- plan: row_meta (lengths + kind), one thread per row ------------------------------------------------------------
-__global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, const uint4* __restrict__ vals,
-                               uint32_t n_rows, uint32_t fat_terms, uint32_t* __restrict__ row_meta, uint32_t* __restrict__ counts /*3*/) {
+__global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, uint32_t n_rows, uint32_t fat_terms,
+                               uint32_t n_inputs, uint32_t n_aux, uint32_t* __restrict__ row_meta, uint32_t* __restrict__ counts /*4*/) {
     uint32_t n_kind[3] = {0, 0, 0};
+    bool oob = false;
     for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
         const uint32_t p0 = row_ptr[3 * (size_t)row], p1 = row_ptr[3 * (size_t)row + 1], p2 = row_ptr[3 * (size_t)row + 2],
                        p3 = row_ptr[3 * (size_t)row + 3];
@@ -381,16 +382,18 @@ __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint3
         } else {
             uint32_t mag[3] = {0, 0, 0};
             for (uint32_t t = p0; t < p3 && k == kRowPlain; ++t) {
-                const uint32_t cls = (__ldg(cols + t) >> kColClsShift) & 7u;
+                const uint32_t col = __ldg(cols + t);
+                const uint32_t cls = (col >> kColClsShift) & 7u;
                 const int lc_i = t < p1 ? 0 : (t < p2 ? 1 : 2);
-                if (cls == kClsGen) k = kRowGeneric;
+                if (cls == kClsGen || cls == kClsPS || cls == kClsMS) k = kRowGeneric;  // check_small knows +-1, +-2 and 0
                 else if (cls == kClsP1 || cls == kClsM1) mag[lc_i] += 1;
                 else if (cls == kClsP2 || cls == kClsM2) mag[lc_i] += 2;
-                else if (cls == kClsPS || cls == kClsMS) {
-                    const uint32_t sm = __ldg(reinterpret_cast<const uint32_t*>(vals + 2 * (size_t)t));
-                    mag[lc_i] += sm > 8u ? 8u : sm;
-                }
                 if (mag[0] > 7u || mag[1] > 7u || mag[2] > 5u) k = kRowGeneric;
+                // check_small does not bound-check its gathers: a plain row only has columns that exist
+                if (cls != kClsZero && (col & kColIdxMask) >= ((col & kColAux) ? n_aux : n_inputs)) {
+                    oob = true;
+                    k = kRowGeneric;
+                }
             }
         }
         row_meta[row] = (enc ? (la | (lb << 8) | (lc << 16)) : kMetaNoLens) | (k << 24);
@@ -403,21 +406,36 @@ __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint3
         const uint32_t tot = __reduce_add_sync(0xffffffffu, n_kind[i]);
         if ((threadIdx.x & 31u) == 0 && tot) atomicAdd(counts + i, tot);
     }
+    if (__any_sync(0xffffffffu, oob) && (threadIdx.x & 31u) == 0) atomicOr(counts + 3, 1u);
 }
 
 // ---- K1, plain rows with small operands: 64-bit integer arithmetic on the witness shadows ---------------------------------
-// A warp owns 32 consecutive rows.  Lane l reads row_meta[row0+l] (coalesced); a shuffle scan turns the lengths into term
-// offsets; the terms of the block are then handled TERM-parallel -- lane-contiguous column words (coalesced), one 4-byte
-// shadow gather each, all of a round's loads in flight together -- and each term's signed contribution c*w is parked in
-// shared memory; finally lane l sums its own row's three ranges and tests  Az*Bz + sum_C(-c)w == 0  as integers
-// (|Az|,|Bz| < 2^27, |Cz| < 2^27: nothing wraps, and |X| < p so X = 0 mod p iff X = 0).
+// A warp owns 64 consecutive rows, two per lane.  A shuffle scan turns the row lengths (row_meta, one coalesced 8-byte
+// load per lane) into term offsets; the block's terms are then handled TERM-parallel -- column words out of shared memory,
+// one 4-byte shadow gather each, four gathers in flight per lane -- and each term's signed contribution c*w replaces its
+// column word; finally every lane sums the three ranges of its two rows and tests  Az*Bz + sum_C(-c)w == 0  as integers
+// (|Az|,|Bz|,|Cz| < 2^27: nothing wraps, and |X| < p, so X = 0 mod p iff X = 0).
 // A row with an operand that is not small is appended to `deferred` and decided by check_rows<LIST>.
+//
+// Per-warp software pipeline over its blocks b, b+W, b+2W, ...:
+//   two blocks ahead   the block's term range [row_ptr[192b'], row_ptr[192(b'+1)]) is loaded into registers,
+//   one block ahead    its column words are brought into shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier,
+//                      double-buffered) and its row_meta words are loaded into registers,
+//   current block      scan, contributions, row sums.
+// Only the shadow gathers of the current block are exposed latency.  A block whose range does not fit the buffer (it
+// contains a fat row) is done thread-per-row straight from global memory.
 constexpr int kSmallThreads = 256;
-constexpr int32_t kPoison = (int32_t)0x80000000;
+constexpr uint32_t kSmallRows = 64;        // rows per warp and round
+constexpr uint32_t kPoisonBit = 1u << 28;  // added to a contribution whose operand is not small (see small_sum)
 
 __device__ __forceinline__ uint32_t ldg_early(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_early2(const uint32_t* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -441,101 +459,64 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
     }
 }
 
-// A term's contribution from the shadows, in two branch-free halves so that the gathers of several terms are issued
-// back to back (a branch between two gathers makes the second wait for the first).
-//   small_gather : column word -> shadow of its variable (index 0 of the inputs, i.e. ONE, stands in for "no load needed")
-//   small_value  : signed contribution c*w, kPoison when the operand is not small or the coefficient is full-width
+// Column word -> index into the shadow array (inputs at 0, aux at aux_off).
+__device__ __forceinline__ uint32_t shadow_index(uint32_t col, const CsrView& m) {
+    return (col & kColIdxMask) + (((int32_t)col >> 31) & m.aux_off);
+}
+// Shadow of a term's variable, with a bounds check (index 0 = ONE stands in when there is nothing to load); branch-free so
+// that the gathers of several terms are issued back to back.
 __device__ __forceinline__ uint32_t small_gather(uint32_t col, const CsrView& m, unsigned int& err) {
     const uint32_t cls = (col >> kColClsShift) & 7u;
-    const uint32_t idx = col & kColIdxMask;
-    const bool is_aux = (col & kColAux) != 0;
-    const bool oob = idx >= (is_aux ? m.n_aux : m.n_inputs);
-    const bool skip = oob || cls == kClsZero;
+    const bool oob = (col & kColIdxMask) >= ((col & kColAux) ? m.n_aux : m.n_inputs);
     if (oob && cls != kClsZero) err = 1;
-    const uint32_t* p = (is_aux && !skip) ? m.aux_s : m.inputs_s;
-    return __ldg(p + (skip ? 0u : idx));
+    return __ldg(m.shadow + ((oob || cls == kClsZero) ? 0u : shadow_index(col, m)));
 }
-__device__ __forceinline__ int32_t small_value(uint32_t col, uint32_t s, uint32_t k, const CsrView& m) {
-    const uint32_t cls = (col >> kColClsShift) & 7u;
-    // multiplier by class: GEN 0, P1 +1, M1 -1, P2 +2, M2 -2, PS +s, MS -s, ZERO 0  (one sign-extended nibble each)
-    uint32_t mult = (uint32_t)(((int32_t)(0x0F1E2F10u << (28u - 4u * cls))) >> 28);
-    if (cls == kClsPS || cls == kClsMS) mult *= __ldg(reinterpret_cast<const uint32_t*>(m.vals + 2 * (size_t)k));  // rare
-    const int32_t v = (int32_t)(mult * s);
-    return cls == kClsZero ? 0 : ((cls == kClsGen || s == kShadowBig) ? kPoison : v);
+// Contribution of a plain term (classes P1 M1 P2 M2 ZERO; anything else gives 0 and belongs to a row that is not plain):
+// multiplier from a nibble table indexed by the class, times the shadow; + kPoisonBit when the operand is not small.
+__device__ __forceinline__ uint32_t small_contrib(uint32_t col, uint32_t s) {
+    const uint32_t sh4 = (col >> (kColClsShift - 2)) & 28u;                // 4 * class
+    const int32_t mult = ((int32_t)((0x000E2F10u >> sh4) << 28)) >> 28;  // GEN 0, P1 +1, M1 -1, P2 +2, M2 -2, PS/MS/ZERO 0
+    return (s == kShadowBig && mult != 0) ? kPoisonBit : (uint32_t)(mult * (int32_t)s);
 }
 
-// Sum of n staged contributions; returns true when one of them was poisoned (operand not small, or a GEN coefficient).
-__device__ __forceinline__ bool small_sum(const int32_t* st, uint32_t n, int32_t& sum) {
-    bool bad = false;
-    int32_t a = 0;
+// Sum of n staged contributions.  A plain LC has at most 7 non-zero terms and |sum of the clean ones| < 2^27, so the number
+// of poisoned terms can be read off the total: bits 28.. of (sum + 2^27) are zero iff none was.
+__device__ __forceinline__ uint32_t small_sum(const uint32_t* q, uint32_t n) {
+    uint32_t a = 0;
 #pragma unroll 1
-    for (uint32_t j = 0; j < n; ++j) {
-        const int32_t v = st[j];
-        bad |= (v == kPoison);
-        a += v;
-    }
-    sum = a;
-    return bad;
+    for (uint32_t j = 0; j < n; ++j) a += q[j];
+    return a;
+}
+__device__ __forceinline__ bool small_poisoned(uint32_t a) { return ((a + (1u << 27)) >> 28) != 0u; }
+
+// One row from its three sums: 0 = holds, 1 = fails, 2 = needs the full-width path.
+__device__ __forceinline__ uint32_t small_verdict(uint32_t a, uint32_t b, uint32_t c) {
+    if (small_poisoned(a) | small_poisoned(b) | small_poisoned(c)) return 2u;
+    return ((long long)(int32_t)a * (long long)(int32_t)b + (long long)(int32_t)c) != 0ll ? 1u : 0u;
 }
 
-// buf[0..nt) holds column words (FROM_SMEM) or is filled from cols[k0..k0+nt): replace every word by its contribution.
-// Term-parallel: lane-contiguous words, four rounds of shadow gathers in flight per lane.
-template <bool FROM_SMEM>
-__device__ __forceinline__ void small_stage(uint32_t* buf, uint32_t nt, uint32_t k0, const CsrView& m, unsigned int& err) {
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t t0 = 0; t0 < nt; t0 += 128u) {
-        uint32_t col[4];
+// One plain row by its own thread straight from global memory (blocks that do not fit the staging buffer).
+__device__ __forceinline__ uint32_t small_row_direct(uint32_t row, const CsrView& m) {
+    const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
+                   p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
+    uint32_t sum[3] = {0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t t = t0 + 32u * j + lane;
-            col[j] = t < nt ? (FROM_SMEM ? buf[t] : __ldg(m.cols + k0 + t)) : (kClsZero << kColClsShift);
-        }
-        uint32_t sh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sh[j] = small_gather(col[j], m, err);
-        int32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = small_value(col[j], sh[j], k0 + t0 + 32u * j + lane, m);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t t = t0 + 32u * j + lane;
-            if (t < nt) buf[t] = (uint32_t)v[j];
+    for (int i = 0; i < 3; ++i) {
+        const uint32_t k0 = i == 0 ? p0 : (i == 1 ? p1 : p2), k1 = i == 0 ? p1 : (i == 1 ? p2 : p3);
+#pragma unroll 1
+        for (uint32_t k = k0; k < k1; ++k) {
+            const uint32_t col = __ldg(m.cols + k);
+            const uint32_t cls = (col >> kColClsShift) & 7u;
+            sum[i] += small_contrib(col, __ldg(m.shadow + (cls == kClsZero ? 0u : shadow_index(col, m))));
         }
     }
+    return small_verdict(sum[0], sum[1], sum[2]);
 }
 
-// Row phase: the lane's row (if `mine`) has its contributions at q[0 .. la+lb+lc).  Deferred rows are appended warp-aggregated.
-__device__ __forceinline__ void small_rows(const int32_t* q, bool mine, uint32_t la, uint32_t lb, uint32_t lc, uint32_t row, uint32_t& my_bad,
-                                           uint32_t* __restrict__ deferred, uint32_t* __restrict__ n_deferred) {
-    const uint32_t lane = threadIdx.x & 31u;
-    bool defer = false;
-    if (mine) {
-        int32_t a, b, c;
-        bool bad = small_sum(q, la, a);
-        bad |= small_sum(q + la, lb, b);
-        bad |= small_sum(q + la + lb, lc, c);
-        if (bad) defer = true;
-        else if ((long long)a * (long long)b + (long long)c != 0ll && row < my_bad) my_bad = row;
-    }
-    const uint32_t dmask = __ballot_sync(0xffffffffu, defer);
-    if (dmask) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(n_deferred, (uint32_t)__popc(dmask));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (defer) deferred[base + (uint32_t)__popc(dmask & ((1u << lane) - 1u))] = row;
-    }
-}
-
-// Per-warp software pipeline over the warp's blocks b, b+W, b+2W, ...:
-//   two blocks ahead   the block's term range [row_ptr[96b'], row_ptr[96(b'+1)]) is loaded into registers,
-//   one block ahead    its column words are brought into shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier,
-//                      double-buffered) and its row_meta word is loaded into a register,
-//   current block      scan of the lengths -> term offsets, contributions in place of the column words, row sums.
-// Only the shadow gathers of the current block are exposed latency.  A block whose range does not fit the buffer (it
-// contains a fat row) is read with plain loads in groups of rows that fit.
-__global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, CheckOut o, uint32_t* __restrict__ deferred,
+__global__ void __launch_bounds__(kSmallThreads, 4) check_small(CsrView m, CheckOut o, uint32_t* __restrict__ deferred,
                                                                 uint32_t* __restrict__ n_deferred) {
-    __shared__ __align__(16) uint32_t s_buf[kSmallThreads / 32][2][kSmallCap];
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    uint32_t(*s_buf)[2][kSmallCap] = reinterpret_cast<uint32_t(*)[2][kSmallCap]>(small_smem);
     __shared__ __align__(8) unsigned long long s_bar[kSmallThreads / 32][2];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     if (lane == 0) {
@@ -545,15 +526,20 @@ __global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, Check
     }
     __syncwarp();
     uint32_t my_bad = 0xffffffffu;
-    unsigned int my_err = 0;
-    const uint32_t n_blocks = (m.n_rows + 31u) / 32u;
+    const uint32_t n_blocks = (m.n_rows + kSmallRows - 1u) / kSmallRows;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t b0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    // (volatile: issued HERE, one iteration before they are needed, not sunk to their first use)
-    auto range_lo = [&](uint32_t b) { return ldg_early(m.row_ptr + 96 * (size_t)b); };
-    auto range_hi = [&](uint32_t b) { return ldg_early(m.row_ptr + 3 * (size_t)min(32u * (b + 1u), m.n_rows)); };
-    auto load_meta = [&](uint32_t b) { return 32u * b + lane < m.n_rows ? ldg_early(m.row_meta + 32u * b + lane) : (kRowGeneric << 24); };
+    // (volatile loads: issued HERE, one iteration before they are needed, not sunk to their first use)
+    auto range_lo = [&](uint32_t b) { return ldg_early(m.row_ptr + 3 * (size_t)kSmallRows * b); };
+    auto range_hi = [&](uint32_t b) { return ldg_early(m.row_ptr + 3 * (size_t)min(kSmallRows * (b + 1u), m.n_rows)); };
+    auto load_meta = [&](uint32_t b) {  // the lane's two rows; row_meta is padded to an even number of words
+        const uint32_t r = kSmallRows * b + 2u * lane;
+        uint2 v = make_uint2(kRowGeneric << 24, kRowGeneric << 24);
+        if (r < m.n_rows) v = ldg_early2(m.row_meta + r);
+        if (r + 1u >= m.n_rows) v.y = kRowGeneric << 24;
+        return v;
+    };
     // copy the words [kb & ~3, roundup4(ke)) of cols into a stage; false when they do not fit
     auto issue_copy = [&](uint32_t kb, uint32_t ke, uint32_t stage) {
         const uint32_t w0 = kb & ~3u, w1 = (ke + 3u) & ~3u;
@@ -565,80 +551,103 @@ __global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, Check
         return true;
     };
 
-    if (b0 >= n_blocks) {  // (keeps publish_first_bad's barriers uniform)
-        publish_first_bad(my_bad, m, o, my_err);
-        return;
-    }
-    // prologue: block b0 staged, block b0+W's range in registers
-    uint32_t kb_cur = range_lo(b0), ke_cur = range_hi(b0);
-    uint32_t meta_cur = load_meta(b0);
-    bool copied_cur = issue_copy(kb_cur, ke_cur, 0);
-    uint32_t kb_nxt = 0, ke_nxt = 0;
-    if (b0 + n_warps < n_blocks) { kb_nxt = range_lo(b0 + n_warps); ke_nxt = range_hi(b0 + n_warps); }
-    uint32_t it = 0, phase = 0;  // phase bit s: parity the next wait on stage s expects (copies and waits pair up per stage)
-    for (uint32_t blk = b0; blk < n_blocks; blk += n_warps, ++it) {
-        const uint32_t stage = it & 1u;
-        const uint32_t b_nxt = blk + n_warps, b_nn = blk + 2u * n_warps;
-        // 1. loads for the blocks ahead (consumed in the next iteration)
-        uint32_t meta_nxt = kRowGeneric << 24, kb_nn = 0, ke_nn = 0;
-        if (b_nxt < n_blocks) meta_nxt = load_meta(b_nxt);
-        if (b_nn < n_blocks) { kb_nn = range_lo(b_nn); ke_nn = range_hi(b_nn); }
-        // 2. the next block's column words: the other stage is free (its rows were finished before the last __syncwarp)
-        bool copied_nxt = false;
-        if (b_nxt < n_blocks) copied_nxt = issue_copy(kb_nxt, ke_nxt, stage ^ 1u);
-        // 3. the current block
-        const uint32_t row0 = blk * 32u, row = row0 + lane;
-        const uint32_t la = meta_cur & 255u, lb = (meta_cur >> 8) & 255u, lc = (meta_cur >> 16) & 255u, kind = meta_cur >> 24;
-        const bool noenc = la == kMetaNoLens;
-        const uint32_t noenc_mask = __ballot_sync(0xffffffffu, noenc);
-        const bool any_plain = __ballot_sync(0xffffffffu, kind == kRowPlain) != 0u;
-        uint32_t nt = la + lb + lc;
-        if (noenc && any_plain) nt = __ldg(m.row_ptr + 3 * (size_t)row + 3) - __ldg(m.row_ptr + 3 * (size_t)row);
-        uint32_t incl = nt;  // inclusive scan of the term counts
+    if (b0 < n_blocks) {
+        // prologue: block b0 staged, block b0+W's range in registers
+        uint32_t kb_cur = range_lo(b0), ke_cur = range_hi(b0);
+        uint2 meta_cur = load_meta(b0);
+        bool copied_cur = issue_copy(kb_cur, ke_cur, 0);
+        uint32_t kb_nxt = 0, ke_nxt = 0;
+        if (b0 + n_warps < n_blocks) { kb_nxt = range_lo(b0 + n_warps); ke_nxt = range_hi(b0 + n_warps); }
+        uint32_t it = 0, phase = 0;  // phase bit s: parity the next wait on stage s expects (copies and waits pair up per stage)
+        for (uint32_t blk = b0; blk < n_blocks; blk += n_warps, ++it) {
+            const uint32_t stage = it & 1u;
+            const uint32_t b_nxt = blk + n_warps, b_nn = blk + 2u * n_warps;
+            // 1. loads for the blocks ahead (consumed in the next iteration)
+            uint2 meta_nxt = make_uint2(kRowGeneric << 24, kRowGeneric << 24);
+            uint32_t kb_nn = 0, ke_nn = 0;
+            if (b_nxt < n_blocks) meta_nxt = load_meta(b_nxt);
+            if (b_nn < n_blocks) { kb_nn = range_lo(b_nn); ke_nn = range_hi(b_nn); }
+            // 2. the next block's column words: the other stage is free (its rows were finished before the last __syncwarp)
+            bool copied_nxt = false;
+            if (b_nxt < n_blocks) copied_nxt = issue_copy(kb_nxt, ke_nxt, stage ^ 1u);
+            // 3. the current block
+            const uint32_t row = blk * kSmallRows + 2u * lane;
+            const bool plain0 = (meta_cur.x >> 24) == kRowPlain, plain1 = (meta_cur.y >> 24) == kRowPlain;
+            const bool any_plain = __any_sync(0xffffffffu, plain0 || plain1);
+            uint32_t verdict0 = 0, verdict1 = 0;
+            if (copied_cur) {
+                if (ke_cur > kb_cur) {
+                    mbar_wait(&s_bar[wib][stage], (phase >> stage) & 1u);
+                    phase ^= 1u << stage;
+                }
+                if (any_plain) {
+                    const uint32_t la0 = meta_cur.x & 255u, lb0 = (meta_cur.x >> 8) & 255u, lc0 = (meta_cur.x >> 16) & 255u;
+                    const uint32_t la1 = meta_cur.y & 255u, lb1 = (meta_cur.y >> 8) & 255u, lc1 = (meta_cur.y >> 16) & 255u;
+                    uint32_t nt0 = la0 + lb0 + lc0, nt1 = la1 + lb1 + lc1;
+                    // (a row whose lengths are not encodable is not plain; it only matters for the offsets of the rows after it)
+                    if (la0 == kMetaNoLens) nt0 = __ldg(m.row_ptr + 3 * (size_t)row + 3) - __ldg(m.row_ptr + 3 * (size_t)row);
+                    if (la1 == kMetaNoLens) nt1 = __ldg(m.row_ptr + 3 * (size_t)row + 6) - __ldg(m.row_ptr + 3 * (size_t)row + 3);
+                    uint32_t incl = nt0 + nt1;  // inclusive scan of the lanes' term counts
 #pragma unroll
-        for (uint32_t d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
+                    for (uint32_t d = 1; d < 32; d <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    const uint32_t off0 = incl - nt0 - nt1;
+                    uint32_t* terms = s_buf[wib][stage] + (kb_cur & 3u);
+                    const uint32_t nt = ke_cur - kb_cur;
+                    // term-parallel: column word -> contribution, in place
+                    for (uint32_t t0 = 0; t0 < nt; t0 += 128u) {
+                        uint32_t col[4], sh[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t t = t0 + 32u * j + lane;
+                            col[j] = t < nt ? terms[t] : (kClsZero << kColClsShift);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            sh[j] = __ldg(m.shadow + (((col[j] >> kColClsShift) & 7u) == kClsZero ? 0u : shadow_index(col[j], m)));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t t = t0 + 32u * j + lane;
+                            if (t < nt) terms[t] = small_contrib(col[j], sh[j]);
+                        }
+                    }
+                    __syncwarp();
+                    if (plain0) {
+                        const uint32_t* q = terms + off0;
+                        verdict0 = small_verdict(small_sum(q, la0), small_sum(q + la0, lb0), small_sum(q + la0 + lb0, lc0));
+                    }
+                    if (plain1) {
+                        const uint32_t* q = terms + off0 + nt0;
+                        verdict1 = small_verdict(small_sum(q, la1), small_sum(q + la1, lb1), small_sum(q + la1 + lb1, lc1));
+                    }
+                }
+            } else if (any_plain) {
+                if (plain0) verdict0 = small_row_direct(row, m);
+                if (plain1) verdict1 = small_row_direct(row + 1u, m);
+            }
+            if (verdict0 == 1u && row < my_bad) my_bad = row;
+            if (verdict1 == 1u && row + 1u < my_bad) my_bad = row + 1u;
+            // deferred rows, appended warp-aggregated
+            const uint32_t d0 = __ballot_sync(0xffffffffu, verdict0 == 2u), d1 = __ballot_sync(0xffffffffu, verdict1 == 2u);
+            if (d0 | d1) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(n_deferred, (uint32_t)(__popc(d0) + __popc(d1)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t below = (1u << lane) - 1u;
+                if (verdict0 == 2u) deferred[base + (uint32_t)__popc(d0 & below)] = row;
+                if (verdict1 == 2u) deferred[base + (uint32_t)__popc(d0) + (uint32_t)__popc(d1 & below)] = row + 1u;
+            }
+            __syncwarp();  // every lane is done with this stage before it is refilled
+            // 4. rotate
+            kb_cur = kb_nxt; ke_cur = ke_nxt; meta_cur = meta_nxt; copied_cur = copied_nxt;
+            kb_nxt = kb_nn; ke_nxt = ke_nn;
         }
-        const uint32_t off = incl - nt;
-        uint32_t* buf = s_buf[wib][stage];
-        if (copied_cur) {
-            if (ke_cur > kb_cur) {
-                mbar_wait(&s_bar[wib][stage], (phase >> stage) & 1u);
-                phase ^= 1u << stage;
-            }
-            if (any_plain) {
-                uint32_t* terms = buf + (kb_cur & 3u);
-                small_stage<true>(terms, ke_cur - kb_cur, kb_cur, m, my_err);
-                __syncwarp();
-                small_rows(reinterpret_cast<const int32_t*>(terms) + off, kind == kRowPlain, la, lb, lc, row, my_bad, deferred, n_deferred);
-            }
-        } else if (any_plain) {
-            uint32_t done = 0;
-            while (done < 32u) {
-                const uint32_t rest = noenc_mask >> done;
-                if (rest & 1u) { ++done; continue; }
-                const uint32_t stop = rest ? done + (uint32_t)__ffs((int)rest) - 1u : 32u;  // first lane we cannot stage
-                const uint32_t base_off = __shfl_sync(0xffffffffu, off, done);
-                const bool fits = lane >= done && lane < stop && (incl - base_off) <= kSmallCap;
-                const uint32_t r = max(1u, (uint32_t)__popc(__ballot_sync(0xffffffffu, fits)));
-                const uint32_t nt_g = min(kSmallCap, __shfl_sync(0xffffffffu, incl, done + r - 1u) - base_off);
-                small_stage<false>(buf, nt_g, kb_cur + base_off, m, my_err);
-                __syncwarp();
-                // (a generic row longer than the buffer can only be the single row of its group: it is not plain, nobody reads it)
-                small_rows(reinterpret_cast<const int32_t*>(buf) + (off - base_off), lane >= done && lane < done + r && kind == kRowPlain, la,
-                           lb, lc, row, my_bad, deferred, n_deferred);
-                __syncwarp();  // the buffer is reused by the next group
-                done += r;
-            }
-        }
-        __syncwarp();  // every lane is done with this stage before it is refilled
-        // 4. rotate
-        kb_cur = kb_nxt; ke_cur = ke_nxt; meta_cur = meta_nxt; copied_cur = copied_nxt;
-        kb_nxt = kb_nn; ke_nxt = ke_nn;
     }
-    publish_first_bad(my_bad, m, o, my_err);
+    publish_first_bad(my_bad, m, o, 0u);
 }
+constexpr size_t kSmallSmem = (size_t)(kSmallThreads / 32) * 2 * kSmallCap * 4;
 
 // 17-limb sum across the warp; every lane ends with the total.
 __device__ __forceinline__ void warp_sum17(uint32_t* acc) {
@@ -781,7 +790,7 @@ __device__ __forceinline__ void fold_lane_slow(uint32_t* acc, uint32_t k0, uint3
         const uint32_t idx = col & kColIdxMask;
         const bool is_aux = (col & kColAux) != 0;
         if (idx >= (is_aux ? m.n_aux : m.n_inputs)) continue;  // reported by pass 1
-        if (!shadow_slow<IS_C>(cls, __ldg((is_aux ? m.aux_s : m.inputs_s) + idx))) continue;
+        if (!shadow_slow<IS_C>(cls, __ldg(m.shadow + (is_aux ? m.aux_off : 0u) + idx))) continue;
         TermW t;
         t.cls = cls;
         ld8(t.w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx);

@@ -193,7 +193,7 @@ def _gadget_like_instance(fid, seed, n_rows, n_aux, big_every):
         else:
             aux.append(rng.choice(edge) if rng.random() < 0.02 else rng.choice(small))
     inputs = [1, 5, 0]
-    coef_small = [1, 1, 1, p - 1, p - 1, 2, p - 2, 3, p - 3, 0, 5, p - 7]
+    coef_small = [1, 1, 1, p - 1, p - 1, 2, p - 2, 1, p - 1, 0, 1, 3]
 
     def val(col):
         return aux[col & 0x7FFFFFFF] if col & 0x80000000 else inputs[col]
