@@ -42,25 +42,29 @@ struct bp_cs {
 
     uint64_t n_rows = 0, nnz = 0, n_inputs = 0, n_aux = 0, row_base = 0;
     uint64_t n_gen = 0;  // terms that need a full 256x256 product (drives the kernel-configuration heuristic)
-    DevBuf row_ptr, cols, vals, inputs, aux;
+    DevBuf row_ptr, cols, vals, kexp, inputs, aux;
     DevBuf shadow;             // witness shadows (u32 per element, kernels.cuh: shadow_of): inputs at [0, n_inputs), aux at
     uint64_t shadow_aux_off = 1u << 16;  // [shadow_aux_off, +n_aux): one array, so that a column word maps to one 32-bit index
     bool cols_in_range = true; // plan: every column index of every row exists (checked when the plan is built)
+    bool fat_int_ok = false;   // plan: the fat rows have term words for the integer pass
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
     DevBuf u8_stage;           // packed witness uploads land here before widen_u8
-    DevBuf row_meta;           // plan: lengths + RowKind per row
+    DevBuf row_meta;           // plan: offset + lengths + RowKind per row (kernels.cuh: meta_pack)
+    DevBuf scols;              // plan: per term, the word check_small works from
     DevBuf fat_rows;           // plan: rows handled by check_fat_rows (+ one u32 counter at the end)
     DevBuf gen_rows;           // plan: rows of kind Generic when the instance also has plain rows (+ counter)
     DevBuf deferred;           // per check: plain rows check_small handed to check_rows
+    DevBuf fat_undecided;      // per check: fat rows check_fat_int handed to check_fat_rows
     uint64_t n_fat_rows = 0, n_gen_rows = 0, n_plain_rows = 0;  // plan statistics (host copies)
     uint64_t fat_terms = 96;   // rows with more terms than this go to the warp-per-row kernel
     int64_t fat_ctas_per_sm = 8;  // grid of check_fat_rows = sm_count * this
     int64_t kernels_mask = 3;  // measurement aid: bit 0 = launch the thin-row kernels, bit 1 = launch check_fat_rows
-    int64_t variant = -1;      // < 0: default; >= 0: bit 0 = no small-row kernel, bit 1 = no shadows in the fat kernel, bit 2 = park az/bz
+    int64_t variant = -1;      // < 0: default; >= 0: bit 0 = no small-row kernel, bit 1 = no shadows in the fat kernel, bit 2 = park az/bz,
+                               // bit 3 = no integer pass over the fat rows
     bool plan_valid = false;
     long long* d_result = nullptr;  // [0] first_bad
     unsigned int* d_err = nullptr;  // [0] err word, [1] GEN-term counter of the last ingest call
-    uint32_t* d_ndef = nullptr;     // number of rows in `deferred`
+    uint32_t* d_ndef = nullptr;     // [0] number of rows in `deferred`, [1] in `fat_undecided`
     void* h_pinned_small = nullptr;  // 64 B: [0,32) element, [32,40) first_bad, [40,44) err word, [48,56) tiny row_ptr
     void* h_stage[kNumStage] = {nullptr, nullptr};
     cudaEvent_t stage_ev[kNumStage] = {nullptr, nullptr};
@@ -130,7 +134,7 @@ uint32_t* shadow_ptr(bp_cs* h, int is_aux) { return (uint32_t*)h->shadow.p + (is
 // offset; outgrowing the input region (rare: circuits have few public inputs) moves it.
 int ensure_shadow(bp_cs* h, uint64_t need_in, uint64_t need_aux) {
     uint64_t off = h->shadow_aux_off;
-    while (need_in > off) off *= 4;
+    while (need_in + 1 > off) off *= 4;  // the last slot of the input region stays 0: the null term word points at it
     if (off + need_aux >= 0xffffffffull) return fail(h, BP_E_RANGE, "too many variables for one handle");
     const size_t have = h->shadow.cap / 4;
     if (off == h->shadow_aux_off && off + need_aux <= have) return BP_OK;
@@ -155,8 +159,10 @@ int ensure_shadow(bp_cs* h, uint64_t need_in, uint64_t need_aux) {
         CU(h, cudaStreamSynchronize(h->stream));
         CU(h, cudaFree(h->shadow.p));
     }
+    CU(h, cudaMemsetAsync((uint32_t*)np + off - 1, 0, 4, h->stream));
     h->shadow.p = np;
     h->shadow.cap = bytes;
+    if (off != h->shadow_aux_off) h->plan_valid = false;  // the plan's term words hold shadow indices
     h->shadow_aux_off = off;
     return BP_OK;
 }
@@ -189,11 +195,13 @@ CsrView view(const bp_cs* h) {
     m.row_ptr = (const uint32_t*)h->row_ptr.p;
     m.cols = (const uint32_t*)h->cols.p;
     m.vals = (const uint4*)h->vals.p;
+    m.kexp = (const uint16_t*)h->kexp.p;
     m.inputs = (const uint4*)h->inputs.p;
     m.aux = (const uint4*)h->aux.p;
     m.shadow = (const uint32_t*)h->shadow.p;
     m.aux_off = (uint32_t)h->shadow_aux_off;
     m.row_meta = (const uint32_t*)h->row_meta.p;
+    m.scols = (const uint32_t*)h->scols.p;
     m.n_rows = (uint32_t)h->n_rows;
     m.n_inputs = (uint32_t)h->n_inputs;
     m.n_aux = (uint32_t)h->n_aux;
@@ -264,7 +272,7 @@ constexpr int kVDefault = kVMagSkip | kVBitRow;
 struct RowKindIs {
     const uint32_t* meta;
     uint32_t kind;
-    __host__ __device__ bool operator()(uint32_t row) const { return (meta[row] >> 24) == kind; }
+    __host__ __device__ bool operator()(uint32_t row) const { return meta_kind(meta[row]) == kind; }
 };
 
 // Ascending list of the rows whose kind is `kind` (stable selection: warps that run at the same time then work on
@@ -294,12 +302,16 @@ int ensure_plan(bp_cs* h) {
         int rc = ensure(h, h->row_meta, ((size_t)n + 1) * 4, 0);
         if (rc != BP_OK) return rc;
         if ((rc = ensure(h, h->scratch, 16, 0)) != BP_OK) return rc;
+        const size_t n_scols = (((size_t)h->nnz + 3) & ~size_t(3)) + 4;  // whole 16-byte groups, and one past the end
+        if ((rc = ensure(h, h->scols, n_scols * 4, 0)) != BP_OK) return rc;
         uint32_t* d_cnt = (uint32_t*)h->scratch.p;
         CU(h, cudaMemsetAsync(d_cnt, 0, 16, h->stream));
+        fill_u32<<<grid_for(h, n_scols, 256, 8), 256, 0, h->stream>>>((uint32_t*)h->scols.p, n_scols, (uint32_t)h->shadow_aux_off - 1u);
         build_row_meta<<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p, n,
                                                                        (uint32_t)h->fat_terms, (uint32_t)h->n_inputs, (uint32_t)h->n_aux,
-                                                                       (uint32_t*)h->row_meta.p, d_cnt);
-        h->launches++;
+                                                                       (uint32_t)h->shadow_aux_off, (uint32_t*)h->row_meta.p,
+                                                                       (uint32_t*)h->scols.p, d_cnt);
+        h->launches += 2;
         CU(h, cudaGetLastError());
         uint32_t* hc = (uint32_t*)((char*)h->h_pinned_small + 48);
         CU(h, cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, h->stream));
@@ -309,9 +321,22 @@ int ensure_plan(bp_cs* h) {
         h->n_fat_rows = hc[kRowFat];
         h->cols_in_range = hc[3] == 0;  // (rows with a column that does not exist are generic: check_rows reports them)
         if ((rc = select_rows(h, h->fat_rows, kRowFat, h->n_fat_rows)) != BP_OK) return rc;
+        h->fat_int_ok = false;
+        if (h->n_fat_rows) {
+            CU(h, cudaMemsetAsync(d_cnt, 0, 4, h->stream));
+            build_fat_words<<<grid_for(h, h->n_fat_rows * 32, 128, 16), 128, 0, h->stream>>>(
+                (const uint32_t*)h->fat_rows.p, (uint32_t)h->n_fat_rows, (const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p,
+                (uint32_t)h->n_inputs, (uint32_t)h->n_aux, (uint32_t)h->shadow_aux_off, (uint32_t*)h->scols.p, (uint16_t*)h->kexp.p, d_cnt);
+            h->launches++;
+            CU(h, cudaGetLastError());
+            CU(h, cudaMemcpyAsync(hc, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaStreamSynchronize(h->stream));
+            h->fat_int_ok = hc[0] == 0;
+        }
         // the generic list is only needed when the thin rows are split between check_small and check_rows
         if ((rc = select_rows(h, h->gen_rows, kRowGeneric, h->n_plain_rows ? h->n_gen_rows : 0)) != BP_OK) return rc;
         if ((rc = ensure(h, h->deferred, std::max<size_t>((size_t)h->n_plain_rows * 4, 4), 0)) != BP_OK) return rc;
+        if ((rc = ensure(h, h->fat_undecided, std::max<size_t>((size_t)h->n_fat_rows * 4, 4), 0)) != BP_OK) return rc;
     }
     h->plan_valid = true;
     return BP_OK;
@@ -376,7 +401,7 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
         if (h->kernels_mask & 1) {
             if (use_small) {
                 const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;  // one warp per block of rows
-                const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 4);
+                const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
                 CU(h, cudaFuncSetAttribute(check_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
                 check_small<<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
                 h->launches++;
@@ -397,12 +422,20 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             }
         }
         if ((h->kernels_mask & 2) && h->n_fat_rows) {
-            if (fat_shadow) {
+            if (fat_shadow && !(v & 8) && h->fat_int_ok) {  // integer pass first; the modular kernel takes what it could not decide
+                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * 6);
+                DISPATCH_FIELD(h, (check_fat_int<F><<<igrid, block, 0, h->stream>>>(m, o, fat, (uint32_t)h->n_fat_rows,
+                                                                                 (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fat_grid, block, 0, h->stream>>>(
+                                      m, o, h->fc, (const uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+                h->launches += 2;
+            } else if (fat_shadow) {
                 DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));
+                h->launches++;
             } else {
                 DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));
+                h->launches++;
             }
-            h->launches++;
         }
     }
 #undef BP_LAUNCH
@@ -461,6 +494,7 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     if (reserve_nnz) {
         if (ensure(h, h->cols, (size_t)reserve_nnz * 4, 0) != BP_OK) return bail(BP_E_OOM);
         if (ensure(h, h->vals, (size_t)reserve_nnz * 32, 0) != BP_OK) return bail(BP_E_OOM);
+        if (ensure(h, h->kexp, (size_t)reserve_nnz * 2, 0) != BP_OK) return bail(BP_E_OOM);
     }
     if (ensure(h, h->row_ptr, 4, 0) != BP_OK) return bail(BP_E_OOM);
     if (cudaMemsetAsync(h->row_ptr.p, 0, 4, h->stream) != cudaSuccess) return bail(BP_E_CUDA);
@@ -473,8 +507,8 @@ void bp_cs_free(bp_cs* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->inputs, &h->aux, &h->shadow, &h->scan_tmp, &h->scratch, &h->u8_stage,
-                      &h->row_meta, &h->fat_rows, &h->gen_rows, &h->deferred})
+    for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->kexp, &h->inputs, &h->aux, &h->shadow, &h->scan_tmp, &h->scratch, &h->u8_stage,
+                      &h->row_meta, &h->scols, &h->fat_rows, &h->gen_rows, &h->deferred, &h->fat_undecided})
         if (b->p) cudaFree(b->p);
     if (h->d_result) cudaFree(h->d_result);
     if (h->h_pinned_small) cudaFreeHost(h->h_pinned_small);
@@ -546,13 +580,14 @@ int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
         *v = (int64_t)(key[0] == 'f' ? h->n_fat_rows : (key[0] == 'p' ? h->n_plain_rows : h->n_gen_rows));
         return BP_OK;
     }
-    if (!std::strcmp(key, "deferred_rows")) {  // plain rows the last check handed to the full-width kernel
+    // plain rows / fat rows the last check handed on to the full-width kernels
+    if (!std::strcmp(key, "deferred_rows") || !std::strcmp(key, "fat_undecided_rows")) {
         CU(h, cudaSetDevice(h->device));
-        CU(h, cudaMemcpyAsync(h->h_pinned_small, h->d_ndef, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(h->h_pinned_small, h->d_ndef, 8, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
-        uint32_t n;
-        std::memcpy(&n, h->h_pinned_small, 4);
-        *v = n;
+        uint32_t n[2];
+        std::memcpy(n, h->h_pinned_small, 8);
+        *v = n[key[0] == 'f' ? 1 : 0];
         return BP_OK;
     }
     return fail(h, BP_E_ARG, "unknown option '%s'", key);
@@ -708,6 +743,7 @@ int bp_cs_enforce(bp_cs* h, uint64_t n_rows, const uint32_t* lens, const uint32_
     if ((rc = ensure(h, h->row_ptr, (lc_old + lc_add + 1) * 4, (lc_old + 1) * 4)) != BP_OK) return rc;
     if ((rc = ensure(h, h->cols, (size_t)(h->nnz + add) * 4, (size_t)h->nnz * 4)) != BP_OK) return rc;
     if ((rc = ensure(h, h->vals, (size_t)(h->nnz + add) * 32, (size_t)h->nnz * 32)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->kexp, (size_t)(h->nnz + add) * 2, (size_t)h->nnz * 2)) != BP_OK) return rc;
     uint32_t* rp = (uint32_t*)h->row_ptr.p;
     // lens -> row_ptr[lc_old .. lc_old+lc_add] : exclusive scan of (lens ++ [0]) then + nnz
     // stage the lens right where the scan output goes, shifted by one slot so in-place scan is safe
@@ -731,7 +767,7 @@ int bp_cs_enforce(bp_cs* h, uint64_t n_rows, const uint32_t* lens, const uint32_
         DISPATCH_FIELD(h, (classify_lcs<F><<<grid_for(h, lc_add, 128, 16), 128, 0, h->stream>>>((const uint4*)h->vals.p, rp, (uint32_t)lc_old,
                                                                                           (uint32_t)lc_add, kind)));
         DISPATCH_FIELD(h, (convert_terms<F><<<grid_for(h, add, 128, 16), 128, 0, h->stream>>>(
-                              (uint4*)h->vals.p, (uint32_t*)h->cols.p, rp, kind, (uint32_t)lc_old, (uint32_t)lc_add, (uint32_t)h->nnz,
+                              (uint4*)h->vals.p, (uint32_t*)h->cols.p, (uint16_t*)h->kexp.p, rp, kind, (uint32_t)lc_old, (uint32_t)lc_add, (uint32_t)h->nnz,
                               (uint32_t)add, h->fc, h->d_err)));
         h->launches += 2;
         CU(h, cudaGetLastError());
@@ -856,6 +892,7 @@ int bp_cs_synth_rows(bp_cs* h, uint64_t seed, uint32_t t, uint64_t n_vars, uint6
     }
     if ((rc = ensure(h, h->cols, (size_t)(h->nnz + add) * 4, (size_t)h->nnz * 4)) != BP_OK) return rc;
     if ((rc = ensure(h, h->vals, (size_t)(h->nnz + add) * 32, (size_t)h->nnz * 32)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->kexp, (size_t)(h->nnz + add) * 2, (size_t)h->nnz * 2)) != BP_OK) return rc;  // (unspecified: GEN terms)
     DISPATCH_FIELD(h, (synth_fill<F><<<grid_for(h, lc_add, 128, 16), 128, 0, h->stream>>>(
                           (uint32_t*)h->cols.p, (uint4*)h->vals.p, rp, (uint32_t)lc_old, (uint32_t)lc_add, seed, 3 * row0, n_vars, n_inputs,
                           h->fc)));

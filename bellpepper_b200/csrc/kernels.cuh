@@ -41,11 +41,13 @@ struct CsrView {
     const uint32_t* __restrict__ row_ptr;
     const uint32_t* __restrict__ cols;
     const uint4* __restrict__ vals;
+    const uint16_t* __restrict__ kexp;  // packed exponents of the terms whose class is POW2P / POW2M (others: unspecified)
     const uint4* __restrict__ inputs;
     const uint4* __restrict__ aux;
     const uint32_t* __restrict__ shadow;    // witness shadows (the value when it is < 2^24, else kShadowBig): inputs at
     uint32_t aux_off;                       // [0, n_inputs), aux at [aux_off, aux_off + n_aux)
-    const uint32_t* __restrict__ row_meta;  // plan: |A| | |B|<<8 | |C|<<16 | RowKind<<24   (lengths 255,0,0 = not encodable)
+    const uint32_t* __restrict__ row_meta;  // plan: per row, see meta_pack
+    const uint32_t* __restrict__ scols;     // plan: per term, the word check_small works from (small_word)
     uint32_t n_rows;
     uint32_t n_inputs;
     uint32_t n_aux;
@@ -68,8 +70,16 @@ enum RowKind : uint32_t {
                       // check_small decides it from the witness shadows when every value it touches is small
     kRowFat = 2       // check_fat_rows
 };
-constexpr uint32_t kMetaNoLens = 255u;
-constexpr uint32_t kSmallCap = 768;  // words per staging buffer of check_small; a plain row has at most this many terms
+// row_meta word: bits 0..9 = offset of the row's first term from the first term of its 64-row block (saturating),
+// bits 10..17 = |A|, bits 18..25 = |B| (both saturating at 255; a plain row has every length <= 254), bits 26..27 = RowKind.
+// |C| of a row is the next row's offset minus its own offset, |A| and |B|.
+constexpr uint32_t kSmallRows = 64;  // rows per warp and round of check_small
+constexpr uint32_t kSmallCap = 640;  // words per staging buffer of check_small; a block with more terms is done row by row
+constexpr uint32_t kMetaOffMask = 1023u;
+__host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t off, uint32_t la, uint32_t lb, uint32_t kind) {
+    return (off < kMetaOffMask ? off : kMetaOffMask) | ((la < 255u ? la : 255u) << 10) | ((lb < 255u ? lb : 255u) << 18) | (kind << 26);
+}
+__host__ __device__ __forceinline__ uint32_t meta_kind(uint32_t meta) { return (meta >> 26) & 3u; }
 
 // Witness shadow: a second, 4-byte copy of every witness element, maintained wherever the witness is written.
 // Gadget circuits (sha256, blake2s, boolean, uint32) have bit- or byte-valued witnesses; a row whose operands are all
@@ -123,30 +133,24 @@ template <int F, int RIPPLE>
 __device__ __forceinline__ void apply_term(uint32_t* acc /*17*/, TermW& t, uint32_t k, const CsrView& m, uint32_t& gen, uint32_t& mag) {
     const uint32_t cls = t.cls;
     if (cls == kClsZero) return;
-    if (cls == kClsGen) {
+    if (cls == kClsGen || cls == kClsPow2P || cls == kClsPow2M) {  // (+-2^k is stored like any full-width coefficient)
         uint32_t c[8];
         ld8(c, m.vals + 2 * (size_t)k);
         mac_wide(acc, c, t.w);
         gen = 1;
         return;
     }
-    if (cls == kClsM1 || cls == kClsM2 || cls == kClsMS) {
+    if (cls == kClsM1 || cls == kClsM2) {
         uint32_t n[8];
         neg_mod<F>(n, t.w);
 #pragma unroll
         for (int i = 0; i < 8; ++i) t.w[i] = n[i];
     }
-    if (cls == kClsP1 || cls == kClsM1) {
+    acc_add8<RIPPLE>(acc, t.w);
+    mag += 1;
+    if (cls == kClsP2 || cls == kClsM2) {
         acc_add8<RIPPLE>(acc, t.w);
         mag += 1;
-    } else if (cls == kClsP2 || cls == kClsM2) {
-        acc_add8<RIPPLE>(acc, t.w);
-        acc_add8<RIPPLE>(acc, t.w);
-        mag += 2;
-    } else {
-        const uint32_t sm = __ldg(reinterpret_cast<const uint32_t*>(m.vals + 2 * (size_t)k));
-        acc_mad_small<RIPPLE>(acc, t.w, sm);
-        mag += sm > 8u ? 8u : sm;
     }
 }
 
@@ -364,20 +368,27 @@ __global__ void __launch_bounds__(128, MB) check_rows(CsrView m, CheckOut o, Fie
     publish_first_bad(my_bad, m, o, my_err);
 }
 
-// ---- plan: row_meta (lengths + kind), one thread per row ------------------------------------------------------------
+// ---- plan: row_meta and the term words of the plain rows, one thread per row ---------------------------------------------
+// scols[k] for a term of a plain row: bits 28..31 = signed multiplier (+-1, +-2), bits 0..27 = index of its variable in
+// the shadow array; every other term (and the padding) holds the null word: multiplier 0, index of the slot that is always 0.
+__global__ void fill_u32(uint32_t* p, size_t n, uint32_t v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
 __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, uint32_t n_rows, uint32_t fat_terms,
-                               uint32_t n_inputs, uint32_t n_aux, uint32_t* __restrict__ row_meta, uint32_t* __restrict__ counts /*4*/) {
+                               uint32_t n_inputs, uint32_t n_aux, uint32_t aux_off, uint32_t* __restrict__ row_meta,
+                               uint32_t* __restrict__ scols, uint32_t* __restrict__ counts /*4*/) {
     uint32_t n_kind[3] = {0, 0, 0};
     bool oob = false;
+    const bool idx_fits = (uint64_t)aux_off + n_aux <= (1ull << 28);  // shadow indices must fit 28 bits
     for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
         const uint32_t p0 = row_ptr[3 * (size_t)row], p1 = row_ptr[3 * (size_t)row + 1], p2 = row_ptr[3 * (size_t)row + 2],
                        p3 = row_ptr[3 * (size_t)row + 3];
+        const uint32_t pb = row_ptr[3 * (size_t)(row & ~(kSmallRows - 1u))];
         const uint32_t la = p1 - p0, lb = p2 - p1, lc = p3 - p2;
-        const bool enc = la < kMetaNoLens && lb < kMetaNoLens && lc < kMetaNoLens;
         uint32_t k = kRowPlain;
         if (p3 - p0 > fat_terms) {
             k = kRowFat;
-        } else if (!enc || p3 - p0 > kSmallCap) {
+        } else if (la > 254u || lb > 254u || lc > 254u || !idx_fits) {
             k = kRowGeneric;
         } else {
             uint32_t mag[3] = {0, 0, 0};
@@ -385,7 +396,7 @@ __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint3
                 const uint32_t col = __ldg(cols + t);
                 const uint32_t cls = (col >> kColClsShift) & 7u;
                 const int lc_i = t < p1 ? 0 : (t < p2 ? 1 : 2);
-                if (cls == kClsGen || cls == kClsPS || cls == kClsMS) k = kRowGeneric;  // check_small knows +-1, +-2 and 0
+                if (cls == kClsGen || cls == kClsPow2P || cls == kClsPow2M) k = kRowGeneric;  // check_small knows +-1, +-2 and 0
                 else if (cls == kClsP1 || cls == kClsM1) mag[lc_i] += 1;
                 else if (cls == kClsP2 || cls == kClsM2) mag[lc_i] += 2;
                 if (mag[0] > 7u || mag[1] > 7u || mag[2] > 5u) k = kRowGeneric;
@@ -395,8 +406,16 @@ __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint3
                     k = kRowGeneric;
                 }
             }
+            if (k == kRowPlain) {
+                for (uint32_t t = p0; t < p3; ++t) {
+                    const uint32_t col = __ldg(cols + t);
+                    const uint32_t cls = (col >> kColClsShift) & 7u;
+                    const uint32_t nib = (0x000E2F10u >> (4u * cls)) & 15u;  // P1 +1, M1 -1, P2 +2, M2 -2, else 0
+                    if (nib) scols[t] = (nib << 28) | ((col & kColIdxMask) + ((col & kColAux) ? aux_off : 0u));
+                }
+            }
         }
-        row_meta[row] = (enc ? (la | (lb << 8) | (lc << 16)) : kMetaNoLens) | (k << 24);
+        row_meta[row] = meta_pack(p0 - pb, la, lb, k);
         n_kind[0] += k == kRowGeneric;
         n_kind[1] += k == kRowPlain;
         n_kind[2] += k == kRowFat;
@@ -410,23 +429,23 @@ __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint3
 }
 
 // ---- K1, plain rows with small operands: 64-bit integer arithmetic on the witness shadows ---------------------------------
-// A warp owns 64 consecutive rows, two per lane.  A shuffle scan turns the row lengths (row_meta, one coalesced 8-byte
-// load per lane) into term offsets; the block's terms are then handled TERM-parallel -- column words out of shared memory,
-// one 4-byte shadow gather each, four gathers in flight per lane -- and each term's signed contribution c*w replaces its
-// column word; finally every lane sums the three ranges of its two rows and tests  Az*Bz + sum_C(-c)w == 0  as integers
+// A warp owns 64 consecutive rows, two per lane.  The block's term words (scols) are brought into shared memory by one TMA
+// bulk copy; they are handled TERM-parallel -- four consecutive words per lane (one 16-byte shared load), one 4-byte
+// shadow gather each, four gathers in flight per lane -- and replaced in place by the EXCLUSIVE PREFIX SUM of the signed
+// contributions c*w over the block (4 adds per lane + one shuffle scan per 128 terms).  A row's three sums are then four
+// shared loads and three subtractions, and the row holds iff  Az*Bz + sum_C(-c)w == 0  as integers
 // (|Az|,|Bz|,|Cz| < 2^27: nothing wraps, and |X| < p, so X = 0 mod p iff X = 0).
 // A row with an operand that is not small is appended to `deferred` and decided by check_rows<LIST>.
 //
 // Per-warp software pipeline over its blocks b, b+W, b+2W, ...:
 //   two blocks ahead   the block's term range [row_ptr[192b'], row_ptr[192(b'+1)]) is loaded into registers,
-//   one block ahead    its column words are brought into shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier,
-//                      double-buffered) and its row_meta words are loaded into registers,
-//   current block      scan, contributions, row sums.
+//   one block ahead    its term words are copied to shared memory (cp.async.bulk + mbarrier, double-buffered) and its
+//                      row_meta words are loaded into registers,
+//   current block      contributions + prefix sums, row verdicts.
 // Only the shadow gathers of the current block are exposed latency.  A block whose range does not fit the buffer (it
 // contains a fat row) is done thread-per-row straight from global memory.
 constexpr int kSmallThreads = 256;
-constexpr uint32_t kSmallRows = 64;        // rows per warp and round
-constexpr uint32_t kPoisonBit = 1u << 28;  // added to a contribution whose operand is not small (see small_sum)
+constexpr uint32_t kPoisonBit = 1u << 28;  // contribution of a term whose operand is not small (see small_poisoned)
 
 __device__ __forceinline__ uint32_t ldg_early(const uint32_t* p) {
     uint32_t v;
@@ -471,22 +490,13 @@ __device__ __forceinline__ uint32_t small_gather(uint32_t col, const CsrView& m,
     if (oob && cls != kClsZero) err = 1;
     return __ldg(m.shadow + ((oob || cls == kClsZero) ? 0u : shadow_index(col, m)));
 }
-// Contribution of a plain term (classes P1 M1 P2 M2 ZERO; anything else gives 0 and belongs to a row that is not plain):
-// multiplier from a nibble table indexed by the class, times the shadow; + kPoisonBit when the operand is not small.
-__device__ __forceinline__ uint32_t small_contrib(uint32_t col, uint32_t s) {
-    const uint32_t sh4 = (col >> (kColClsShift - 2)) & 28u;                // 4 * class
-    const int32_t mult = ((int32_t)((0x000E2F10u >> sh4) << 28)) >> 28;  // GEN 0, P1 +1, M1 -1, P2 +2, M2 -2, PS/MS/ZERO 0
-    return (s == kShadowBig && mult != 0) ? kPoisonBit : (uint32_t)(mult * (int32_t)s);
+// Contribution of a term word: multiplier (top nibble, signed) times the shadow; kPoisonBit when the operand is not small.
+// (The null word's variable is the always-zero slot, so it is never poisoned.)
+__device__ __forceinline__ uint32_t small_contrib(uint32_t word, uint32_t s) {
+    return s == kShadowBig ? kPoisonBit : (uint32_t)(((int32_t)word >> 28) * (int32_t)s);
 }
-
-// Sum of n staged contributions.  A plain LC has at most 7 non-zero terms and |sum of the clean ones| < 2^27, so the number
-// of poisoned terms can be read off the total: bits 28.. of (sum + 2^27) are zero iff none was.
-__device__ __forceinline__ uint32_t small_sum(const uint32_t* q, uint32_t n) {
-    uint32_t a = 0;
-#pragma unroll 1
-    for (uint32_t j = 0; j < n; ++j) a += q[j];
-    return a;
-}
+// A plain LC has at most 7 non-zero terms and |sum of the clean ones| < 2^27, so whether one was poisoned can be read off
+// the total: bits 28.. of (sum + 2^27) are zero iff none was.
 __device__ __forceinline__ bool small_poisoned(uint32_t a) { return ((a + (1u << 27)) >> 28) != 0u; }
 
 // One row from its three sums: 0 = holds, 1 = fails, 2 = needs the full-width path.
@@ -505,18 +515,18 @@ __device__ __forceinline__ uint32_t small_row_direct(uint32_t row, const CsrView
         const uint32_t k0 = i == 0 ? p0 : (i == 1 ? p1 : p2), k1 = i == 0 ? p1 : (i == 1 ? p2 : p3);
 #pragma unroll 1
         for (uint32_t k = k0; k < k1; ++k) {
-            const uint32_t col = __ldg(m.cols + k);
-            const uint32_t cls = (col >> kColClsShift) & 7u;
-            sum[i] += small_contrib(col, __ldg(m.shadow + (cls == kClsZero ? 0u : shadow_index(col, m))));
+            const uint32_t w = __ldg(m.scols + k);
+            sum[i] += small_contrib(w, __ldg(m.shadow + (w & kColIdxMask)));
         }
     }
     return small_verdict(sum[0], sum[1], sum[2]);
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 4) check_small(CsrView m, CheckOut o, uint32_t* __restrict__ deferred,
+__global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, CheckOut o, uint32_t* __restrict__ deferred,
                                                                 uint32_t* __restrict__ n_deferred) {
     extern __shared__ __align__(16) unsigned char small_smem[];
-    uint32_t(*s_buf)[2][kSmallCap] = reinterpret_cast<uint32_t(*)[2][kSmallCap]>(small_smem);
+    constexpr uint32_t kStageWords = kSmallCap + 4u;  // + one group for the prefix value past the last term
+    uint32_t(*s_buf)[2][kStageWords] = reinterpret_cast<uint32_t(*)[2][kStageWords]>(small_smem);
     __shared__ __align__(8) unsigned long long s_bar[kSmallThreads / 32][2];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     if (lane == 0) {
@@ -535,18 +545,17 @@ __global__ void __launch_bounds__(kSmallThreads, 4) check_small(CsrView m, Check
     auto range_hi = [&](uint32_t b) { return ldg_early(m.row_ptr + 3 * (size_t)min(kSmallRows * (b + 1u), m.n_rows)); };
     auto load_meta = [&](uint32_t b) {  // the lane's two rows; row_meta is padded to an even number of words
         const uint32_t r = kSmallRows * b + 2u * lane;
-        uint2 v = make_uint2(kRowGeneric << 24, kRowGeneric << 24);
-        if (r < m.n_rows) v = ldg_early2(m.row_meta + r);
-        if (r + 1u >= m.n_rows) v.y = kRowGeneric << 24;
+        uint2 v = make_uint2(kMetaOffMask, kMetaOffMask);  // kind Generic
+        if (r < m.n_rows) v = ldg_early2(m.row_meta + r);  // (v.y of a last odd row is whatever the padding holds: see plain1)
         return v;
     };
-    // copy the words [kb & ~3, roundup4(ke)) of cols into a stage; false when they do not fit
+    // copy the words [kb & ~3, roundup4(ke)) of scols into a stage; false when they do not fit
     auto issue_copy = [&](uint32_t kb, uint32_t ke, uint32_t stage) {
         const uint32_t w0 = kb & ~3u, w1 = (ke + 3u) & ~3u;
         if (w1 - w0 > kSmallCap) return false;
         if (ke > kb && lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our generic-proxy accesses of the stage are done
-            bulk_g2s(s_buf[wib][stage], m.cols + w0, (w1 - w0) * 4u, &s_bar[wib][stage]);
+            bulk_g2s(s_buf[wib][stage], m.scols + w0, (w1 - w0) * 4u, &s_bar[wib][stage]);
         }
         return true;
     };
@@ -563,16 +572,16 @@ __global__ void __launch_bounds__(kSmallThreads, 4) check_small(CsrView m, Check
             const uint32_t stage = it & 1u;
             const uint32_t b_nxt = blk + n_warps, b_nn = blk + 2u * n_warps;
             // 1. loads for the blocks ahead (consumed in the next iteration)
-            uint2 meta_nxt = make_uint2(kRowGeneric << 24, kRowGeneric << 24);
+            uint2 meta_nxt = make_uint2(kMetaOffMask, kMetaOffMask);
             uint32_t kb_nn = 0, ke_nn = 0;
             if (b_nxt < n_blocks) meta_nxt = load_meta(b_nxt);
             if (b_nn < n_blocks) { kb_nn = range_lo(b_nn); ke_nn = range_hi(b_nn); }
-            // 2. the next block's column words: the other stage is free (its rows were finished before the last __syncwarp)
+            // 2. the next block's term words: the other stage is free (its rows were finished before the last __syncwarp)
             bool copied_nxt = false;
             if (b_nxt < n_blocks) copied_nxt = issue_copy(kb_nxt, ke_nxt, stage ^ 1u);
             // 3. the current block
             const uint32_t row = blk * kSmallRows + 2u * lane;
-            const bool plain0 = (meta_cur.x >> 24) == kRowPlain, plain1 = (meta_cur.y >> 24) == kRowPlain;
+            const bool plain0 = meta_kind(meta_cur.x) == kRowPlain, plain1 = meta_kind(meta_cur.y) == kRowPlain && row + 1u < m.n_rows;
             const bool any_plain = __any_sync(0xffffffffu, plain0 || plain1);
             uint32_t verdict0 = 0, verdict1 = 0;
             if (copied_cur) {
@@ -581,46 +590,51 @@ __global__ void __launch_bounds__(kSmallThreads, 4) check_small(CsrView m, Check
                     phase ^= 1u << stage;
                 }
                 if (any_plain) {
-                    const uint32_t la0 = meta_cur.x & 255u, lb0 = (meta_cur.x >> 8) & 255u, lc0 = (meta_cur.x >> 16) & 255u;
-                    const uint32_t la1 = meta_cur.y & 255u, lb1 = (meta_cur.y >> 8) & 255u, lc1 = (meta_cur.y >> 16) & 255u;
-                    uint32_t nt0 = la0 + lb0 + lc0, nt1 = la1 + lb1 + lc1;
-                    // (a row whose lengths are not encodable is not plain; it only matters for the offsets of the rows after it)
-                    if (la0 == kMetaNoLens) nt0 = __ldg(m.row_ptr + 3 * (size_t)row + 3) - __ldg(m.row_ptr + 3 * (size_t)row);
-                    if (la1 == kMetaNoLens) nt1 = __ldg(m.row_ptr + 3 * (size_t)row + 6) - __ldg(m.row_ptr + 3 * (size_t)row + 3);
-                    uint32_t incl = nt0 + nt1;  // inclusive scan of the lanes' term counts
-#pragma unroll
-                    for (uint32_t d = 1; d < 32; d <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += up;
-                    }
-                    const uint32_t off0 = incl - nt0 - nt1;
-                    uint32_t* terms = s_buf[wib][stage] + (kb_cur & 3u);
-                    const uint32_t nt = ke_cur - kb_cur;
-                    // term-parallel: column word -> contribution, in place
-                    for (uint32_t t0 = 0; t0 < nt; t0 += 128u) {
-                        uint32_t col[4], sh[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t t = t0 + 32u * j + lane;
-                            col[j] = t < nt ? terms[t] : (kClsZero << kColClsShift);
+                    uint32_t* st = s_buf[wib][stage];
+                    const uint32_t head = kb_cur & 3u, nt = ke_cur - kb_cur;
+                    const uint32_t len = ((ke_cur + 3u) & ~3u) - (kb_cur & ~3u);  // staged words (a multiple of 4)
+                    // term words -> exclusive prefix sums of the contributions, in place; one more group holds the total
+                    uint32_t carry = 0;
+                    for (uint32_t t4 = 4u * lane; t4 - 4u * lane <= len; t4 += 128u) {
+                        uint4 w = make_uint4(0, 0, 0, 0);
+                        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                        if (t4 < len) {
+                            w = *reinterpret_cast<const uint4*>(st + t4);
+                            const uint32_t s0 = __ldg(m.shadow + (w.x & kColIdxMask)), s1 = __ldg(m.shadow + (w.y & kColIdxMask)),
+                                           s2 = __ldg(m.shadow + (w.z & kColIdxMask)), s3 = __ldg(m.shadow + (w.w & kColIdxMask));
+                            c0 = small_contrib(w.x, s0);
+                            c1 = small_contrib(w.y, s1);
+                            c2 = small_contrib(w.z, s2);
+                            c3 = small_contrib(w.w, s3);
                         }
+                        const uint32_t tot = c0 + c1 + c2 + c3;
+                        uint32_t incl = tot;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            sh[j] = __ldg(m.shadow + (((col[j] >> kColClsShift) & 7u) == kClsZero ? 0u : shadow_index(col[j], m)));
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t t = t0 + 32u * j + lane;
-                            if (t < nt) terms[t] = small_contrib(col[j], sh[j]);
+                        for (uint32_t d = 1; d < 32; d <<= 1) {
+                            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += up;
                         }
+                        const uint32_t ex = carry + incl - tot;
+                        if (t4 <= len) *reinterpret_cast<uint4*>(st + t4) = make_uint4(ex, ex + c0, ex + c0 + c1, ex + c0 + c1 + c2);
+                        carry += __shfl_sync(0xffffffffu, incl, 31);
                     }
                     __syncwarp();
+                    // offsets of the lane's two rows and of the row after them
+                    const uint32_t o0 = meta_cur.x & kMetaOffMask, o1 = meta_cur.y & kMetaOffMask;
+                    uint32_t o2 = __shfl_down_sync(0xffffffffu, o0, 1);
+                    if (lane == 31u || row + 2u >= m.n_rows) o2 = nt;
+                    if (row + 1u >= m.n_rows) o2 = nt;  // (row + 1 does not exist: row's terms end the block)
+                    const uint32_t e1 = (row + 1u < m.n_rows) ? o1 : nt;
+                    const uint32_t* q = st + head;
                     if (plain0) {
-                        const uint32_t* q = terms + off0;
-                        verdict0 = small_verdict(small_sum(q, la0), small_sum(q + la0, lb0), small_sum(q + la0 + lb0, lc0));
+                        const uint32_t la = (meta_cur.x >> 10) & 255u, lb = (meta_cur.x >> 18) & 255u;
+                        const uint32_t pa = q[o0], pb = q[o0 + la], pc = q[o0 + la + lb], pd = q[e1];
+                        verdict0 = small_verdict(pb - pa, pc - pb, pd - pc);
                     }
                     if (plain1) {
-                        const uint32_t* q = terms + off0 + nt0;
-                        verdict1 = small_verdict(small_sum(q, la1), small_sum(q + la1, lb1), small_sum(q + la1 + lb1, lc1));
+                        const uint32_t la = (meta_cur.y >> 10) & 255u, lb = (meta_cur.y >> 18) & 255u;
+                        const uint32_t pa = q[o1], pb = q[o1 + la], pc = q[o1 + la + lb], pd = q[o2];
+                        verdict1 = small_verdict(pb - pa, pc - pb, pd - pc);
                     }
                 }
             } else if (any_plain) {
@@ -647,7 +661,7 @@ __global__ void __launch_bounds__(kSmallThreads, 4) check_small(CsrView m, Check
     }
     publish_first_bad(my_bad, m, o, 0u);
 }
-constexpr size_t kSmallSmem = (size_t)(kSmallThreads / 32) * 2 * kSmallCap * 4;
+constexpr size_t kSmallSmem = (size_t)(kSmallThreads / 32) * 2 * (kSmallCap + 4) * 4;
 
 // 17-limb sum across the warp; every lane ends with the total.
 __device__ __forceinline__ void warp_sum17(uint32_t* acc) {
@@ -696,9 +710,11 @@ template <int F> __device__ __forceinline__ void fold_small_sums(uint32_t* acc, 
 // coefficient into a 1x8 product and a plain coefficient into two 64-bit additions; anything else takes the general path.
 // IS_C: C LCs take every class; A/B LCs only their GEN terms (a plain A/B LC has at most 7 non-zero terms and a value
 // bound the general path maintains).
-// Is term (col, shadow) one the shadow pass cannot take?  (operand not small; or a plain term of an A/B LC)
+// A term whose coefficient is stored full-width (GEN, or the +-2^k hint classes)?
+__device__ __forceinline__ bool is_product_class(uint32_t cls) { return cls == kClsGen || cls == kClsPow2P || cls == kClsPow2M; }
+// Is term (class, shadow) one the shadow pass cannot take?  (operand not small; or a +-1 / +-2 term of a plain A/B LC)
 template <bool IS_C> __device__ __forceinline__ bool shadow_slow(uint32_t cls, uint32_t sh) {
-    return cls != kClsZero && (sh == kShadowBig || (!IS_C && cls != kClsGen));
+    return cls != kClsZero && (sh == kShadowBig || (!IS_C && !is_product_class(cls)));
 }
 
 constexpr int kFatU = 8;  // terms per lane and round in the shadow pass of the warp-per-row kernel
@@ -739,7 +755,7 @@ __device__ __forceinline__ bool fold_lane_shadow(uint32_t* acc10, uint32_t k0, u
         for (int j = 0; j < kFatU; ++j) {
             const uint32_t cls = (col[j] >> kColClsShift) & 7u;
             if (shadow_slow<IS_C>(cls, sh[j])) { any_slow = true; continue; }
-            if (cls == kClsGen) {
+            if (is_product_class(cls)) {
                 gen = 1;
                 if (sh[j] != 0u) {
                     need_c |= 1u << j;
@@ -759,11 +775,10 @@ __device__ __forceinline__ bool fold_lane_shadow(uint32_t* acc10, uint32_t k0, u
                 c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w;
                 c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
                 acc_mad_small<10>(acc10, c, sh[j]);
-            } else if (IS_C && cls != kClsZero && cls != kClsGen && sh[j] != kShadowBig && sh[j] != 0u) {
-                uint32_t mg = (cls == kClsP1 || cls == kClsM1) ? 1u : 2u;
-                if (cls >= kClsPS) mg = __ldg(reinterpret_cast<const uint32_t*>(m.vals + 2 * (size_t)(kb + 32u * j)));
+            } else if (IS_C && cls != kClsZero && !is_product_class(cls) && sh[j] != kShadowBig && sh[j] != 0u) {
+                const uint32_t mg = (cls == kClsP1 || cls == kClsM1) ? 1u : 2u;
                 const uint64_t v = (uint64_t)mg * sh[j];
-                if (cls == kClsP1 || cls == kClsP2 || cls == kClsPS) {
+                if (cls == kClsP1 || cls == kClsP2) {
                     ss.pos_lo += v;
                     ss.pos_hi += ss.pos_lo < v ? 1u : 0u;
                 } else {
@@ -798,6 +813,230 @@ __device__ __forceinline__ void fold_lane_slow(uint32_t* acc, uint32_t k0, uint3
     }
 }
 
+// ---- integer pass of the warp-per-row kernel -----------------------------------------------------------------------------
+// MultiEq rows (multieq.rs:25-67: lhs * 1 = rhs with coefficients 2^k over bit- or word-valued variables) and their like
+// are decided without any modular arithmetic: a term +-2^k * w with w < 2^24 is the exact integer  w << k, added into one
+// of eight 64-bit buckets (limb position k/32) per sign, private to the lane and kept in shared memory (the index is
+// dynamic); per LC the 32 lanes' buckets are summed and carried into two 10-limb integers P (positive part) and N
+// (negative part).  With b = the LC of A/B that is a non-negative 32-bit integer and Y = the other one:
+//     the row holds  <=>  Y_P * b + C_P == Y_N * b + C_N        (C holds the NEGATED coefficients)
+// as integers whenever they are equal (an integer identity implies the congruence); when they differ and both sides are
+// below 2^253 the difference is non-zero and smaller than p, so the row fails; anything else -- a full-width coefficient
+// that is not +-2^k, an operand >= 2^24, two wide LCs -- falls back to the modular path.  Per term: two coalesced loads
+// (column word, exponent byte), one 4-byte gather, ~20 instructions; the 32-byte coefficient is never read.
+constexpr uint32_t kIntMaxTerms = 16384;  // per LC: < 2^9 terms per lane, each < 2^55, so a lane's bucket cannot overflow
+__device__ __forceinline__ uint32_t bk_slot(uint32_t j, uint32_t lane) { return j * 33u + lane; }  // (33: conflict-free column reads)
+constexpr uint32_t kBucketWords = 16u * 33u;  // u64 per warp
+
+// A full-width coefficient that is not +-2^k (e.g. the constant term of a UInt32 sum: the sum of 2^k over the set bits of
+// a round constant, on ONE) times a small operand: recover the canonical coefficient (A/B LCs store c * 2^288: one
+// Montgomery reduction undoes it; C LCs store p - c as it is) and add the 9 limbs of c * s into the positive buckets.
+template <int F, bool IS_C>
+__device__ __noinline__ void fat_gen_term(uint32_t k, uint32_t s, const CsrView& m, unsigned long long* bk) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t c[8];
+    ld8(c, m.vals + 2 * (size_t)k);
+    if (!IS_C) {
+        uint32_t t[17];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) t[i] = i < 8 ? c[i] : 0u;
+        redc_acc<F>(c, t);  // stored * 2^-288 = c, in [0, 2p)
+        reduce_once<F>(c);
+    }
+    unsigned long long carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        carry += (unsigned long long)c[i] * s;
+        bk[bk_slot(i, lane)] += (uint32_t)carry;
+        carry >>= 32;
+    }
+    bk[bk_slot(7, lane)] += carry << 32;  // (bucket 7 also carries limb 8)
+}
+
+// Term word of a fat row (plan, build_fat_words): bits 0..27 = index of the variable in the shadow array, bit 28 = negative,
+// bits 29..30 = kind: 0 nothing to add (zero coefficient; padding), 1 = +-(2^e1 [+ 2^e2]) with the exponents in kexp,
+// 2 = full-width coefficient.
+constexpr uint32_t kFatNeg = 1u << 28, kFatKindShift = 29, kFatPow2 = 1u, kFatGen = 2u;
+
+// Plan: term words (and exponents of the +-1 / +-2 classes) of the fat rows, one warp per row.
+// flags[0] |= 1 when a column does not exist or a shadow index does not fit: the integer pass is then not used at all.
+__global__ void build_fat_words(const uint32_t* __restrict__ fat_rows, uint32_t n_fat, const uint32_t* __restrict__ row_ptr,
+                                const uint32_t* __restrict__ cols, uint32_t n_inputs, uint32_t n_aux, uint32_t aux_off,
+                                uint32_t* __restrict__ scols, uint16_t* __restrict__ kexp, uint32_t* __restrict__ flags) {
+    const uint32_t lane = threadIdx.x & 31u, warps = (gridDim.x * blockDim.x) >> 5;
+    const bool idx_fits = (uint64_t)aux_off + n_aux <= (1ull << 28);
+    bool bad = !idx_fits;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_fat; i += warps) {
+        const uint32_t row = fat_rows[i];
+        const uint32_t k0 = row_ptr[3 * (size_t)row], k1 = row_ptr[3 * (size_t)row + 3];
+        for (uint32_t k = k0 + lane; k < k1; k += 32u) {
+            const uint32_t col = cols[k];
+            const uint32_t cls = (col >> kColClsShift) & 7u;
+            if (cls == kClsZero) continue;  // (stays the null word)
+            if ((col & kColIdxMask) >= ((col & kColAux) ? n_aux : n_inputs)) { bad = true; continue; }
+            const uint32_t uidx = (col & kColIdxMask) + ((col & kColAux) ? aux_off : 0u);
+            const uint32_t neg = (cls == kClsM1 || cls == kClsM2 || cls == kClsPow2M) ? kFatNeg : 0u;
+            if (idx_fits) scols[k] = uidx | neg | ((cls == kClsGen ? kFatGen : kFatPow2) << kFatKindShift);
+            if (cls == kClsP1 || cls == kClsM1) kexp[k] = (uint16_t)(0u | (kNoExp << 8));
+            if (cls == kClsP2 || cls == kClsM2) kexp[k] = (uint16_t)(1u | (kNoExp << 8));
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1u);
+}
+
+template <int F, bool IS_C>
+__device__ __forceinline__ bool fat_lc_integer(uint32_t* P /*10*/, uint32_t* N /*10*/, uint32_t k0, uint32_t k1, const CsrView& m,
+                                               unsigned long long* bk, uint32_t null_word) {
+    const uint32_t lane = threadIdx.x & 31u;
+    zeron<10>(P);
+    zeron<10>(N);
+    if (k1 == k0) return true;
+    if (k1 - k0 > kIntMaxTerms) return false;
+    if (k1 - k0 == 1u) {  // e.g. the "* 1" of a MultiEq row: +2^0 times a small operand
+        const uint32_t w = __ldg(m.scols + k0), s = __ldg(m.shadow + (w & kColIdxMask));
+        if ((w >> kFatKindShift) == 0u) return true;
+        if ((w >> kFatKindShift) == kFatPow2 && !(w & kFatNeg) && __ldg(m.kexp + k0) == (uint16_t)(kNoExp << 8) && s != kShadowBig) {
+            P[0] = s;
+            return true;
+        }
+    }
+    unsigned long long* mine = bk + lane;
+#pragma unroll
+    for (uint32_t j = 0; j < 16u; ++j) mine[33u * j] = 0ull;
+    bool bad = false;
+    // kFatU terms per lane and round.  The term words and exponents of the NEXT round are fetched (coalesced) while this
+    // round's shadows are gathered, so a round exposes one memory round trip.
+    uint32_t w_n[kFatU], kx_n[kFatU];
+#pragma unroll
+    for (int j = 0; j < kFatU; ++j) {
+        const uint32_t k = k0 + lane + 32u * j;
+        w_n[j] = k < k1 ? __ldg(m.scols + k) : null_word;
+        kx_n[j] = k < k1 ? (uint32_t)__ldg(m.kexp + k) : 0u;
+    }
+#pragma unroll 1
+    for (uint32_t kb = k0 + lane; kb < k1; kb += 32u * kFatU) {
+        uint32_t w[kFatU], kx[kFatU], sh[kFatU];
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) {
+            w[j] = w_n[j];
+            kx[j] = kx_n[j];
+        }
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) sh[j] = __ldg(m.shadow + (w[j] & kColIdxMask));  // (the null word's variable is always 0)
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) {
+            const uint32_t k = kb + 32u * (kFatU + j);
+            w_n[j] = k < k1 ? __ldg(m.scols + k) : null_word;
+            kx_n[j] = k < k1 ? (uint32_t)__ldg(m.kexp + k) : 0u;
+        }
+        uint32_t gen_mask = 0;
+#pragma unroll
+        for (int j = 0; j < kFatU; ++j) {
+            const uint32_t kind = w[j] >> kFatKindShift;
+            if (sh[j] == 0u || kind == 0u) continue;  // (0 times any coefficient)
+            if (sh[j] == kShadowBig) { bad = true; continue; }
+            if (kind == kFatGen) { gen_mask |= 1u << j; continue; }
+            unsigned long long* q = mine + ((w[j] & kFatNeg) ? 8u * 33u : 0u);
+            const uint32_t e1 = kx[j] & 255u, e2 = kx[j] >> 8;
+            q[33u * (e1 >> 5)] += (unsigned long long)sh[j] << (e1 & 31u);
+            if (e2 != kNoExp) q[33u * (e2 >> 5)] += (unsigned long long)sh[j] << (e2 & 31u);
+        }
+#pragma unroll 1
+        for (; gen_mask; gen_mask &= gen_mask - 1u) {  // rare: outlined, one at a time
+            const uint32_t k = kb + 32u * (uint32_t)(__ffs((int)gen_mask) - 1);
+            const uint32_t wk = __ldg(m.scols + k);
+            fat_gen_term<F, IS_C>(k, __ldg(m.shadow + (wk & kColIdxMask)), m, bk);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad)) return false;
+    __syncwarp();
+    // lanes 0..7 sum the positive buckets 0..7 over the 32 lanes, lanes 16..23 the negative ones (96-bit totals)
+    const uint32_t j = (lane & 7u) + ((lane & 16u) >> 1);
+    unsigned long long lo = 0;
+    uint32_t hi = 0;
+#pragma unroll 8
+    for (uint32_t i = 0; i < 32u; ++i) {
+        const unsigned long long x = bk[bk_slot(j, i)];
+        lo += x;
+        hi += lo < x ? 1u : 0u;
+    }
+    __syncwarp();  // the buckets may be cleared by the next LC
+    // limb i of the sum receives word 0 of bucket i, word 1 of bucket i-1, word 2 of bucket i-2
+    const uint32_t li = lane & 15u;  // limb index handled by this lane (0..9 meaningful)
+    const uint32_t w0 = li < 8u ? (uint32_t)lo : 0u;
+    uint32_t w1 = __shfl_up_sync(0xffffffffu, (uint32_t)(lo >> 32), 1), w2 = __shfl_up_sync(0xffffffffu, hi, 2);
+    if (li < 1u || li > 8u) w1 = 0;
+    if (li < 2u || li > 9u) w2 = 0;
+    const unsigned long long t = (unsigned long long)w0 + w1 + w2;  // < 2^34
+    unsigned long long cp = 0, cn = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const unsigned long long tp = ((unsigned long long)__shfl_sync(0xffffffffu, (uint32_t)(t >> 32), i) << 32) |
+                                      __shfl_sync(0xffffffffu, (uint32_t)t, i);
+        const unsigned long long tn = ((unsigned long long)__shfl_sync(0xffffffffu, (uint32_t)(t >> 32), 16 + i) << 32) |
+                                      __shfl_sync(0xffffffffu, (uint32_t)t, 16 + i);
+        cp += tp;
+        cn += tn;
+        P[i] = (uint32_t)cp;
+        N[i] = (uint32_t)cn;
+        cp >>= 32;
+        cn >>= 32;
+    }
+    return true;
+}
+
+// x (10 limbs) * b + y (10 limbs) -> r (12 limbs)
+__device__ __forceinline__ void mad10(uint32_t* r, const uint32_t* x, uint32_t b, const uint32_t* y) {
+    unsigned long long c = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        c += (unsigned long long)x[i] * b + y[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    r[10] = (uint32_t)c;
+    r[11] = (uint32_t)(c >> 32);
+}
+
+// One fat row as integers: 0 = holds, 1 = fails, 2 = undecided (take the modular path).
+template <int F>
+__device__ __forceinline__ uint32_t fat_row_integer(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, const CsrView& m,
+                                                    unsigned long long* bk, uint32_t null_word) {
+    uint32_t Pa[10], Na[10], Pb[10], Nb[10];
+    if (!fat_lc_integer<F, false>(Pa, Na, p0, p1, m, bk, null_word)) return 2u;
+    if (!fat_lc_integer<F, false>(Pb, Nb, p1, p2, m, bk, null_word)) return 2u;
+    uint32_t a_wide = 0, b_wide = 0;  // non-zero when the LC is not a non-negative 32-bit integer
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        a_wide |= Na[i] | (i ? Pa[i] : 0u);
+        b_wide |= Nb[i] | (i ? Pb[i] : 0u);
+    }
+    if (a_wide && b_wide) return 2u;
+    const uint32_t b = b_wide ? Pa[0] : Pb[0];
+    uint32_t YP[10], YN[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        YP[i] = b_wide ? Pb[i] : Pa[i];
+        YN[i] = b_wide ? Nb[i] : Na[i];
+    }
+    uint32_t L[12], R[12];
+    {
+        uint32_t Pc[10], Nc[10];
+        if (!fat_lc_integer<F, true>(Pc, Nc, p2, p3, m, bk, null_word)) return 2u;
+        mad10(L, YP, b, Pc);
+        mad10(R, YN, b, Nc);
+    }
+    uint32_t diff = 0, high = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        diff |= L[i] ^ R[i];
+        if (i >= 8) high |= L[i] | R[i];
+    }
+    if (diff == 0u) return 0u;
+    if (high == 0u && ((L[7] | R[7]) >> 29) == 0u) return 1u;  // both below 2^253: the difference is non-zero and below p
+    return 2u;
+}
+
 // One LC [k0,k1) by a whole warp: lanes stride the terms, then the partial sums are combined.  Every lane returns with
 // the total, the "a full product was folded" flag and the plain magnitude.  SH: use the witness shadows.
 template <int F, int RIPPLE, bool PIPE, bool SH = false>
@@ -826,6 +1065,28 @@ __device__ __forceinline__ void warp_fold_lc(uint32_t* acc, uint32_t k0, uint32_
     warp_sum17(acc);
     any_gen = __any_sync(0xffffffffu, g != 0) ? 1u : 0u;
     mag = __reduce_add_sync(0xffffffffu, mg > 8u ? 8u : mg);
+}
+
+// ---- K1, fat rows, integer pass: one warp per constraint; rows it cannot decide are listed for check_fat_rows -------------
+template <int F>
+__global__ void __launch_bounds__(128, 6) check_fat_int(CsrView m, CheckOut o, const uint32_t* __restrict__ fat_rows, uint32_t n_fat,
+                                                        uint32_t* __restrict__ undecided, uint32_t* __restrict__ n_undecided) {
+    __shared__ unsigned long long s_bk[4][kBucketWords];
+    unsigned long long* bk = s_bk[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t my_bad = 0xffffffffu;
+    const uint32_t null_word = m.aux_off - 1u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_fat; i += warps) {
+        const uint32_t row = __ldg(fat_rows + i);
+        const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
+                       p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
+        const uint32_t v = fat_row_integer<F>(p0, p1, p2, p3, m, bk, null_word);
+        if (v == 1u && row < my_bad) my_bad = row;
+        if (v == 2u && lane == 0) undecided[atomicAdd(n_undecided, 1u)] = row;
+        __syncwarp();
+    }
+    publish_first_bad(my_bad, m, o, 0u);
 }
 
 // ---- K1 / K2, fat rows: one warp per constraint -------------------------------------------------------------------------
@@ -884,7 +1145,7 @@ __global__ void __launch_bounds__(128, MB) check_fat_rows(CsrView m, CheckOut o,
 __global__ void init_result(long long* first_bad, unsigned int* err, uint32_t* n_deferred) {
     *first_bad = 0x7fffffffffffffffLL;
     *err = 0;
-    if (n_deferred) *n_deferred = 0;
+    if (n_deferred) { n_deferred[0] = 0; n_deferred[1] = 0; }  // thin rows deferred by check_small, fat rows left by check_fat_int
 }
 
 // ---- K3: ingest conversion ------------------------------------------------------------------------------------------------
@@ -903,10 +1164,9 @@ __global__ void classify_lcs(const uint4* __restrict__ vals, const uint32_t* __r
             uint32_t c[8], s;
             ld8(c, vals + 2 * (size_t)k);
             const uint32_t cls = classify_coeff<F>(c, &s);
-            if (cls == kClsGen) plain = 0;
-            else if (cls == kClsP1 || cls == kClsM1) mag += 1;
+            if (cls == kClsP1 || cls == kClsM1) mag += 1;
             else if (cls == kClsP2 || cls == kClsM2) mag += 2;
-            else if (cls == kClsPS || cls == kClsMS) mag = s > 7 ? 8 : mag + s;
+            else if (cls != kClsZero) plain = 0;
             if (mag > 7) plain = 0;
         }
         kind[i] = (uint8_t)plain;
@@ -916,8 +1176,8 @@ __global__ void classify_lcs(const uint4* __restrict__ vals, const uint32_t* __r
 // Pass 2, one thread per term: canonical -> internal form in place, class bits into the column word.
 // err bit 1: coefficient >= p; bit 2: variable index does not fit 28 bits.
 template <int F>
-__global__ void convert_terms(uint4* vals, uint32_t* cols, const uint32_t* __restrict__ row_ptr, const uint8_t* __restrict__ kind,
-                              uint32_t lc0, uint32_t n_lc, uint32_t k0, uint32_t n, FieldConsts fc, unsigned int* err) {
+__global__ void convert_terms(uint4* vals, uint32_t* cols, uint16_t* __restrict__ kexp, const uint32_t* __restrict__ row_ptr,
+                              const uint8_t* __restrict__ kind, uint32_t lc0, uint32_t n_lc, uint32_t k0, uint32_t n, FieldConsts fc, unsigned int* err) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t k = k0 + i;
         uint32_t lo = lc0, hi = lc0 + n_lc;  // largest lc with row_ptr[lc] <= k
@@ -941,8 +1201,11 @@ __global__ void convert_terms(uint4* vals, uint32_t* cols, const uint32_t* __res
             for (int j = 0; j < 8; ++j) c[j] = nz ? n8[j] : 0u;
         }
         cls = classify_coeff<F>(c, &s);
-        if (type != 2u && !plain && cls != kClsZero) cls = kClsGen;
-        if (cls == kClsGen) {
+        if (type != 2u && !plain) {  // a general A/B LC is scaled as a whole: its +-1 / +-2 terms are +-2^0 / +-2^1
+            if (cls == kClsP1 || cls == kClsP2) { s = (cls == kClsP2 ? 1u : 0u) | (kNoExp << 8); cls = kClsPow2P; }
+            else if (cls == kClsM1 || cls == kClsM2) { s = (cls == kClsM2 ? 1u : 0u) | (kNoExp << 8); cls = kClsPow2M; }
+        }
+        if (cls == kClsGen || cls == kClsPow2P || cls == kClsPow2M) {
             if (type == 2u) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) r[j] = c[j];
@@ -955,9 +1218,9 @@ __global__ void convert_terms(uint4* vals, uint32_t* cols, const uint32_t* __res
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = 0;
-            r[0] = s;
         }
         st8(vals + 2 * (size_t)k, r);
+        kexp[k] = (uint16_t)s;
         cols[k] = (col & (kColAux | kColIdxMask)) | (cls << kColClsShift);
         // instance statistic for the launch heuristic: how many terms need a full product (err[1] is the counter)
         const unsigned int gen_mask = __ballot_sync(__activemask(), cls == kClsGen);

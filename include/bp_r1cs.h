@@ -131,9 +131,11 @@ int bp_cs_set_row_base(bp_cs* cs, uint64_t row_base);
 int bp_cs_sync(bp_cs* cs);
 /* Tuning / introspection knobs: "fat_terms" (rows with more terms use the warp-per-row kernel; default 96);
  * "variant" (-1 = default; else bit 0: no small-operand kernel, bit 1: no witness shadows in the warp-per-row kernel,
- * bit 2: park A.w/B.w in shared memory -- every variant returns the same results, the parity tests run them all);
+ * bit 2: park A.w/B.w in shared memory, bit 3: no integer pass over the fat rows -- every variant returns the same
+ * results, the parity tests run them all);
  * read-only: "launches" (kernels launched so far), "plain_rows" / "generic_rows" / "fat_rows" (rows per kernel),
- * "deferred_rows" (plain rows the last check sent to the full-width kernel), "gen_terms", "sm_count". */
+ * "deferred_rows" / "fat_undecided_rows" (plain / fat rows the last check sent on to the full-width kernels), "gen_terms",
+ * "sm_count". */
 int bp_cs_set_option(bp_cs* cs, const char* key, int64_t value);
 int bp_cs_get_option(bp_cs* cs, const char* key, int64_t* value);
 

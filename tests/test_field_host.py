@@ -130,10 +130,16 @@ def test_plain_primitives(fh2, fid):
                 assert fh2(fid, 14, x, s, 17, out_init=big) == big + s * x
     for v in [0, 1, p - 1, p, p + 1, 2 * p, 4 * p - 1, 4 * p, 7 * p + 5, 8 * p - 1] + [rng.randrange(8 * p) for _ in range(300)]:
         assert fh2(fid, 15, v, 0, 8, a_limbs=9) == v % p
-    K = {"gen": 0, "p1": 1, "m1": 2, "p2": 3, "m2": 4, "ps": 5, "ms": 6, "zero": 7}
-    cases = [(0, "zero", 0), (1, "p1", 0), (p - 1, "m1", 0), (2, "p2", 0), (p - 2, "m2", 0), (3, "ps", 3), (p - 3, "ms", 3),
-             (0xFFFFFFFF, "ps", 0xFFFFFFFF), (p - 0xFFFFFFFF, "ms", 0xFFFFFFFF), (1 << 32, "gen", 0), (p - (1 << 32), "gen", 0),
-             (p >> 1, "gen", 0), (1 << 200, "gen", 0)]
+    K = {"gen": 0, "p1": 1, "m1": 2, "p2": 3, "m2": 4, "pow2p": 5, "pow2m": 6, "zero": 7}
+    one = lambda k: k | 0xFF00  # packed exponents of a single power of two
+    cases = [(0, "zero", 0), (1, "p1", 0), (p - 1, "m1", 0), (2, "p2", 0), (p - 2, "m2", 0), (3, "pow2p", 0 | 1 << 8),
+             (p - 3, "pow2m", 0 | 1 << 8), (7, "gen", 0), (p - 7, "gen", 0), (4, "pow2p", one(2)), (p - 4, "pow2m", one(2)),
+             (0xFFFFFFFF, "gen", 0), (1 << 31, "pow2p", one(31)), (1 << 32, "pow2p", one(32)), (p - (1 << 32), "pow2m", one(32)),
+             (p >> 1, "gen", 0), (1 << 200, "pow2p", one(200)), (p - (1 << 253), "pow2m", one(253)),
+             ((1 << 200) + 1, "pow2p", 0 | 200 << 8), ((1 << 253) + (1 << 31), "pow2p", 31 | 253 << 8),
+             (p - (1 << 100) - (1 << 37), "pow2m", 37 | 100 << 8), ((1 << 100) + (1 << 37) + 1, "gen", 0)]
+    cases += [(1 << k, "pow2p", one(k)) for k in range(2, 254)] + [(p - (1 << k), "pow2m", one(k)) for k in range(2, 254)]
+    cases += [((1 << k) + (1 << (k + 13)), "pow2p", k | (k + 13) << 8) for k in range(0, 240, 7)]
     for v, cls, s in cases:
         r = fh2(fid, 16, v, 0, 2)
         assert (r & 0xFFFFFFFF, r >> 32) == (K[cls], s), (hex(v), cls)

@@ -14,8 +14,9 @@ from gpu_util import Handle  # noqa: E402
 
 FIDS = sorted(FIELDS)
 # (fat_terms, variant): default split / nearly every row through the warp-per-row kernel, x the kernel variants of
-# bp_cs_set_option("variant"): -1 default, bit 0 no small-operand kernel, bit 1 no shadows in the fat kernel, bit 2 park
-KERNELS = [(96, -1), (8, -1), (96, 1), (8, 3), (96, 4), (8, 2)]
+# bp_cs_set_option("variant"): -1 default, bit 0 no small-operand kernel, bit 1 no shadows in the fat kernel, bit 2 park,
+# bit 3 no integer pass over the fat rows
+KERNELS = [(96, -1), (8, -1), (96, 1), (8, 3), (96, 4), (8, 2), (8, 8)]
 
 
 @pytest.mark.parametrize("fid", FIDS)
