@@ -56,6 +56,7 @@ struct bp_cs {
     DevBuf deferred;           // per check: plain rows check_small handed to check_rows
     DevBuf fat_undecided;      // per check: fat rows check_fat_int handed to check_fat_rows
     uint64_t n_fat_rows = 0, n_gen_rows = 0, n_plain_rows = 0;  // plan statistics (host copies)
+    uint64_t n_terms_kind[3] = {0, 0, 0};                       // terms per RowKind
     uint64_t fat_terms = 96;   // rows with more terms than this go to the warp-per-row kernel
     int64_t fat_ctas_per_sm = 8;  // grid of check_fat_rows = sm_count * this
     int64_t kernels_mask = 3;  // measurement aid: bit 0 = launch the thin-row kernels, bit 1 = launch check_fat_rows
@@ -301,25 +302,26 @@ int ensure_plan(bp_cs* h) {
         const uint32_t n = (uint32_t)h->n_rows;
         int rc = ensure(h, h->row_meta, ((size_t)n + 1) * 4, 0);
         if (rc != BP_OK) return rc;
-        if ((rc = ensure(h, h->scratch, 16, 0)) != BP_OK) return rc;
+        if ((rc = ensure(h, h->scratch, 40, 0)) != BP_OK) return rc;
         const size_t n_scols = (((size_t)h->nnz + 3) & ~size_t(3)) + 4;  // whole 16-byte groups, and one past the end
         if ((rc = ensure(h, h->scols, n_scols * 4, 0)) != BP_OK) return rc;
         uint32_t* d_cnt = (uint32_t*)h->scratch.p;
-        CU(h, cudaMemsetAsync(d_cnt, 0, 16, h->stream));
+        CU(h, cudaMemsetAsync(d_cnt, 0, 40, h->stream));
         fill_u32<<<grid_for(h, n_scols, 256, 8), 256, 0, h->stream>>>((uint32_t*)h->scols.p, n_scols, (uint32_t)h->shadow_aux_off - 1u);
         build_row_meta<<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p, n,
                                                                        (uint32_t)h->fat_terms, (uint32_t)h->n_inputs, (uint32_t)h->n_aux,
                                                                        (uint32_t)h->shadow_aux_off, (uint32_t*)h->row_meta.p,
-                                                                       (uint32_t*)h->scols.p, d_cnt);
+                                                                       (uint32_t*)h->scols.p, d_cnt, (unsigned long long*)(d_cnt + 4));
         h->launches += 2;
         CU(h, cudaGetLastError());
-        uint32_t* hc = (uint32_t*)((char*)h->h_pinned_small + 48);
-        CU(h, cudaMemcpyAsync(hc, d_cnt, 16, cudaMemcpyDeviceToHost, h->stream));
+        uint32_t* hc = (uint32_t*)((char*)h->h_pinned_small + 64);
+        CU(h, cudaMemcpyAsync(hc, d_cnt, 40, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
         h->n_gen_rows = hc[kRowGeneric];
         h->n_plain_rows = hc[kRowPlain];
         h->n_fat_rows = hc[kRowFat];
         h->cols_in_range = hc[3] == 0;  // (rows with a column that does not exist are generic: check_rows reports them)
+        std::memcpy(h->n_terms_kind, hc + 4, 24);
         if ((rc = select_rows(h, h->fat_rows, kRowFat, h->n_fat_rows)) != BP_OK) return rc;
         h->fat_int_ok = false;
         if (h->n_fat_rows) {
@@ -477,7 +479,7 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     h->d_err = (unsigned int*)(h->d_result + 1);
     h->d_ndef = (uint32_t*)(h->d_result + 2);
     if (cudaMemset(h->d_result, 0, 32) != cudaSuccess) return bail(BP_E_CUDA);
-    if (cudaMallocHost(&h->h_pinned_small, 64) != cudaSuccess) return bail(BP_E_OOM);
+    if (cudaMallocHost(&h->h_pinned_small, 128) != cudaSuccess) return bail(BP_E_OOM);
     for (int s = 0; s < kNumStage; ++s) {
         if (cudaMallocHost(&h->h_stage[s], kStageBytes) != cudaSuccess) return bail(BP_E_OOM);
         if (cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
@@ -578,6 +580,13 @@ int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
         int rc = ensure_plan(h);
         if (rc != BP_OK) return rc;
         *v = (int64_t)(key[0] == 'f' ? h->n_fat_rows : (key[0] == 'p' ? h->n_plain_rows : h->n_gen_rows));
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "fat_row_terms") || !std::strcmp(key, "plain_row_terms") || !std::strcmp(key, "generic_row_terms")) {
+        CU(h, cudaSetDevice(h->device));
+        int rc = ensure_plan(h);
+        if (rc != BP_OK) return rc;
+        *v = (int64_t)h->n_terms_kind[key[0] == 'f' ? kRowFat : (key[0] == 'p' ? kRowPlain : kRowGeneric)];
         return BP_OK;
     }
     // plain rows / fat rows the last check handed on to the full-width kernels

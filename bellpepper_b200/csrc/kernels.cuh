@@ -376,8 +376,10 @@ __global__ void fill_u32(uint32_t* p, size_t n, uint32_t v) {
 }
 __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, uint32_t n_rows, uint32_t fat_terms,
                                uint32_t n_inputs, uint32_t n_aux, uint32_t aux_off, uint32_t* __restrict__ row_meta,
-                               uint32_t* __restrict__ scols, uint32_t* __restrict__ counts /*4*/) {
+                               uint32_t* __restrict__ scols, uint32_t* __restrict__ counts /*4*/,
+                               unsigned long long* __restrict__ term_counts /*3: terms per RowKind*/) {
     uint32_t n_kind[3] = {0, 0, 0};
+    unsigned long long t_kind[3] = {0, 0, 0};
     bool oob = false;
     const bool idx_fits = (uint64_t)aux_off + n_aux <= (1ull << 28);  // shadow indices must fit 28 bits
     for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
@@ -419,11 +421,16 @@ __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint3
         n_kind[0] += k == kRowGeneric;
         n_kind[1] += k == kRowPlain;
         n_kind[2] += k == kRowFat;
+        t_kind[k] += p3 - p0;
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {  // all threads are back together here
         const uint32_t tot = __reduce_add_sync(0xffffffffu, n_kind[i]);
         if ((threadIdx.x & 31u) == 0 && tot) atomicAdd(counts + i, tot);
+        unsigned long long tt = t_kind[i];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, d);
+        if ((threadIdx.x & 31u) == 0 && tt) atomicAdd(term_counts + i, tt);
     }
     if (__any_sync(0xffffffffu, oob) && (threadIdx.x & 31u) == 0) atomicOr(counts + 3, 1u);
 }
