@@ -329,9 +329,15 @@ class _Device:
         for kind in (INPUT, AUX):
             vals = self._pend_vals[kind]
             if vals:
-                arr = _limbs(vals)
+                # packed staging (include/bp_r1cs.h: bp_cs_alloc_u8): one byte per value that fits a byte, the others
+                # are patched afterwards -- gadget witnesses are almost entirely bits
                 first = ctypes.c_uint64()
-                self._ck(self.L.bp_cs_alloc(self.h, kind, arr.ctypes.data, len(vals), ctypes.byref(first)))
+                packed = np.fromiter((v if v < 256 else 0 for v in vals), np.uint8, len(vals))
+                self._ck(self.L.bp_cs_alloc_u8(self.h, kind, packed.ctypes.data, len(vals), ctypes.byref(first)))
+                for pos, v in enumerate(vals):
+                    if v >= 256:
+                        arr = _limbs([v])
+                        self._ck(self.L.bp_cs_set(self.h, kind, first.value + pos, arr.ctypes.data))
                 vals.clear()
         if self._lens:
             lens = np.asarray(self._lens, np.uint32)

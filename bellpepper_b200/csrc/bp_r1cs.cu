@@ -37,6 +37,8 @@ struct bp_cs {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;            // the fat-row kernels of a check run beside the thin-row kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -397,9 +399,34 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
     } else {
         const int64_t v = h->variant < 0 ? 0 : h->variant;
         const bool use_small = !(v & 1) && h->n_plain_rows > 0;
+        if ((h->kernels_mask & 2) && h->n_fat_rows) {  // fork: the fat-row kernels start after init_result, beside the thin ones
+            CU(h, cudaEventRecord(h->ev_fork, h->stream));
+            CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        }
         const bool fat_shadow = !(v & 2);
         // product-heavy instances (synthetic) park az/bz in shared memory while C is folded
         const bool park = (v & 4) || (h->variant < 0 && 2 * h->n_gen > h->nnz);
+        if ((h->kernels_mask & 2) && h->n_fat_rows) {
+            cudaStream_t fs = h->side_stream;  // joined below: the check is complete on h->stream when the call returns
+            const int fgrid_small = std::min(fat_grid, h->sm_count);
+            if (fat_shadow && !(v & 8) && h->fat_int_ok) {  // integer pass first; the modular kernel takes what it could not decide
+                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * 6);
+                DISPATCH_FIELD(h, (check_fat_int<F><<<igrid, block, 0, fs>>>(m, o, fat, (uint32_t)h->n_fat_rows,
+                                                                            (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+                // (normally nothing is left: a small grid, grid-stride over whatever there is)
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fgrid_small, block, 0, fs>>>(
+                                      m, o, h->fc, (const uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+                h->launches += 2;
+            } else if (fat_shadow) {
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fat_grid, block, 0, fs>>>(m, o, h->fc, fat, n_fat)));
+                h->launches++;
+            } else {
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault, 4><<<fat_grid, block, 0, fs>>>(m, o, h->fc, fat, n_fat)));
+                h->launches++;
+            }
+            CU(h, cudaGetLastError());
+            CU(h, cudaEventRecord(h->ev_join, fs));
+        }
         if (h->kernels_mask & 1) {
             if (use_small) {
                 const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;  // one warp per block of rows
@@ -408,7 +435,8 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
                 check_small<<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
                 h->launches++;
                 const uint32_t* gl = (const uint32_t*)h->gen_rows.p;
-                const int lgrid = grid_for(h, h->n_gen_rows + h->n_plain_rows, block, 16);
+                // the plan's generic rows, plus whatever check_small deferred (normally nothing): grid-stride over both
+                const int lgrid = grid_for(h, h->n_gen_rows + (uint64_t)h->sm_count * block, block, 16);
                 if (park) {
                     DISPATCH_FIELD(h, (check_rows<F, false, kVDefault | kVPark, 6, true><<<lgrid, block, 0, h->stream>>>(
                                           m, o, h->fc, gl, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
@@ -423,22 +451,7 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
                 h->launches++;
             }
         }
-        if ((h->kernels_mask & 2) && h->n_fat_rows) {
-            if (fat_shadow && !(v & 8) && h->fat_int_ok) {  // integer pass first; the modular kernel takes what it could not decide
-                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * 6);
-                DISPATCH_FIELD(h, (check_fat_int<F><<<igrid, block, 0, h->stream>>>(m, o, fat, (uint32_t)h->n_fat_rows,
-                                                                                 (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
-                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fat_grid, block, 0, h->stream>>>(
-                                      m, o, h->fc, (const uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
-                h->launches += 2;
-            } else if (fat_shadow) {
-                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));
-                h->launches++;
-            } else {
-                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));
-                h->launches++;
-            }
-        }
+        if ((h->kernels_mask & 2) && h->n_fat_rows) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));  // join
     }
 #undef BP_LAUNCH
     CU(h, cudaGetLastError());
@@ -475,6 +488,9 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BP_E_CUDA);
     h->stream = h->own_stream;
+    if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BP_E_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
     if (cudaMalloc(&h->d_result, 32) != cudaSuccess) return bail(BP_E_OOM);
     h->d_err = (unsigned int*)(h->d_result + 1);
     h->d_ndef = (uint32_t*)(h->d_result + 2);
@@ -518,6 +534,12 @@ void bp_cs_free(bp_cs* h) {
         if (h->h_stage[s]) cudaFreeHost(h->h_stage[s]);
         if (h->stage_ev[s]) cudaEventDestroy(h->stage_ev[s]);
     }
+    if (h->side_stream) {
+        cudaStreamSynchronize(h->side_stream);
+        cudaStreamDestroy(h->side_stream);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     (void)cudaGetLastError();
     delete h;

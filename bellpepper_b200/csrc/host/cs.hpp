@@ -42,6 +42,10 @@ struct SynthesisError : std::runtime_error {
 struct Sink {
     virtual ~Sink() {}
     virtual void alloc(int is_aux, const uint64_t* vals, uint64_t n) = 0;
+    // Packed batch: one byte per value; wide[i] = (position in the batch, 4 limbs) for the values that do not fit a byte
+    // (their byte is a 0 placeholder).
+    virtual void alloc_packed(int is_aux, const uint8_t* bytes, uint64_t n, const uint64_t* wide_pos, const uint64_t* wide_vals,
+                              uint64_t n_wide) = 0;
     virtual void enforce(uint64_t n_rows, const uint32_t* lens, const uint32_t* cols, const uint64_t* coeffs, uint64_t nnz) = 0;
     virtual bp_cs* handle() { return nullptr; }
 };
@@ -52,6 +56,14 @@ struct DeviceSink : Sink {
     void alloc(int is_aux, const uint64_t* vals, uint64_t n) override {
         uint64_t first;
         if (bp_cs_alloc(h, is_aux, vals, n, &first) != BP_OK) throw SynthesisError(SynthesisError::Native, bp_cs_last_error(h));
+    }
+    void alloc_packed(int is_aux, const uint8_t* bytes, uint64_t n, const uint64_t* wide_pos, const uint64_t* wide_vals,
+                      uint64_t n_wide) override {
+        uint64_t first;
+        if (bp_cs_alloc_u8(h, is_aux, bytes, n, &first) != BP_OK) throw SynthesisError(SynthesisError::Native, bp_cs_last_error(h));
+        for (uint64_t i = 0; i < n_wide; ++i)
+            if (bp_cs_set(h, is_aux, first + wide_pos[i], wide_vals + 4 * i) != BP_OK)
+                throw SynthesisError(SynthesisError::Native, bp_cs_last_error(h));
     }
     void enforce(uint64_t n_rows, const uint32_t* lens, const uint32_t* cols, const uint64_t* coeffs, uint64_t) override {
         if (bp_cs_enforce(h, n_rows, lens, cols, coeffs) != BP_OK) throw SynthesisError(SynthesisError::Native, bp_cs_last_error(h));
@@ -66,6 +78,15 @@ struct HostSink : Sink {
     void alloc(int is_aux, const uint64_t* vals, uint64_t n) override {
         auto& v = is_aux ? aux : inputs;
         v.insert(v.end(), vals, vals + 4 * n);
+    }
+    void alloc_packed(int is_aux, const uint8_t* bytes, uint64_t n, const uint64_t* wide_pos, const uint64_t* wide_vals,
+                      uint64_t n_wide) override {
+        auto& v = is_aux ? aux : inputs;
+        const size_t base = v.size();
+        v.resize(base + 4 * n, 0);
+        for (uint64_t i = 0; i < n; ++i) v[base + 4 * i] = bytes[i];
+        for (uint64_t i = 0; i < n_wide; ++i)
+            for (int j = 0; j < 4; ++j) v[base + 4 * wide_pos[i] + j] = wide_vals[4 * i + j];
     }
     void enforce(uint64_t n_rows, const uint32_t* l, const uint32_t* c, const uint64_t* v, uint64_t nnz) override {
         lens.insert(lens.end(), l, l + 3 * n_rows);
@@ -201,8 +222,10 @@ template <bool kNamed> class TestConstraintSystemT {
     void flush() {
         for (int k = 0; k < 2; ++k) {
             if (!pend_[k].empty()) {
-                sink_->alloc(k, pend_[k].data(), pend_[k].size() / 4);
+                sink_->alloc_packed(k, pend_[k].data(), pend_[k].size(), wide_pos_[k].data(), wide_vals_[k].data(), wide_pos_[k].size());
                 pend_[k].clear();
+                wide_pos_[k].clear();
+                wide_vals_[k].clear();
             }
         }
         if (!lens_.empty()) {
@@ -219,13 +242,20 @@ template <bool kNamed> class TestConstraintSystemT {
         if (kNamed) path = compute_path(name());
         const Fr v = value();  // may throw: nothing has been registered yet (test_cs.rs:388)
         const uint64_t idx = count_[is_aux]++;
-        pend_[is_aux].insert(pend_[is_aux].end(), v.l, v.l + 4);
+        // packed staging: a byte when the value fits one (AllocatedBit / Boolean witnesses), else a placeholder + the limbs
+        if ((v.l[0] >> 8) == 0 && (v.l[1] | v.l[2] | v.l[3]) == 0) {
+            pend_[is_aux].push_back((uint8_t)v.l[0]);
+        } else {
+            wide_pos_[is_aux].push_back(pend_[is_aux].size());
+            wide_vals_[is_aux].insert(wide_vals_[is_aux].end(), v.l, v.l + 4);
+            pend_[is_aux].push_back(0);
+        }
         const Variable var = is_aux ? Variable::aux((uint32_t)idx) : Variable::input((uint32_t)idx);
         if (kNamed) {
             (is_aux ? aux_names_ : input_names_).push_back(path);
             set_named_obj(path, NamedObject{kVar, var.tagged});
         }
-        if (pend_[is_aux].size() >= (4u << 20)) flush();
+        if (pend_[is_aux].size() >= (4u << 20)) flush();  // (rows first: flush() keeps alloc-before-enforce order)
         return var;
     }
     void push_lc(const LinearCombination& lc) {
@@ -267,7 +297,8 @@ template <bool kNamed> class TestConstraintSystemT {
     size_t flush_terms_;
     uint64_t n_rows_ = 0;
     uint64_t count_[2];
-    std::vector<uint64_t> pend_[2];
+    std::vector<uint8_t> pend_[2];
+    std::vector<uint64_t> wide_pos_[2], wide_vals_[2];
     std::vector<uint32_t> lens_, cols_;
     std::vector<uint64_t> coeffs_;
     std::unordered_map<std::string, NamedObject> named_;

@@ -18,6 +18,9 @@ struct FilterSink : Sink {
     uint64_t rows_dropped = 0;
     explicit FilterSink(Sink* s) : inner(s) {}
     void alloc(int is_aux, const uint64_t* v, uint64_t n) override { inner->alloc(is_aux, v, n); }
+    void alloc_packed(int is_aux, const uint8_t* b, uint64_t n, const uint64_t* wp, const uint64_t* wv, uint64_t nw) override {
+        inner->alloc_packed(is_aux, b, n, wp, wv, nw);
+    }
     void enforce(uint64_t n_rows, const uint32_t* l, const uint32_t* c, const uint64_t* v, uint64_t nnz) override {
         if (rows_enabled) inner->enforce(n_rows, l, c, v, nnz);
         else rows_dropped += n_rows;

@@ -25,6 +25,8 @@ extern "C" {
     pub fn bp_cs_free(cs: *mut bp_cs);
     pub fn bp_cs_last_error(cs: *const bp_cs) -> *const c_char;
     pub fn bp_cs_alloc(cs: *mut bp_cs, is_aux: c_int, vals_le: *const u64, n: u64, first_index: *mut u64) -> c_int;
+    pub fn bp_cs_alloc_u8(cs: *mut bp_cs, is_aux: c_int, vals: *const u8, n: u64, first_index: *mut u64) -> c_int;
+    pub fn bp_cs_set_range_u8(cs: *mut bp_cs, is_aux: c_int, first: u64, n: u64, vals: *const u8) -> c_int;
     pub fn bp_cs_set(cs: *mut bp_cs, is_aux: c_int, idx: u64, v: *const u64) -> c_int;
     pub fn bp_cs_get(cs: *mut bp_cs, is_aux: c_int, idx: u64, v: *mut u64) -> c_int;
     pub fn bp_cs_set_range(cs: *mut bp_cs, is_aux: c_int, first: u64, n: u64, vals_le: *const u64) -> c_int;

@@ -37,8 +37,11 @@ pub struct B200ConstraintSystem<Scalar: B200Field> {
     constraint_paths: Vec<String>,
     input_names: Vec<String>,
     aux_names: Vec<String>,
-    // pending (not yet flushed) data
-    pend_vals: [Vec<u64>; 2],
+    // pending (not yet flushed) witness values, packed: one byte per value that fits a byte (AllocatedBit / Boolean
+    // witnesses, i.e. nearly everything a gadget circuit allocates); a value that does not fit leaves a 0 placeholder and
+    // goes to `pend_wide` as (position in pend_bytes, limbs), patched with bp_cs_set after the batch is appended
+    pend_bytes: [Vec<u8>; 2],
+    pend_wide: [Vec<(u64, [u64; 4])>; 2],
     count: [u64; 2],
     lens: Vec<u32>,
     cols: Vec<u32>,
@@ -48,6 +51,22 @@ pub struct B200ConstraintSystem<Scalar: B200Field> {
 
 // The handle is thread-compatible (no TLS, every call selects its device): `ConstraintSystem: Send` holds.
 unsafe impl<Scalar: B200Field> Send for B200ConstraintSystem<Scalar> {}
+
+/// Stage one witness value: a byte when it fits, else a placeholder plus an entry in the wide list.
+fn stage_value<S: PrimeField>(s: &S, bytes: &mut Vec<u8>, wide: &mut Vec<(u64, [u64; 4])>) {
+    let repr = s.to_repr();
+    let r = repr.as_ref();
+    if r[1..].iter().all(|&b| b == 0) {
+        bytes.push(r[0]);
+    } else {
+        let mut l = [0u64; 4];
+        for (i, chunk) in r.chunks_exact(8).enumerate() {
+            l[i] = u64::from_le_bytes(chunk.try_into().unwrap());
+        }
+        wide.push((bytes.len() as u64, l));
+        bytes.push(0);
+    }
+}
 
 fn repr_to_limbs<S: PrimeField>(s: &S, out: &mut Vec<u64>) {
     let repr = s.to_repr(); // canonical little-endian 32 bytes (test_cs.rs:108-111 reverses it for big-endian)
@@ -78,7 +97,8 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
             constraint_paths: vec![],
             input_names: vec!["ONE".into()],
             aux_names: vec![],
-            pend_vals: [vec![], vec![]],
+            pend_bytes: [vec![], vec![]],
+            pend_wide: [vec![], vec![]],
             count: [1, 0],
             lens: vec![],
             cols: vec![],
@@ -96,12 +116,16 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
 
     pub fn flush(&mut self) {
         for k in 0..2 {
-            if !self.pend_vals[k].is_empty() {
-                let n = (self.pend_vals[k].len() / 4) as u64;
+            if !self.pend_bytes[k].is_empty() {
+                let n = self.pend_bytes[k].len() as u64;
                 let mut first = 0u64;
-                let rc = unsafe { ffi::bp_cs_alloc(self.h, k as i32, self.pend_vals[k].as_ptr(), n, &mut first) };
+                let rc = unsafe { ffi::bp_cs_alloc_u8(self.h, k as i32, self.pend_bytes[k].as_ptr(), n, &mut first) };
                 self.check(rc);
-                self.pend_vals[k].clear();
+                for (pos, limbs) in std::mem::take(&mut self.pend_wide[k]) {
+                    let rc = unsafe { ffi::bp_cs_set(self.h, k as i32, first + pos, limbs.as_ptr()) };
+                    self.check(rc);
+                }
+                self.pend_bytes[k].clear();
             }
         }
         if !self.lens.is_empty() {
@@ -219,7 +243,7 @@ impl<Scalar: B200Field> ConstraintSystem<Scalar> for B200ConstraintSystem<Scalar
         let index = self.count[1] as usize;
         let path = compute_path(&self.current_namespace, &annotation().into());
         let value = f()?; // an Err leaves no variable behind (test_cs.rs:388)
-        repr_to_limbs(&value, &mut self.pend_vals[1]);
+        stage_value(&value, &mut self.pend_bytes[1], &mut self.pend_wide[1]);
         self.count[1] += 1;
         self.aux_names.push(path.clone());
         let var = Variable::new_unchecked(Index::Aux(index));
@@ -236,7 +260,7 @@ impl<Scalar: B200Field> ConstraintSystem<Scalar> for B200ConstraintSystem<Scalar
         let index = self.count[0] as usize;
         let path = compute_path(&self.current_namespace, &annotation().into());
         let value = f()?;
-        repr_to_limbs(&value, &mut self.pend_vals[0]);
+        stage_value(&value, &mut self.pend_bytes[0], &mut self.pend_wide[0]);
         self.count[0] += 1;
         self.input_names.push(path.clone());
         let var = Variable::new_unchecked(Index::Input(index));
