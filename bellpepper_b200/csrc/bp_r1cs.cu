@@ -39,6 +39,7 @@ struct bp_cs {
     cudaStream_t own_stream = nullptr;
     cudaStream_t side_stream = nullptr;            // the fat-row kernels of a check run beside the thin-row kernels
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_chunk[16] = {};                 // packed witness upload: copy of chunk i+1 overlaps the widening of chunk i
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -491,6 +492,8 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     if (cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BP_E_CUDA);
     if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
     if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
+    for (auto& e : h->ev_chunk)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
     if (cudaMalloc(&h->d_result, 32) != cudaSuccess) return bail(BP_E_OOM);
     h->d_err = (unsigned int*)(h->d_result + 1);
     h->d_ndef = (uint32_t*)(h->d_result + 2);
@@ -538,6 +541,8 @@ void bp_cs_free(bp_cs* h) {
         cudaStreamSynchronize(h->side_stream);
         cudaStreamDestroy(h->side_stream);
     }
+    for (auto& e : h->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -710,11 +715,35 @@ int bp_cs_set(bp_cs* h, int is_aux, uint64_t idx, const uint64_t v[4]) { return 
 static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals) {
     int rc = ensure(h, h->u8_stage, (size_t)n, 0);
     if (rc != BP_OK) return rc;
-    if ((rc = upload(h, h->u8_stage.p, vals, (size_t)n)) != BP_OK) return rc;
     DevBuf& b = is_aux ? h->aux : h->inputs;
-    widen_u8<<<grid_for(h, 2 * n, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p, n, (uint4*)((char*)b.p + first * 32),
-                                                                 shadow_ptr(h, is_aux) + first);
-    h->launches++;
+    auto widen = [&](uint64_t off, uint64_t len) {
+        widen_u8<<<grid_for(h, 2 * len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len,
+                                                                       (uint4*)((char*)b.p + (first + off) * 32),
+                                                                       shadow_ptr(h, is_aux) + first + off);
+        h->launches++;
+    };
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, vals);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    const bool dma_able = e == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+    if (dma_able && n >= (8u << 20)) {
+        // bulk refresh from pinned memory: the copies go down the side stream in up to 16 chunks, each widened on the
+        // handle's stream as soon as it has landed (H2D of chunk i+1 overlaps the widening of chunk i)
+        const uint64_t chunk = (((n + 15) / 16) + 255) & ~uint64_t(255);
+        CU(h, cudaEventRecord(h->ev_fork, h->stream));  // earlier users of the staging buffer
+        CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        int i = 0;
+        for (uint64_t off = 0; off < n; off += chunk, ++i) {
+            const uint64_t len = std::min(chunk, n - off);
+            CU(h, cudaMemcpyAsync((char*)h->u8_stage.p + off, vals + off, len, cudaMemcpyHostToDevice, h->side_stream));
+            CU(h, cudaEventRecord(h->ev_chunk[i], h->side_stream));
+            CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0));
+            widen(off, len);
+        }
+    } else {
+        if ((rc = upload(h, h->u8_stage.p, vals, (size_t)n)) != BP_OK) return rc;
+        widen(0, n);
+    }
     CU(h, cudaGetLastError());
     return BP_OK;
 }

@@ -182,6 +182,34 @@ int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t bb, uint
     });
 }
 
+int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint8_t digest[32]) {
+    if (!t || (!msg && len) || !personalization || !digest) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            std::vector<Boolean> bits;
+            bits.reserve(len * 8);
+            for (uint64_t i = 0; i < len; ++i)
+                for (int j = 0; j < 8; ++j) {  // little-endian bit order per byte (blake2s.rs:520)
+                    auto ns = cs.ns([&] { return "input bit " + std::to_string(i) + " " + std::to_string(j); });
+                    bits.push_back(Boolean::from(AllocatedBit::alloc(ns, (OptBool)((msg[i] >> j) & 1))));
+                }
+            std::vector<Boolean> out = blake2s(cs, bits, personalization);
+            for (size_t i = 0; i < 32; ++i) {
+                uint8_t b = 0;
+                for (int j = 0; j < 8; ++j) {
+                    const OptBool v = out[8 * i + j].get_value();
+                    if (v < 0) throw SynthesisError::assignment_missing();
+                    b = (uint8_t)(b | (v << j));
+                }
+                digest[i] = b;
+            }
+            cs.flush();
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
 int64_t bp_tcs_which_is_unsatisfied(bp_tcs* t, char* path, uint64_t cap) {
     if (!t) return -5;
     int64_t row = -1;

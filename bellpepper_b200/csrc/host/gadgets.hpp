@@ -546,4 +546,94 @@ template <class CS> std::vector<Boolean> sha256(CS&& cs, const std::vector<Boole
     return out;
 }
 
+// ---- blake2s (crates/bellpepper/src/gadgets/blake2s.rs) -----------------------------------------------------------------
+namespace blake2s_detail {
+static const unsigned R1 = 16, R2 = 12, R3 = 8, R4 = 7;  // blake2s.rs:29-32
+static const uint8_t SIGMA[10][16] = {  // blake2s.rs:50-61
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+static const uint8_t G_ARGS[8][4] = {{0, 4, 8, 12}, {1, 5, 9, 13}, {2, 6, 10, 14}, {3, 7, 11, 15},
+                                     {0, 5, 10, 15}, {1, 6, 11, 12}, {2, 7, 8, 13}, {3, 4, 9, 14}};  // blake2s.rs:226-305
+static const uint32_t IV[8] = {0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A, 0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19};
+
+// blake2s.rs:86-121 (the root of `cs` is a MultiEq)
+template <class M> void mixing_g(M&& cs, std::vector<UInt32>& v, unsigned a, unsigned b, unsigned c, unsigned d, const UInt32& x, const UInt32& y) {
+    auto step = [&](int i) { return cs.ns([i] { return "mixing step " + std::to_string(i); }); };
+    { auto ns = step(1); const UInt32 ops[3] = {v[a], v[b], x}; v[a] = UInt32::addmany(ns, ops, 3); }
+    { auto ns = step(2); v[d] = v[d].xor_(ns, v[a]).rotr(R1); }
+    { auto ns = step(3); const UInt32 ops[2] = {v[c], v[d]}; v[c] = UInt32::addmany(ns, ops, 2); }
+    { auto ns = step(4); v[b] = v[b].xor_(ns, v[c]).rotr(R2); }
+    { auto ns = step(5); const UInt32 ops[3] = {v[a], v[b], y}; v[a] = UInt32::addmany(ns, ops, 3); }
+    { auto ns = step(6); v[d] = v[d].xor_(ns, v[a]).rotr(R3); }
+    { auto ns = step(7); const UInt32 ops[2] = {v[c], v[d]}; v[c] = UInt32::addmany(ns, ops, 2); }
+    { auto ns = step(8); v[b] = v[b].xor_(ns, v[c]).rotr(R4); }
+}
+}  // namespace blake2s_detail
+
+// blake2s.rs:171-315: h is updated in place
+template <class CS> void blake2s_compression(CS&& cs_in, std::vector<UInt32>& h, const std::vector<UInt32>& m, uint64_t t, bool f) {
+    using namespace blake2s_detail;
+    using CSv = std::remove_reference_t<CS>;
+    std::vector<UInt32> v(h);
+    for (int i = 0; i < 8; ++i) v.push_back(UInt32::constant(IV[i]));
+    { auto ns = cs_in.ns([] { return std::string("first xor"); }); v[12] = v[12].xor_(ns, UInt32::constant((uint32_t)t)); }
+    { auto ns = cs_in.ns([] { return std::string("second xor"); }); v[13] = v[13].xor_(ns, UInt32::constant((uint32_t)(t >> 32))); }
+    if (f) { auto ns = cs_in.ns([] { return std::string("third xor"); }); v[14] = v[14].xor_(ns, UInt32::constant(0xffffffffu)); }
+    {
+        MultiEq<CSv> cs(cs_in);
+        for (int i = 0; i < 10; ++i) {
+            auto rns = cs.ns([i] { return "round " + std::to_string(i); });
+            const uint8_t* s = SIGMA[i % 10];
+            for (int j = 0; j < 8; ++j) {
+                auto ns = rns.ns([j] { return "mixing invocation " + std::to_string(j + 1); });
+                mixing_g(ns, v, G_ARGS[j][0], G_ARGS[j][1], G_ARGS[j][2], G_ARGS[j][3], m[s[2 * j]], m[s[2 * j + 1]]);
+            }
+        }
+    }  // MultiEq drops here
+    for (int i = 0; i < 8; ++i) {
+        auto ns = cs_in.ns([i] { return "h[" + std::to_string(i) + "] ^ v[" + std::to_string(i) + "] ^ v[" + std::to_string(i) + " + 8]"; });
+        { auto n2 = ns.ns([] { return std::string("first xor"); }); h[i] = h[i].xor_(n2, v[i]); }
+        { auto n2 = ns.ns([] { return std::string("second xor"); }); h[i] = h[i].xor_(n2, v[i + 8]); }
+    }
+}
+
+// blake2s.rs:344-406: input bits little-endian per byte; output through into_bits (little-endian)
+template <class CS> std::vector<Boolean> blake2s(CS&& cs, const std::vector<Boolean>& input, const uint8_t personalization[8]) {
+    using namespace blake2s_detail;
+    if (input.size() % 8 != 0) throw std::logic_error("blake2s: input must be whole bytes");
+    auto le32 = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+    std::vector<UInt32> h;
+    for (int i = 0; i < 8; ++i) h.push_back(UInt32::constant(IV[i]));
+    h[0] = UInt32::constant(IV[0] ^ 0x01010000u ^ 32u);
+    h[6] = UInt32::constant(IV[6] ^ le32(personalization));
+    h[7] = UInt32::constant(IV[7] ^ le32(personalization + 4));
+    std::vector<std::vector<UInt32>> blocks;
+    for (size_t b0 = 0; b0 < input.size(); b0 += 512) {
+        std::vector<UInt32> words;
+        const size_t b1 = std::min(input.size(), b0 + 512);
+        for (size_t w0 = b0; w0 < b1; w0 += 32) {
+            Boolean tmp[32];
+            for (size_t i = 0; i < 32; ++i) tmp[i] = (w0 + i < b1) ? input[w0 + i] : Boolean::constant(false);
+            words.push_back(UInt32::from_bits(tmp));
+        }
+        while (words.size() < 16) words.push_back(UInt32::constant(0));
+        blocks.push_back(std::move(words));
+    }
+    if (blocks.empty()) blocks.push_back(std::vector<UInt32>(16, UInt32::constant(0)));
+    for (size_t i = 0; i + 1 < blocks.size(); ++i) {
+        auto ns = cs.ns([i] { return "block " + std::to_string(i); });
+        blake2s_compression(ns, h, blocks[i], (uint64_t)(i + 1) * 64, false);
+    }
+    {
+        auto ns = cs.ns([] { return std::string("final block"); });
+        blake2s_compression(ns, h, blocks.back(), input.size() / 8, true);
+    }
+    std::vector<Boolean> out;
+    for (auto& wd : h) wd.into_bits(out);
+    return out;
+}
+
 }  // namespace bph

@@ -20,6 +20,7 @@ _SIGS = {
     "bp_tcs_flush": (ctypes.c_int, [vp]),
     "bp_tcs_sha256_block": (ctypes.c_int, [vp, vp, vp]),
     "bp_tcs_sha256": (ctypes.c_int, [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, u64p]),
+    "bp_tcs_blake2s": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, vp]),
     "bp_tcs_which_is_unsatisfied": (ctypes.c_int64, [vp, vp, ctypes.c_uint64]),
     "bp_tcs_set": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
     "bp_tcs_get": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
@@ -107,6 +108,12 @@ class Tcs:
         self._ck(self.L.bp_tcs_sha256(self.t, msg, len(msg), block_begin, block_end, out, ctypes.byref(before)))
         return out.raw, before.value
 
+    def blake2s(self, msg: bytes, personalization: bytes = b"12345678") -> bytes:
+        assert len(personalization) == 8
+        out = ctypes.create_string_buffer(32)
+        self._ck(self.L.bp_tcs_blake2s(self.t, msg, len(msg), personalization, out))
+        return out.raw
+
     def which_is_unsatisfied(self) -> Optional[str]:
         buf = ctypes.create_string_buffer(512)
         row = self.L.bp_tcs_which_is_unsatisfied(self.t, buf, 512)
@@ -170,6 +177,21 @@ class Tcs:
 def chain_message(blocks: int) -> bytes:
     """Message whose sha256() circuit has exactly `blocks` compression calls (the last one holds the padding)."""
     return xorshift_bytes(64 * blocks - 9)
+
+
+def blake2s_into_new_handle(field: int, device: int, n_bytes: int):
+    """BASELINE configs[2]: blake2s gadget over an n_bytes preimage (xorshift bytes), streamed into a fresh device handle."""
+    blocks = max(1, (n_bytes + 63) // 64)
+    t = Tcs(field, device, named=False, reserve=(blocks * 21600 + 4096, blocks * 140000 + 65536, blocks * 21700 + 4096))
+    digest = t.blake2s(xorshift_bytes(n_bytes))
+    info = {"rows_total": t.num_constraints(), "row0": 0, "bytes": n_bytes, "digest": digest.hex(), "tcs": t}
+    return vp(t.handle), info
+
+
+def blake2s_host_csr(field: int, n_bytes: int):
+    with Tcs(field, device=-1, named=False) as t:
+        t.blake2s(xorshift_bytes(n_bytes))
+        return t.host_csr()
 
 
 def sha256_chain_host_csr(field: int, blocks: int):

@@ -44,6 +44,7 @@ WORKLOADS = {
     "synthetic_2p24_t6_bls12_381": ("synthetic", 0, {"log_rows": 24, "t": 6}),        # configs[3]
     "synthetic_2p27_t32_pallas": ("synthetic", 1, {"log_rows": 27, "t": 32}),         # configs[4] (8 GPUs)
     "synthetic_2p20_t6_bls12_381": ("synthetic", 0, {"log_rows": 20, "t": 6}),        # small, for quick checks
+    "blake2s_64KiB_vesta": ("blake2s", 2, {"bytes": 65536}),                          # configs[2]
     "sha256_chain_64_pallas": ("sha256", 1, {"blocks": 64}),
     "sha256_chain_512_pallas": ("sha256", 1, {"blocks": 512}),
 }
@@ -137,6 +138,12 @@ def build_workload(L, ffi, name, rank, world, device):
 
         h, finfo = fixtures.sha256_chain_into_new_handle(field, device, prm["blocks"], rank, world)
         info.update(finfo)
+    elif kind == "blake2s":
+        from bellpepper_b200 import fixtures
+
+        assert world == 1, "blake2s workload: single shard"
+        h, finfo = fixtures.blake2s_into_new_handle(field, device, prm["bytes"])
+        info.update(finfo)
     else:
         raise ValueError(kind)
     assert L.bp_cs_sync(h) == 0
@@ -159,6 +166,14 @@ def cpu_reference_rate(name, sample_rows_log2, threads, steps=1, warmup=0):
         w = c_api.synth_witness(field, SEED, 0, n_vars)
         inst = c_api.Instance(field, lens, cols, coeffs, w[:N_INPUTS], w[N_INPUTS:])
         sample = f"first 2^{sample_rows_log2} rows of {name} (full {n_vars}-element witness)"
+    elif kind == "blake2s":
+        from bellpepper_b200 import fixtures
+
+        nb = min(prm["bytes"], 64 * max(1, (1 << sample_rows_log2) // 21600))
+        lens, cols, coeffs, inputs, aux = fixtures.blake2s_host_csr(field, nb)
+        n = lens.size // 3
+        inst = c_api.Instance(field, lens, cols, coeffs, inputs, aux)
+        sample = f"blake2s of the first {nb} bytes ({n} rows) of {name}"
     else:
         from bellpepper_b200 import fixtures
 

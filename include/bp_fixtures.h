@@ -38,6 +38,11 @@ int bp_tcs_sha256_block(bp_tcs* t, const uint8_t block[64], uint8_t out32[32]);
 int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t block_begin, uint64_t block_end, uint8_t digest[32],
                   uint64_t* rows_before);
 
+/* blake2s() gadget over `len` message bytes, each bit allocated as "input bit <byte> <bit>" least significant first,
+ * with an 8-byte personalization (crates/bellpepper/src/gadgets/blake2s.rs:344-406, tests :498-555).  digest = the 32
+ * output bytes (the gadget's output bits are little-endian per byte). */
+int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint8_t digest[32]);
+
 /* TestConstraintSystem surface (test_cs.rs:239-323).  which_is_unsatisfied: returns the row (>= 0), -1 when
  * satisfied, < -1 on error; `path` (cap bytes) receives the constraint's path when named. */
 int64_t bp_tcs_which_is_unsatisfied(bp_tcs* t, char* path, uint64_t cap);

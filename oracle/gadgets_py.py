@@ -547,6 +547,101 @@ def sha256(cs, field, input_bits: List[Boolean]) -> List[Boolean]:  # sha256.rs:
     return [b for word in cur for b in word.into_bits_be()]
 
 
+# ---- blake2s (crates/bellpepper/src/gadgets/blake2s.rs) -------------------------------------------------------------------
+BLAKE2S_R = (16, 12, 8, 7)  # blake2s.rs:29-32
+BLAKE2S_SIGMA = [  # blake2s.rs:50-61
+    [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15],
+    [14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3],
+    [11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4],
+    [7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8],
+    [9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13],
+    [2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9],
+    [12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11],
+    [13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10],
+    [6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5],
+    [10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0],
+]
+
+
+def blake2s_mixing_g(cs, field, v: List[UInt32], a: int, b: int, c: int, d: int, x: UInt32, y: UInt32):
+    """blake2s.rs:86-121 (cs's root is a MultiEq)."""
+    r1, r2, r3, r4 = BLAKE2S_R
+    with cs.namespace("mixing step 1") as ns:
+        v[a] = UInt32.addmany(ns, field, [v[a], v[b], x])
+    with cs.namespace("mixing step 2") as ns:
+        v[d] = v[d].xor(ns, v[a]).rotr(r1)
+    with cs.namespace("mixing step 3") as ns:
+        v[c] = UInt32.addmany(ns, field, [v[c], v[d]])
+    with cs.namespace("mixing step 4") as ns:
+        v[b] = v[b].xor(ns, v[c]).rotr(r2)
+    with cs.namespace("mixing step 5") as ns:
+        v[a] = UInt32.addmany(ns, field, [v[a], v[b], y])
+    with cs.namespace("mixing step 6") as ns:
+        v[d] = v[d].xor(ns, v[a]).rotr(r3)
+    with cs.namespace("mixing step 7") as ns:
+        v[c] = UInt32.addmany(ns, field, [v[c], v[d]])
+    with cs.namespace("mixing step 8") as ns:
+        v[b] = v[b].xor(ns, v[c]).rotr(r4)
+
+
+BLAKE2S_G_ARGS = [(0, 4, 8, 12), (1, 5, 9, 13), (2, 6, 10, 14), (3, 7, 11, 15), (0, 5, 10, 15), (1, 6, 11, 12), (2, 7, 8, 13),
+                  (3, 4, 9, 14)]  # blake2s.rs:226-305
+
+
+def blake2s_compression(cs, field, h: List[UInt32], m: List[UInt32], t: int, f: bool):
+    """blake2s.rs:171-315; updates h in place."""
+    assert len(h) == 8 and len(m) == 16
+    v = list(h) + [UInt32.constant(x) for x in IV]
+    with cs.namespace("first xor") as ns:
+        v[12] = v[12].xor(ns, UInt32.constant(t & 0xFFFFFFFF))
+    with cs.namespace("second xor") as ns:
+        v[13] = v[13].xor(ns, UInt32.constant((t >> 32) & 0xFFFFFFFF))
+    if f:
+        with cs.namespace("third xor") as ns:
+            v[14] = v[14].xor(ns, UInt32.constant(0xFFFFFFFF))
+    me = MultiEq(cs, field)
+    for i in range(10):
+        with me.namespace(f"round {i}") as rns:
+            s = BLAKE2S_SIGMA[i % 10]
+            for j, (a, b, c, d) in enumerate(BLAKE2S_G_ARGS):
+                with rns.namespace(f"mixing invocation {j + 1}") as ns:
+                    blake2s_mixing_g(ns, field, v, a, b, c, d, m[s[2 * j]], m[s[2 * j + 1]])
+    me.finish()  # MultiEq::drop at the end of the scope (blake2s.rs:224-306)
+    for i in range(8):
+        with cs.namespace(f"h[{i}] ^ v[{i}] ^ v[{i} + 8]") as ns:
+            with ns.namespace("first xor") as n2:
+                h[i] = h[i].xor(n2, v[i])
+            with ns.namespace("second xor") as n2:
+                h[i] = h[i].xor(n2, v[i + 8])
+
+
+def blake2s(cs, field, input_bits: List[Boolean], personalization: bytes) -> List[Boolean]:
+    """blake2s.rs:344-406; input bits little-endian per byte, output via into_bits (little-endian)."""
+    assert len(personalization) == 8 and len(input_bits) % 8 == 0
+    h = [UInt32.constant(x) for x in IV]
+    h[0] = UInt32.constant(IV[0] ^ 0x01010000 ^ 32)
+    h[6] = UInt32.constant(IV[6] ^ int.from_bytes(personalization[0:4], "little"))
+    h[7] = UInt32.constant(IV[7] ^ int.from_bytes(personalization[4:8], "little"))
+    blocks = []
+    for b0 in range(0, len(input_bits), 512):
+        block = input_bits[b0: b0 + 512]
+        words = []
+        for w0 in range(0, len(block), 32):
+            tmp = list(block[w0: w0 + 32])
+            tmp += [Boolean.constant(False)] * (32 - len(tmp))
+            words.append(UInt32.from_bits(tmp))
+        words += [UInt32.constant(0)] * (16 - len(words))
+        blocks.append(words)
+    if not blocks:
+        blocks.append([UInt32.constant(0) for _ in range(16)])
+    for i, block in enumerate(blocks[:-1]):
+        with cs.namespace(f"block {i}") as ns:
+            blake2s_compression(ns, field, h, block, (i + 1) * 64, False)
+    with cs.namespace("final block") as ns:
+        blake2s_compression(ns, field, h, blocks[-1], len(input_bits) // 8, True)
+    return [b for word in h for b in word.into_bits()]
+
+
 def xorshift_bytes(seed_bytes: bytes, n: int) -> bytes:
     """rand_xorshift 0.3 XorShiftRng::from_seed(seed).next_u32() as u8, n times (SURVEY.md section 4: verified to
     regenerate the reference's pinned BLAKE2s digests)."""

@@ -112,3 +112,25 @@ def test_front_end_output_satisfies_the_oracle_and_flips():
     inst.set(True, 5, 2)  # aux 5 is message bit 5: its own boolean constraint (row 5) is the first to fail
     bad = inst.check(1, True)
     assert bad == 5 and paths[bad] == "input bit 0 2/boolean constraint"
+
+
+@pytest.mark.parametrize("fid,n_bytes", [(0, 64), (2, 64), (1, 97), (2, 0)])
+def test_blake2s_identical_to_oracle_gadgets(fid, n_bytes):  # blake2s.rs:443-457 (21518), :498-555 (digests)
+    F = FIELDS[fid]
+    msg = fixtures.xorshift_bytes(n_bytes)
+    cs = TestConstraintSystem(F)
+    bits = []
+    for i, byte in enumerate(msg):
+        for j in range(8):
+            with cs.namespace(f"input bit {i} {j}") as ns:
+                bits.append(G.Boolean.from_bit(G.AllocatedBit.alloc(ns, bool((byte >> j) & 1))))
+    G.blake2s(cs, F, bits, b"12345678")
+    with fixtures.Tcs(fid, device=-1, named=True) as t:
+        digest = t.blake2s(msg)
+        assert digest == hashlib.blake2s(msg, digest_size=32, person=b"12345678").digest()
+        assert t.num_constraints() == cs.num_constraints()
+        if n_bytes == 64:
+            assert t.num_constraints() == 21518
+        same(t.host_csr(), oracle_csr(cs))
+        for row in (0, cs.num_constraints() // 2, cs.num_constraints() - 1) if cs.num_constraints() else ():
+            assert t.row_path(row) == cs.constraints[row][3]

@@ -123,3 +123,46 @@ def test_sha256_chain_64_blocks_pallas_satisfied_and_sharded():
             assert L.bp_cs_first_unsatisfied(h, ctypes.byref(row)) == 0
             got.append(row.value + before if row.value >= 0 else None)
     assert min(g for g in got if g is not None) == want
+
+
+@pytest.mark.parametrize("fid,n_bytes", [(2, 200), (0, 64)])
+def test_blake2s_bit_exact_and_flips(fid, n_bytes):
+    """configs[2]-shaped: blake2s gadget (Vesta Fr in BASELINE): every LC value equals the oracle's, satisfied, digest right;
+    then witness edits (bit flips and non-boolean values) give the oracle's first failing row."""
+    msg = fixtures.xorshift_bytes(n_bytes)
+    with fixtures.Tcs(fid, device=-1, named=False) as rec:
+        rec.blake2s(msg)
+        lens, cols, coeffs, inputs, aux = rec.host_csr()
+    inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+    bad, az_r, bz_r, cz_r = inst.eval(4)
+    assert bad == -1
+    L = ffi.load()
+    rng = random.Random(5 + fid)
+    with fixtures.Tcs(fid, device=0, named=False) as t:
+        digest = t.blake2s(msg)
+        assert digest == hashlib.blake2s(msg, digest_size=32, person=b"12345678").digest()
+        n = t.num_constraints()
+        assert n == lens.size // 3
+        assert t.is_satisfied()
+        az, bz, cz = device_eval(t, n)
+        assert (az == az_r).all() and (bz == bz_r).all() and (cz == cz_r).all()
+        h = ffi.vp(t.handle)
+        stats = {}
+        for key in (b"plain_rows", b"fat_rows", b"fat_undecided_rows", b"deferred_rows"):
+            v = ctypes.c_int64()
+            assert L.bp_cs_get_option(h, key, ctypes.byref(v)) == 0
+            stats[key.decode()] = v.value
+        assert stats["fat_rows"] > 10 and stats["plain_rows"] > n // 2
+        assert stats["fat_undecided_rows"] == 0 and stats["deferred_rows"] == 0  # honest witness: integer kernels decide all
+        for _ in range(10):
+            idx = rng.randrange(aux.shape[0])
+            old = int(aux[idx][0])
+            new = 1 - old if rng.random() < 0.7 else rng.randrange(FIELDS[fid].p)
+            v = c_api.ints_to_limbs([new])
+            assert L.bp_cs_set(h, 1, idx, v.ctypes.data) == 0
+            inst.set(True, idx, new)
+            assert t.first_unsatisfied_row() == inst.check(4, False)
+            v = c_api.ints_to_limbs([old])
+            assert L.bp_cs_set(h, 1, idx, v.ctypes.data) == 0
+            inst.set(True, idx, old)
+        assert t.is_satisfied()
