@@ -379,7 +379,41 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             h->launches++;                                                                                                                     \
         }                                                                                                                                      \
     } while (0)
-    if (emit) {
+    const int64_t ev = h->variant < 0 ? 0 : h->variant;
+    if (emit && ev < 100 && !(ev & 1) && h->n_plain_rows > 0) {
+        // emit mode on a gadget-shaped instance: the integer kernels write the rows they can decide, the full-width kernels
+        // the generic rows and whatever was deferred / left undecided (same lists as in check mode)
+        const bool fat_int = !(ev & 2) && !(ev & 8) && h->fat_int_ok && h->n_fat_rows;
+        if (h->n_fat_rows) {
+            CU(h, cudaEventRecord(h->ev_fork, h->stream));
+            CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            cudaStream_t fs = h->side_stream;
+            if (fat_int) {
+                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * 6);
+                DISPATCH_FIELD(h, (check_fat_int<F, true><<<igrid, block, 0, fs>>>(m, o, fat, (uint32_t)h->n_fat_rows,
+                                                                                  (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+                DISPATCH_FIELD(h, (check_fat_rows<F, true, 0, 4><<<std::min(fat_grid, h->sm_count), block, 0, fs>>>(
+                                      m, o, h->fc, (const uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+                h->launches += 2;
+            } else {
+                DISPATCH_FIELD(h, (check_fat_rows<F, true, 0, 4><<<fat_grid, block, 0, fs>>>(m, o, h->fc, fat, n_fat)));
+                h->launches++;
+            }
+            CU(h, cudaGetLastError());
+            CU(h, cudaEventRecord(h->ev_join, fs));
+        }
+        const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;
+        const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
+        cudaError_t ae = cudaSuccess;
+        DISPATCH_FIELD(h, (ae = cudaFuncSetAttribute(check_small<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem)));
+        CU(h, ae);
+        DISPATCH_FIELD(h, (check_small<F, true><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef)));
+        const int lgrid = grid_for(h, h->n_gen_rows + (uint64_t)h->sm_count * block, block, 16);
+        DISPATCH_FIELD(h, (check_rows<F, true, 0, 4, true><<<lgrid, block, 0, h->stream>>>(
+                              m, o, h->fc, (const uint32_t*)h->gen_rows.p, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
+        h->launches += 2;
+        if (h->n_fat_rows) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    } else if (emit) {
         BP_LAUNCH(true, 0, 4, 0, 4);
     } else if (h->variant >= 100) {
 #ifdef BP_EXPERIMENTAL_VARIANTS
@@ -412,8 +446,8 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             const int fgrid_small = std::min(fat_grid, h->sm_count);
             if (fat_shadow && !(v & 8) && h->fat_int_ok) {  // integer pass first; the modular kernel takes what it could not decide
                 const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * 6);
-                DISPATCH_FIELD(h, (check_fat_int<F><<<igrid, block, 0, fs>>>(m, o, fat, (uint32_t)h->n_fat_rows,
-                                                                            (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+                DISPATCH_FIELD(h, (check_fat_int<F, false><<<igrid, block, 0, fs>>>(m, o, fat, (uint32_t)h->n_fat_rows,
+                                                                                   (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
                 // (normally nothing is left: a small grid, grid-stride over whatever there is)
                 DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fgrid_small, block, 0, fs>>>(
                                       m, o, h->fc, (const uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
@@ -432,8 +466,8 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             if (use_small) {
                 const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;  // one warp per block of rows
                 const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
-                CU(h, cudaFuncSetAttribute(check_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
-                check_small<<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
+                CU(h, cudaFuncSetAttribute(check_small<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
+                check_small<0, false><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
                 h->launches++;
                 const uint32_t* gl = (const uint32_t*)h->gen_rows.p;
                 // the plan's generic rows, plus whatever check_small deferred (normally nothing): grid-stride over both

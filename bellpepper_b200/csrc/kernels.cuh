@@ -512,8 +512,26 @@ __device__ __forceinline__ uint32_t small_verdict(uint32_t a, uint32_t b, uint32
     return ((long long)(int32_t)a * (long long)(int32_t)b + (long long)(int32_t)c) != 0ll ? 1u : 0u;
 }
 
+// Canonical residue of a small signed integer: v, or p - |v|.
+template <int F> __device__ __forceinline__ void st_small_canonical(uint4* dst, int32_t v) {
+    uint32_t x[8] = {(uint32_t)(v < 0 ? -v : v), 0, 0, 0, 0, 0, 0, 0};
+    if (v < 0) {
+        uint32_t r[8];
+        neg_mod<F>(r, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = r[i];
+    }
+    st8(dst, x);
+}
+// Emit mode: A.w, B.w, C.w of a row the integer kernel decided (c is the sum over the NEGATED C coefficients).
+template <int F> __device__ __forceinline__ void emit_small(const CheckOut& o, uint32_t row, uint32_t a, uint32_t b, uint32_t c) {
+    if (o.az) st_small_canonical<F>(o.az + 2 * (size_t)row, (int32_t)a);
+    if (o.bz) st_small_canonical<F>(o.bz + 2 * (size_t)row, (int32_t)b);
+    if (o.cz) st_small_canonical<F>(o.cz + 2 * (size_t)row, -(int32_t)c);
+}
+
 // One plain row by its own thread straight from global memory (blocks that do not fit the staging buffer).
-__device__ __forceinline__ uint32_t small_row_direct(uint32_t row, const CsrView& m) {
+__device__ __forceinline__ uint32_t small_row_direct(uint32_t row, const CsrView& m, uint32_t* sums = nullptr) {
     const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
                    p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
     uint32_t sum[3] = {0, 0, 0};
@@ -526,9 +544,12 @@ __device__ __forceinline__ uint32_t small_row_direct(uint32_t row, const CsrView
             sum[i] += small_contrib(w, __ldg(m.shadow + (w & kColIdxMask)));
         }
     }
+    if (sums) { sums[0] = sum[0]; sums[1] = sum[1]; sums[2] = sum[2]; }
     return small_verdict(sum[0], sum[1], sum[2]);
 }
 
+// EMIT: also write the canonical A.w, B.w, C.w of every row decided here (F is only used for that).
+template <int F, bool EMIT>
 __global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, CheckOut o, uint32_t* __restrict__ deferred,
                                                                 uint32_t* __restrict__ n_deferred) {
     extern __shared__ __align__(16) unsigned char small_smem[];
@@ -637,16 +658,25 @@ __global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, Check
                         const uint32_t la = (meta_cur.x >> 10) & 255u, lb = (meta_cur.x >> 18) & 255u;
                         const uint32_t pa = q[o0], pb = q[o0 + la], pc = q[o0 + la + lb], pd = q[e1];
                         verdict0 = small_verdict(pb - pa, pc - pb, pd - pc);
+                        if (EMIT && verdict0 != 2u) emit_small<F>(o, row, pb - pa, pc - pb, pd - pc);
                     }
                     if (plain1) {
                         const uint32_t la = (meta_cur.y >> 10) & 255u, lb = (meta_cur.y >> 18) & 255u;
                         const uint32_t pa = q[o1], pb = q[o1 + la], pc = q[o1 + la + lb], pd = q[o2];
                         verdict1 = small_verdict(pb - pa, pc - pb, pd - pc);
+                        if (EMIT && verdict1 != 2u) emit_small<F>(o, row + 1u, pb - pa, pc - pb, pd - pc);
                     }
                 }
             } else if (any_plain) {
-                if (plain0) verdict0 = small_row_direct(row, m);
-                if (plain1) verdict1 = small_row_direct(row + 1u, m);
+                uint32_t sums[3];
+                if (plain0) {
+                    verdict0 = small_row_direct(row, m, sums);
+                    if (EMIT && verdict0 != 2u) emit_small<F>(o, row, sums[0], sums[1], sums[2]);
+                }
+                if (plain1) {
+                    verdict1 = small_row_direct(row + 1u, m, sums);
+                    if (EMIT && verdict1 != 2u) emit_small<F>(o, row + 1u, sums[0], sums[1], sums[2]);
+                }
             }
             if (verdict0 == 1u && row < my_bad) my_bad = row;
             if (verdict1 == 1u && row + 1u < my_bad) my_bad = row + 1u;
@@ -1005,13 +1035,27 @@ __device__ __forceinline__ void mad10(uint32_t* r, const uint32_t* x, uint32_t b
     r[11] = (uint32_t)(c >> 32);
 }
 
-// One fat row as integers: 0 = holds, 1 = fails, 2 = undecided (take the modular path).
-template <int F>
+// (P - N) mod p for P, N < p, canonical; false when either is not below p.
+template <int F> __device__ __forceinline__ bool int_residue(uint32_t* out /*8*/, const uint32_t* P /*10*/, const uint32_t* N /*10*/) {
+    if ((P[8] | P[9] | N[8] | N[9]) != 0u || !is_canonical<F>(P) || !is_canonical<F>(N)) return false;
+    uint32_t d[8], pl[8];
+    const uint32_t borrow = subn<8>(d, P, N);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pl[i] = borrow ? PL<F>(i) : 0u;
+    (void)addn<8>(out, d, pl);
+    return true;
+}
+
+// One fat row as integers: 0 = holds, 1 = fails, 2 = undecided (take the modular path).  EMIT: lane 0 also writes the
+// canonical A.w, B.w, C.w (a row whose sums are not below p is left undecided).
+template <int F, bool EMIT>
 __device__ __forceinline__ uint32_t fat_row_integer(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, const CsrView& m,
-                                                    unsigned long long* bk, uint32_t null_word) {
+                                                    unsigned long long* bk, uint32_t null_word, const CheckOut& o, uint32_t row) {
     uint32_t Pa[10], Na[10], Pb[10], Nb[10];
     if (!fat_lc_integer<F, false>(Pa, Na, p0, p1, m, bk, null_word)) return 2u;
     if (!fat_lc_integer<F, false>(Pb, Nb, p1, p2, m, bk, null_word)) return 2u;
+    uint32_t ea[8], eb[8];
+    if (EMIT && (!int_residue<F>(ea, Pa, Na) || !int_residue<F>(eb, Pb, Nb))) return 2u;
     uint32_t a_wide = 0, b_wide = 0;  // non-zero when the LC is not a non-negative 32-bit integer
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -1032,6 +1076,15 @@ __device__ __forceinline__ uint32_t fat_row_integer(uint32_t p0, uint32_t p1, ui
         if (!fat_lc_integer<F, true>(Pc, Nc, p2, p3, m, bk, null_word)) return 2u;
         mad10(L, YP, b, Pc);
         mad10(R, YN, b, Nc);
+        if (EMIT) {
+            uint32_t ec[8];
+            if (!int_residue<F>(ec, Nc, Pc)) return 2u;  // C holds the negated coefficients
+            if ((threadIdx.x & 31u) == 0) {
+                if (o.az) st8(o.az + 2 * (size_t)row, ea);
+                if (o.bz) st8(o.bz + 2 * (size_t)row, eb);
+                if (o.cz) st8(o.cz + 2 * (size_t)row, ec);
+            }
+        }
     }
     uint32_t diff = 0, high = 0;
 #pragma unroll
@@ -1040,7 +1093,9 @@ __device__ __forceinline__ uint32_t fat_row_integer(uint32_t p0, uint32_t p1, ui
         if (i >= 8) high |= L[i] | R[i];
     }
     if (diff == 0u) return 0u;
-    if (high == 0u && ((L[7] | R[7]) >> 29) == 0u) return 1u;  // both below 2^253: the difference is non-zero and below p
+    // both below 2^253: the difference is non-zero and below p.  (Emit mode has written the row: it is decided either way;
+    // the first-failure word is not read back by bp_cs_eval.)
+    if (EMIT || (high == 0u && ((L[7] | R[7]) >> 29) == 0u)) return 1u;
     return 2u;
 }
 
@@ -1075,7 +1130,7 @@ __device__ __forceinline__ void warp_fold_lc(uint32_t* acc, uint32_t k0, uint32_
 }
 
 // ---- K1, fat rows, integer pass: one warp per constraint; rows it cannot decide are listed for check_fat_rows -------------
-template <int F>
+template <int F, bool EMIT>
 __global__ void __launch_bounds__(128, 6) check_fat_int(CsrView m, CheckOut o, const uint32_t* __restrict__ fat_rows, uint32_t n_fat,
                                                         uint32_t* __restrict__ undecided, uint32_t* __restrict__ n_undecided) {
     __shared__ unsigned long long s_bk[4][kBucketWords];
@@ -1088,7 +1143,7 @@ __global__ void __launch_bounds__(128, 6) check_fat_int(CsrView m, CheckOut o, c
         const uint32_t row = __ldg(fat_rows + i);
         const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
                        p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
-        const uint32_t v = fat_row_integer<F>(p0, p1, p2, p3, m, bk, null_word);
+        const uint32_t v = fat_row_integer<F, EMIT>(p0, p1, p2, p3, m, bk, null_word, o, row);
         if (v == 1u && row < my_bad) my_bad = row;
         if (v == 2u && lane == 0) undecided[atomicAdd(n_undecided, 1u)] = row;
         __syncwarp();

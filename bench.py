@@ -351,6 +351,47 @@ def main():
         else:
             e2e_s, e2e_h2d = e2e_full_s, n_vars * 32
             e2e_what = "witness (pinned host, 32 B per element) -> bp_cs_set_range -> check -> result to host; matrices resident (ingested once)"
+        # ---- K2, informational: batched LinearCombination::eval (canonical A.w, B.w, C.w of every row into device buffers)
+        eval_info = None
+        try:
+            n_loc = info["rows"]
+            outs = [torch.empty((n_loc, 4), dtype=torch.int64, device=f"cuda:{local_rank}") for _ in range(3)]
+            ptrs = [ctypes.c_void_p(t.data_ptr()) for t in outs]
+            for _ in range(2):
+                assert L.bp_cs_eval_async(h, *ptrs) == 0, L.bp_cs_last_error(h)
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(stream)
+            for _ in range(3):
+                L.bp_cs_eval_async(h, *ptrs)
+            v1.record(stream)
+            barrier()
+            ev_ms = v0.elapsed_time(v1) / 3
+            eval_info = {"ms_per_pass": ev_ms, "rows_per_s_this_rank": n_loc / (ev_ms * 1e-3), "out_bytes": 96 * n_loc,
+                         "what": "bp_cs_eval_async: canonical A.w, B.w, C.w of every row of this rank's shard, device to device"}
+            del outs
+        except Exception as e:  # e.g. not enough memory for the three output vectors
+            eval_info = {"skipped": str(e)[:200]}
+
+        # ---- full-size self-check (untimed): a satisfied instance must fail after one witness bit is flipped, at a row
+        # that exists, and hold again once it is restored (exact first-failure parity is tests/'s job at oracle-sized inputs)
+        selfcheck = None
+        if first_bad == 0x7FFFFFFFFFFFFFFF and info["n_aux"] > 10:
+            import numpy as np
+
+            victim = (info["n_aux"] * 2) // 3
+            old = np.zeros(4, np.uint64)
+            assert L.bp_cs_get(h, 1, victim, ctypes.c_void_p(old.ctypes.data)) == 0
+            new = np.array([1 - int(old[0]) if int(old[0]) in (0, 1) and not old[1:].any() else int(old[0]) ^ 1, old[1], old[2], old[3]], np.uint64)
+            assert L.bp_cs_set(h, 1, victim, ctypes.c_void_p(new.ctypes.data)) == 0
+            step_device()
+            after_flip = int(result.item())
+            assert L.bp_cs_set(h, 1, victim, ctypes.c_void_p(old.ctypes.data)) == 0
+            step_device()
+            restored = int(result.item())
+            assert 0 <= after_flip < n_rows_total, f"flipping aux[{victim}] was not detected ({after_flip})"
+            assert restored == 0x7FFFFFFFFFFFFFFF, "instance does not hold after the witness was restored"
+            selfcheck = {"flipped_aux": victim, "first_unsatisfied_after_flip": after_flip, "holds_after_restore": True}
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / a.steps
@@ -400,6 +441,8 @@ def main():
                          **plan},
             "clocks": clocks,
             "first_unsatisfied_row": None if first_bad == 0x7FFFFFFFFFFFFFFF else first_bad,
+            "selfcheck": selfcheck,
+            "eval_all_rows": eval_info,
             "instance": {k: info[k] for k in ("rows", "nnz", "n_inputs", "n_aux", "ingest_s")},
         })
         if not a.no_cpu_baseline:
