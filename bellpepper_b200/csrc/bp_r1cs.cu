@@ -50,6 +50,13 @@ struct bp_cs {
     uint64_t shadow_aux_off = 1u << 16;  // [shadow_aux_off, +n_aux): one array, so that a column word maps to one 32-bit index
     bool cols_in_range = true; // plan: every column index of every row exists (checked when the plan is built)
     bool fat_int_ok = false;   // plan: the fat rows have term words for the integer pass
+    // plan of the pipelined re-check: after aux chunk i has arrived, rows [0, rows[i]) / fat list [0, fat[i]) are ready
+    struct {
+        bool valid = false;
+        uint64_t n_aux = 0, chunk = 0;
+        int n_chunks = 0;
+        uint32_t rows[16], fat[16], gen[16];
+    } chunk_plan;
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
     DevBuf u8_stage;           // packed witness uploads land here before widen_u8
     DevBuf row_meta;           // plan: offset + lengths + RowKind per row (kernels.cuh: meta_pack)
@@ -301,6 +308,7 @@ int select_rows(bp_cs* h, DevBuf& list, uint32_t kind, uint64_t expect) {
 int ensure_plan(bp_cs* h) {
     if (h->plan_valid) return BP_OK;
     h->n_fat_rows = h->n_gen_rows = h->n_plain_rows = 0;
+    h->chunk_plan.valid = false;
     if (h->n_rows) {
         const uint32_t n = (uint32_t)h->n_rows;
         int rc = ensure(h, h->row_meta, ((size_t)n + 1) * 4, 0);
@@ -344,6 +352,52 @@ int ensure_plan(bp_cs* h) {
         if ((rc = ensure(h, h->fat_undecided, std::max<size_t>((size_t)h->n_fat_rows * 4, 4), 0)) != BP_OK) return rc;
     }
     h->plan_valid = true;
+    return BP_OK;
+}
+
+struct MaxU32 {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+// Which rows / fat-list entries are ready after each of the n_chunks aux chunks of `chunk` elements has arrived.
+int ensure_chunk_plan(bp_cs* h, uint64_t chunk, int n_chunks) {
+    auto& cp = h->chunk_plan;
+    if (cp.valid && cp.n_aux == h->n_aux && cp.chunk == chunk && cp.n_chunks == n_chunks) return BP_OK;
+    const uint32_t n = (uint32_t)h->n_rows;
+    const size_t off_small = (((size_t)n * 4) + 255) & ~size_t(255);  // [row_max | bounds 16 | out 48]
+    int rc = ensure(h, h->scratch, off_small + 64 * 4, 0);
+    if (rc != BP_OK) return rc;
+    uint32_t* row_max = (uint32_t*)h->scratch.p;
+    uint32_t* d_bounds = (uint32_t*)((char*)h->scratch.p + off_small);
+    uint32_t* d_out = d_bounds + 16;
+    row_max_aux<<<grid_for(h, (uint64_t)n * 32, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p, n, row_max);
+    size_t tmp_bytes = 0;
+    CU(h, cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, row_max, row_max, MaxU32(), (int)n, h->stream));
+    if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
+    CU(h, cub::DeviceScan::InclusiveScan(h->scan_tmp.p, tmp_bytes, row_max, row_max, MaxU32(), (int)n, h->stream));
+    uint32_t* hb = (uint32_t*)((char*)h->h_pinned_small + 64);  // 16 words of bounds out, 48 words back: needs 256 B
+    for (int i = 0; i < n_chunks; ++i) hb[i] = (uint32_t)std::min<uint64_t>(h->n_aux, (uint64_t)(i + 1) * chunk);
+    CU(h, cudaMemcpyAsync(d_bounds, hb, n_chunks * 4, cudaMemcpyHostToDevice, h->stream));
+    ready_rows<<<1, 32, 0, h->stream>>>(row_max, n, (const uint32_t*)h->fat_rows.p, (uint32_t)h->n_fat_rows, (const uint32_t*)h->gen_rows.p,
+                                        (uint32_t)(h->n_plain_rows ? h->n_gen_rows : 0), d_bounds, (uint32_t)n_chunks, d_out);
+    h->launches += 2;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(hb + 16, d_out, n_chunks * 12, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_chunks; ++i) {
+        cp.rows[i] = hb[16 + 3 * i];
+        cp.fat[i] = hb[16 + 3 * i + 1];
+        cp.gen[i] = hb[16 + 3 * i + 2];
+    }
+    // a value >= bound means "reads an element that has not arrived": the strict comparison in ready_rows is on indices, so
+    // rows reading index bound-1 are ready; after the LAST chunk everything is
+    cp.rows[n_chunks - 1] = n;
+    cp.fat[n_chunks - 1] = (uint32_t)h->n_fat_rows;
+    cp.gen[n_chunks - 1] = (uint32_t)(h->n_plain_rows ? h->n_gen_rows : 0);
+    cp.valid = true;
+    cp.n_aux = h->n_aux;
+    cp.chunk = chunk;
+    cp.n_chunks = n_chunks;
     return BP_OK;
 }
 
@@ -407,7 +461,8 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
         cudaError_t ae = cudaSuccess;
         DISPATCH_FIELD(h, (ae = cudaFuncSetAttribute(check_small<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem)));
         CU(h, ae);
-        DISPATCH_FIELD(h, (check_small<F, true><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef)));
+        DISPATCH_FIELD(h, (check_small<F, true><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, 0u,
+                                                                                             0xffffffffu)));
         const int lgrid = grid_for(h, h->n_gen_rows + (uint64_t)h->sm_count * block, block, 16);
         DISPATCH_FIELD(h, (check_rows<F, true, 0, 4, true><<<lgrid, block, 0, h->stream>>>(
                               m, o, h->fc, (const uint32_t*)h->gen_rows.p, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
@@ -467,7 +522,8 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
                 const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;  // one warp per block of rows
                 const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
                 CU(h, cudaFuncSetAttribute(check_small<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
-                check_small<0, false><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef);
+                check_small<0, false><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, 0u,
+                                                                                       0xffffffffu);
                 h->launches++;
                 const uint32_t* gl = (const uint32_t*)h->gen_rows.p;
                 // the plan's generic rows, plus whatever check_small deferred (normally nothing): grid-stride over both
@@ -532,7 +588,7 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
     h->d_err = (unsigned int*)(h->d_result + 1);
     h->d_ndef = (uint32_t*)(h->d_result + 2);
     if (cudaMemset(h->d_result, 0, 32) != cudaSuccess) return bail(BP_E_CUDA);
-    if (cudaMallocHost(&h->h_pinned_small, 128) != cudaSuccess) return bail(BP_E_OOM);
+    if (cudaMallocHost(&h->h_pinned_small, 512) != cudaSuccess) return bail(BP_E_OOM);
     for (int s = 0; s < kNumStage; ++s) {
         if (cudaMallocHost(&h->h_stage[s], kStageBytes) != cudaSuccess) return bail(BP_E_OOM);
         if (cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
@@ -891,6 +947,95 @@ int bp_cs_first_unsatisfied(bp_cs* h, int64_t* row) {
     CU(h, cudaSetDevice(h->device));
     int rc = launch_check(h, h->d_result, nullptr, nullptr, nullptr);
     if (rc != BP_OK) return rc;
+    long long fb;
+    unsigned int e;
+    if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;
+    if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
+    *row = fb == 0x7fffffffffffffffLL ? -1 : (int64_t)(fb - (long long)h->row_base);
+    return BP_OK;
+}
+
+int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* row) {
+    if (!h || !row || (!aux_u8 && h->n_aux)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    int rc;
+    if (inputs_u8 && (rc = bp_cs_set_range_u8(h, 0, 0, h->n_inputs, inputs_u8)) != BP_OK) return rc;
+    const uint64_t n = h->n_aux;
+    if ((rc = ensure_plan(h)) != BP_OK) return rc;
+    cudaPointerAttributes at;
+    cudaError_t pe = cudaPointerGetAttributes(&at, aux_u8);
+    if (pe != cudaSuccess) (void)cudaGetLastError();
+    const bool dma_able = pe == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+    const bool pipelined = dma_able && n >= (4u << 20) && h->n_plain_rows > 0 && h->variant < 0 && h->kernels_mask == 3 && h->n_rows > 0;
+    if (!pipelined) {
+        if (n && (rc = bp_cs_set_range_u8(h, 1, 0, n, aux_u8)) != BP_OK) return rc;
+        return bp_cs_first_unsatisfied(h, row);
+    }
+    // Pipelined: the copy of aux chunk i+1 (side stream) overlaps the widening of chunk i and the check of the rows that
+    // became ready with it (handle's stream); the full-width kernels take the generic / deferred / undecided rows at the end.
+    const uint64_t chunk = (((n + 15) / 16) + 255) & ~uint64_t(255);
+    const int n_chunks = (int)((n + chunk - 1) / chunk);
+    if ((rc = ensure_chunk_plan(h, chunk, n_chunks)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->u8_stage, (size_t)n, 0)) != BP_OK) return rc;
+    const auto& cp = h->chunk_plan;
+    CsrView m = view(h);
+    CheckOut o{h->d_result, h->d_err, nullptr, nullptr, nullptr};
+    init_result<<<1, 1, 0, h->stream>>>(h->d_result, h->d_err, h->d_ndef);
+    h->launches++;
+    CU(h, cudaFuncSetAttribute(check_small<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
+    CU(h, cudaEventRecord(h->ev_fork, h->stream));
+    CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    const uint32_t n_blocks = (uint32_t)((h->n_rows + kSmallRows - 1) / kSmallRows);
+    uint32_t blk_done = 0, fat_done = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+        const uint64_t off = (uint64_t)i * chunk, len = std::min(chunk, n - off);
+        CU(h, cudaMemcpyAsync((char*)h->u8_stage.p + off, aux_u8 + off, len, cudaMemcpyHostToDevice, h->side_stream));
+        CU(h, cudaEventRecord(h->ev_chunk[i], h->side_stream));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0));
+        widen_u8<<<grid_for(h, 2 * len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len,
+                                                                       (uint4*)((char*)h->aux.p + off * 32), shadow_ptr(h, 1) + off);
+        h->launches++;
+        const uint32_t blk_ready = i == n_chunks - 1 ? n_blocks : cp.rows[i] / kSmallRows;  // whole 64-row blocks only
+        if (blk_ready > blk_done) {
+            const uint32_t nb = blk_ready - blk_done;
+            const int sgrid = (int)std::min<uint64_t>((nb + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
+            check_small<0, false><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, blk_done,
+                                                                                   blk_ready);
+            h->launches++;
+            blk_done = blk_ready;
+        }
+        // fat rows below the last whole block that is ready (their operands have arrived as well)
+        uint32_t fat_ready = cp.fat[i];
+        if (h->fat_int_ok && fat_ready > fat_done) {
+            const uint32_t nf = fat_ready - fat_done;
+            const int igrid = (int)std::min<uint64_t>((nf + 3) / 4, (uint64_t)h->sm_count * 6);
+            DISPATCH_FIELD(h, (check_fat_int<F, false><<<igrid, 128, 0, h->stream>>>(m, o, (const uint32_t*)h->fat_rows.p + fat_done, nf,
+                                                                                    (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+            h->launches++;
+            fat_done = fat_ready;
+        }
+    }
+    CU(h, cudaGetLastError());
+    // leftovers: the plan's generic rows + deferred plain rows; undecided fat rows (or all of them without an integer plan)
+    {
+        const int lgrid = grid_for(h, h->n_gen_rows + (uint64_t)h->sm_count * 128, 128, 16);
+        DISPATCH_FIELD(h, (check_rows<F, false, kVDefault, 6, true><<<lgrid, 128, 0, h->stream>>>(
+                              m, o, h->fc, (const uint32_t*)h->gen_rows.p, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
+        h->launches++;
+        if (h->n_fat_rows) {
+            const int fat_grid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * (uint64_t)h->fat_ctas_per_sm);
+            if (h->fat_int_ok) {
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<std::min(fat_grid, h->sm_count), 128, 0, h->stream>>>(
+                                      m, o, h->fc, (const uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
+            } else {
+                const uint32_t* fat = (const uint32_t*)h->fat_rows.p;
+                DISPATCH_FIELD(h, (check_fat_rows<F, false, kVDefault | kVShadow | kVPark, 5><<<fat_grid, 128, 0, h->stream>>>(m, o, h->fc, fat,
+                                                                                                                    fat + h->n_fat_rows)));
+            }
+            h->launches++;
+        }
+    }
+    CU(h, cudaGetLastError());
     long long fb;
     unsigned int e;
     if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;

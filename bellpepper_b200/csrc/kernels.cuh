@@ -435,6 +435,45 @@ __global__ void build_row_meta(const uint32_t* __restrict__ row_ptr, const uint3
     if (__any_sync(0xffffffffu, oob) && (threadIdx.x & 31u) == 0) atomicOr(counts + 3, 1u);
 }
 
+// ---- plan for the pipelined re-check (bp_cs_recheck_u8): which rows only read aux variables below a given index? ---------
+// row_max[r] = largest aux index row r reads (0 when none); after an inclusive max-scan the rows that are ready once the
+// aux elements [0, bound) have arrived are a PREFIX of the rows (circuits allocate a variable before they constrain it, so
+// the prefix is long); ready_rows finds its length for every chunk boundary.
+__global__ void row_max_aux(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, uint32_t n_rows,
+                            uint32_t* __restrict__ row_max) {
+    const uint32_t lane = threadIdx.x & 31u, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+        const uint32_t k0 = row_ptr[3 * (size_t)row], k1 = row_ptr[3 * (size_t)row + 3];
+        uint32_t mx = 0;
+        for (uint32_t k = k0 + lane; k < k1; k += 32u) {
+            const uint32_t col = cols[k];
+            if ((col & kColAux) && ((col >> kColClsShift) & 7u) != kClsZero) mx = max(mx, col & kColIdxMask);
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) row_max[row] = mx;
+    }
+}
+// out[3*i + 0] = number of leading rows whose aux reads are all below bounds[i]; [1], [2] = how many entries of the
+// (ascending) fat / generic row lists lie below that row.
+__global__ void ready_rows(const uint32_t* __restrict__ prefix_max, uint32_t n_rows, const uint32_t* __restrict__ fat_rows, uint32_t n_fat,
+                           const uint32_t* __restrict__ gen_rows, uint32_t n_gen, const uint32_t* __restrict__ bounds, uint32_t n_bounds,
+                           uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bounds) return;
+    auto lower = [](const uint32_t* a, uint32_t n, uint32_t v) {  // first index with a[idx] >= v
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (a[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const uint32_t rows = lower(prefix_max, n_rows, bounds[i]);
+    out[3 * i] = rows;
+    out[3 * i + 1] = lower(fat_rows, n_fat, rows);
+    out[3 * i + 2] = lower(gen_rows, n_gen, rows);
+}
+
 // ---- K1, plain rows with small operands: 64-bit integer arithmetic on the witness shadows ---------------------------------
 // A warp owns 64 consecutive rows, two per lane.  The block's term words (scols) are brought into shared memory by one TMA
 // bulk copy; they are handled TERM-parallel -- four consecutive words per lane (one 16-byte shared load), one 4-byte
@@ -551,7 +590,7 @@ __device__ __forceinline__ uint32_t small_row_direct(uint32_t row, const CsrView
 // EMIT: also write the canonical A.w, B.w, C.w of every row decided here (F is only used for that).
 template <int F, bool EMIT>
 __global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, CheckOut o, uint32_t* __restrict__ deferred,
-                                                                uint32_t* __restrict__ n_deferred) {
+                                                                uint32_t* __restrict__ n_deferred, uint32_t blk_lo, uint32_t blk_hi) {
     extern __shared__ __align__(16) unsigned char small_smem[];
     constexpr uint32_t kStageWords = kSmallCap + 4u;  // + one group for the prefix value past the last term
     uint32_t(*s_buf)[2][kStageWords] = reinterpret_cast<uint32_t(*)[2][kStageWords]>(small_smem);
@@ -564,9 +603,9 @@ __global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, Check
     }
     __syncwarp();
     uint32_t my_bad = 0xffffffffu;
-    const uint32_t n_blocks = (m.n_rows + kSmallRows - 1u) / kSmallRows;
+    const uint32_t n_blocks = min(blk_hi, (m.n_rows + kSmallRows - 1u) / kSmallRows);  // this launch: blocks [blk_lo, blk_hi)
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t b0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t b0 = blk_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 
     // (volatile loads: issued HERE, one iteration before they are needed, not sunk to their first use)
     auto range_lo = [&](uint32_t b) { return ldg_early(m.row_ptr + 3 * (size_t)kSmallRows * b); };

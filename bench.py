@@ -340,14 +340,20 @@ def main():
             b_aux = w_aux[:, 0].to(torch.uint8).pin_memory()
 
             def step_e2e_packed():
+                if world == 1:  # one call: upload pipelined with the check (rows are checked as their variables arrive)
+                    assert L.bp_cs_recheck_u8(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()),
+                                              ctypes.byref(row)) == 0, L.bp_cs_last_error(h)
+                    return row.value
                 assert L.bp_cs_set_range_u8(h, 0, 0, info["n_inputs"], ctypes.c_void_p(b_in.data_ptr())) == 0, L.bp_cs_last_error(h)
                 assert L.bp_cs_set_range_u8(h, 1, 0, info["n_aux"], ctypes.c_void_p(b_aux.data_ptr())) == 0, L.bp_cs_last_error(h)
                 return finish_step()
 
             e2e_s = time_e2e(step_e2e_packed)
             e2e_h2d = n_vars
-            e2e_what = ("witness as 1 byte per element in pinned host memory -> bp_cs_set_range_u8 (H2D + widen on device) -> check -> "
-                        "result to host; matrices resident (ingested once)")
+            e2e_what = ("witness as 1 byte per element in pinned host memory -> bp_cs_recheck_u8 (chunked H2D, widened on the device, rows "
+                        "checked as their variables arrive) -> result to host; matrices resident (ingested once)" if world == 1 else
+                        "witness as 1 byte per element in pinned host memory -> bp_cs_set_range_u8 (H2D + widen on device) -> check -> "
+                        "all-reduce -> result to host; matrices resident (ingested once)")
         else:
             e2e_s, e2e_h2d = e2e_full_s, n_vars * 32
             e2e_what = "witness (pinned host, 32 B per element) -> bp_cs_set_range -> check -> result to host; matrices resident (ingested once)"

@@ -107,6 +107,12 @@ int bp_cs_counts(bp_cs* cs, uint64_t* n_inputs, uint64_t* n_aux, uint64_t* n_row
  * slice index, test_cs.rs:146-147). */
 int bp_cs_first_unsatisfied(bp_cs* cs, int64_t* row);
 
+/* Re-check with a NEW witness given in the packed form (see bp_cs_alloc_u8): replaces all inputs (inputs_u8 may be NULL to
+ * keep them; otherwise n_inputs bytes including ONE) and all aux values (n_aux bytes), then does which_is_unsatisfied.
+ * The SizedWitness / WitnessCS flow (witness_cs.rs:7-41): same circuit, next witness.  When aux_u8 is pinned host memory the
+ * upload is pipelined with the check: rows are checked as soon as the variables they read have arrived. */
+int bp_cs_recheck_u8(bp_cs* cs, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* row);
+
 /* Same check, asynchronous: enqueue on the handle's stream and leave the result in DEVICE memory as one
  * int64 (first failing GLOBAL row = row_base + local row; INT64_MAX when satisfied) so that a row-sharded
  * multi-GPU caller can min-all-reduce it without a host round trip.  No host synchronisation. */

@@ -166,3 +166,47 @@ def test_blake2s_bit_exact_and_flips(fid, n_bytes):
             assert L.bp_cs_set(h, 1, idx, v.ctypes.data) == 0
             inst.set(True, idx, old)
         assert t.is_satisfied()
+
+
+def test_pipelined_recheck_equals_plain_recheck():
+    """bp_cs_recheck_u8 with a pinned packed witness (upload pipelined with the check) vs upload-then-check, on a chain long
+    enough to take the pipelined path; edits early, late and at chunk boundaries; a non-byte value stays a patch."""
+    import torch
+
+    fid, blocks = 1, 170
+    L = ffi.load()
+    with fixtures.Tcs(fid, device=0, named=False) as t:
+        t.sha256(fixtures.chain_message(blocks))
+        h = ffi.vp(t.handle)
+        n_in, n_aux = t.num_inputs(), t.num_aux()
+        assert n_aux >= (4 << 20)
+        w = np.zeros((n_aux, 4), np.uint64)
+        assert L.bp_cs_witness(h, 1, 0, n_aux, w.ctypes.data) == 0
+        assert not w[:, 1:].any() and int(w[:, 0].max()) <= 1
+        b_aux = torch.from_numpy(w[:, 0].astype(np.uint8)).pin_memory()
+        b_in = torch.ones(n_in, dtype=torch.uint8).pin_memory()
+        row = ctypes.c_int64()
+
+        def pipelined():
+            assert L.bp_cs_recheck_u8(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()), ctypes.byref(row)) == 0, \
+                L.bp_cs_last_error(h)
+            return row.value
+
+        def plain():
+            assert L.bp_cs_set_range_u8(h, 1, 0, n_aux, ctypes.c_void_p(b_aux.data_ptr())) == 0
+            assert L.bp_cs_first_unsatisfied(h, ctypes.byref(row)) == 0
+            return row.value
+
+        assert pipelined() == -1 and plain() == -1
+        chunk = (((n_aux + 15) // 16) + 255) & ~255
+        rng = random.Random(1)
+        for victim in [5, chunk - 1, chunk, 7 * chunk + 3, n_aux - 1, rng.randrange(n_aux), rng.randrange(n_aux)]:
+            old = int(b_aux[victim])
+            b_aux[victim] = 1 - old
+            a, b = pipelined(), plain()
+            assert a == b and a >= 0, (victim, a, b)
+            b_aux[victim] = old
+        assert pipelined() == -1
+        # the last rows of the chain: the final blocks' rows only become ready with the last chunk
+        b_aux[n_aux - 2000] = 1 - int(b_aux[n_aux - 2000])
+        assert pipelined() == plain() > t.num_constraints() - 30000
