@@ -50,6 +50,7 @@ struct bp_cs {
     uint64_t shadow_aux_off = 1u << 16;  // [shadow_aux_off, +n_aux): one array, so that a column word maps to one 32-bit index
     bool cols_in_range = true; // plan: every column index of every row exists (checked when the plan is built)
     bool fat_int_ok = false;   // plan: the fat rows have term words for the integer pass
+    bool wide_valid = true;    // false after a packed upload: inputs/aux are current only where the shadow says "big"
     // plan of the pipelined re-check: after aux chunk i has arrived, rows [0, rows[i]) / fat list [0, fat[i]) are ready
     struct {
         bool valid = false;
@@ -211,6 +212,7 @@ CsrView view(const bp_cs* h) {
     m.aux = (const uint4*)h->aux.p;
     m.shadow = (const uint32_t*)h->shadow.p;
     m.aux_off = (uint32_t)h->shadow_aux_off;
+    m.wide_valid = h->wide_valid ? 1u : 0u;
     m.row_meta = (const uint32_t*)h->row_meta.p;
     m.scols = (const uint32_t*)h->scols.p;
     m.n_rows = (uint32_t)h->n_rows;
@@ -805,11 +807,10 @@ int bp_cs_set(bp_cs* h, int is_aux, uint64_t idx, const uint64_t v[4]) { return 
 static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals) {
     int rc = ensure(h, h->u8_stage, (size_t)n, 0);
     if (rc != BP_OK) return rc;
-    DevBuf& b = is_aux ? h->aux : h->inputs;
+    h->wide_valid = false;  // only the shadows are written (kernels.cuh: ld_witness)
     auto widen = [&](uint64_t off, uint64_t len) {
-        widen_u8<<<grid_for(h, 2 * len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len,
-                                                                       (uint4*)((char*)b.p + (first + off) * 32),
-                                                                       shadow_ptr(h, is_aux) + first + off);
+        widen_u8<<<grid_for(h, len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len,
+                                                                   shadow_ptr(h, is_aux) + first + off);
         h->launches++;
     };
     cudaPointerAttributes at;
@@ -871,6 +872,11 @@ int bp_cs_witness(bp_cs* h, int is_aux, uint64_t first, uint64_t n, uint64_t* ou
                                                    (unsigned long long)n, (unsigned long long)cnt);
     if (!n) return BP_OK;
     const DevBuf& b = is_aux ? h->aux : h->inputs;
+    if (!h->wide_valid) {  // small values live in the shadows only: write their 32-byte form before it is read
+        materialize_wide<<<grid_for(h, 2 * n, 256, 8), 256, 0, h->stream>>>(shadow_ptr(h, is_aux) + first, n, (uint4*)((char*)b.p + first * 32));
+        h->launches++;
+        CU(h, cudaGetLastError());
+    }
     CU(h, cudaMemcpyAsync(out, (const char*)b.p + first * 32, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return BP_OK;
@@ -979,6 +985,8 @@ int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, 
     if ((rc = ensure(h, h->u8_stage, (size_t)n, 0)) != BP_OK) return rc;
     const auto& cp = h->chunk_plan;
     CsrView m = view(h);
+    h->wide_valid = false;
+    m.wide_valid = 0;
     CheckOut o{h->d_result, h->d_err, nullptr, nullptr, nullptr};
     init_result<<<1, 1, 0, h->stream>>>(h->d_result, h->d_err, h->d_ndef);
     h->launches++;
@@ -992,8 +1000,7 @@ int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, 
         CU(h, cudaMemcpyAsync((char*)h->u8_stage.p + off, aux_u8 + off, len, cudaMemcpyHostToDevice, h->side_stream));
         CU(h, cudaEventRecord(h->ev_chunk[i], h->side_stream));
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0));
-        widen_u8<<<grid_for(h, 2 * len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len,
-                                                                       (uint4*)((char*)h->aux.p + off * 32), shadow_ptr(h, 1) + off);
+        widen_u8<<<grid_for(h, len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len, shadow_ptr(h, 1) + off);
         h->launches++;
         const uint32_t blk_ready = i == n_chunks - 1 ? n_blocks : cp.rows[i] / kSmallRows;  // whole 64-row blocks only
         if (blk_ready > blk_done) {
@@ -1159,6 +1166,7 @@ int bp_cs_synth_witness(bp_cs* h, uint64_t seed, uint64_t n_vars, uint64_t n_inp
     CU(h, cudaGetLastError());
     h->n_inputs = n_inputs;
     h->n_aux = n_vars - n_inputs;
+    h->wide_valid = true;   // the whole witness was just written in both forms
     h->plan_valid = false;  // the plan vouches for column ranges
     return BP_OK;
 }

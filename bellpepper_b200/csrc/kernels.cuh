@@ -46,6 +46,7 @@ struct CsrView {
     const uint4* __restrict__ aux;
     const uint32_t* __restrict__ shadow;    // witness shadows (the value when it is < 2^24, else kShadowBig): inputs at
     uint32_t aux_off;                       // [0, n_inputs), aux at [aux_off, aux_off + n_aux)
+    uint32_t wide_valid;                    // 0 after a packed upload: inputs/aux are then current only where the shadow says "big"
     const uint32_t* __restrict__ row_meta;  // plan: per row, see meta_pack
     const uint32_t* __restrict__ scols;     // plan: per term, the word check_small works from (small_word)
     uint32_t n_rows;
@@ -92,6 +93,23 @@ __host__ __device__ __forceinline__ uint32_t shadow_of(const uint32_t* x /*8*/) 
     const uint32_t hi = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
     return (hi == 0u && x[0] < (1u << kSmallBits)) ? x[0] : kShadowBig;
 }
+// A witness element as 8 limbs.  Packed uploads (bp_cs_*_u8) write only the shadows; from then on (wide_valid = 0) the
+// 32-byte arrays are current exactly where the shadow says "big", and a small value is its zero-extended shadow.
+__device__ __forceinline__ void ld_witness(uint32_t* w, const CsrView& m, bool is_aux, uint32_t idx) {
+    if (!m.wide_valid) {
+        const uint32_t s = __ldg(m.shadow + (is_aux ? m.aux_off : 0u) + idx);
+        if (s != kShadowBig) {
+            w[0] = s;
+#pragma unroll
+            for (int i = 1; i < 8; ++i) w[i] = 0;
+            return;
+        }
+    }
+    const uint4* p = (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx;
+    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w;
+    w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+}
 
 __device__ __forceinline__ void ld8(uint32_t* x, const uint4* p) {
     const uint4 lo = __ldg(p), hi = __ldg(p + 1);
@@ -124,7 +142,7 @@ __device__ __forceinline__ void load_term(TermW& t, uint32_t k, bool valid, cons
     const bool is_aux = (col & kColAux) != 0;
     if (idx >= (is_aux ? m.n_aux : m.n_inputs)) { err = 1; return; }
     t.cls = cls;
-    ld8(t.w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx);
+    ld_witness(t.w, m, is_aux, idx);
 }
 
 // Fold term k (already loaded into t) into acc.  RIPPLE = 9: A/B accumulator (plain sums stay below 2^288); 17: the
@@ -884,7 +902,7 @@ __device__ __forceinline__ void fold_lane_slow(uint32_t* acc, uint32_t k0, uint3
         if (!shadow_slow<IS_C>(cls, __ldg(m.shadow + (is_aux ? m.aux_off : 0u) + idx))) continue;
         TermW t;
         t.cls = cls;
-        ld8(t.w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx);
+        ld_witness(t.w, m, is_aux, idx);
         apply_term<F, RIPPLE>(acc, t, k, m, gen, mag);
     }
 }
@@ -1339,18 +1357,16 @@ template <int F> __global__ void validate_canonical(const uint4* __restrict__ v,
     }
 }
 
-// Packed witness upload (bp_cs_alloc_u8 / bp_cs_set_range_u8): element i = bytes[i], widened to the canonical 32-byte form
-// and to its shadow.  Two lanes write one element (16 bytes each) so that a warp stores 512 contiguous bytes.
-__global__ void widen_u8(const uint8_t* __restrict__ bytes, uint64_t n, uint4* __restrict__ out, uint32_t* __restrict__ shadow) {
+// Packed witness upload (bp_cs_alloc_u8 / bp_cs_set_range_u8 / bp_cs_recheck_u8): element i = bytes[i].  Only the shadow is
+// written (the handle's wide_valid flag goes to 0: see ld_witness); the 32-byte element is materialised when someone asks
+// for it (bp_cs_witness / bp_cs_get).
+__global__ void widen_u8(const uint8_t* __restrict__ bytes, uint64_t n, uint32_t* __restrict__ shadow) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) shadow[i] = bytes[i];
+}
+__global__ void materialize_wide(const uint32_t* __restrict__ shadow, uint64_t n, uint4* __restrict__ out) {
     for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < 2 * n; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = j >> 1;
-        const uint32_t b = bytes[i];
-        if (j & 1) {
-            out[j] = make_uint4(0, 0, 0, 0);
-        } else {
-            out[j] = make_uint4(b, 0, 0, 0);
-            shadow[i] = b;
-        }
+        const uint32_t s = shadow[j >> 1];
+        if (s != kShadowBig) out[j] = make_uint4((j & 1) ? 0u : s, 0, 0, 0);
     }
 }
 
@@ -1376,7 +1392,7 @@ __global__ void eval_lc_kernel(const uint32_t* __restrict__ cols, const uint4* _
         ld8(c, coeffs_canonical + 2 * (size_t)k);
         if (!is_canonical<F>(c)) { my_err |= 2; continue; }
         mont_mul<F>(cm, c, kk);
-        ld8(w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx);
+        ld_witness(w, m, is_aux, idx);
         mac_wide(acc, cm, w);
     }
     warp_sum17(acc);
