@@ -495,9 +495,11 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             CU(h, cudaEventRecord(h->ev_fork, h->stream));
             CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         }
-        const bool fat_shadow = !(v & 2);
-        // product-heavy instances (synthetic) park az/bz in shared memory while C is folded
-        const bool park = (v & 4) || (h->variant < 0 && 2 * h->n_gen > h->nnz);
+        // product-heavy instances (synthetic: most terms a full product, witness values full-width): az/bz parked in shared
+        // memory while C is folded; no shadow / integer passes over the fat rows (every gather would be done twice)
+        const bool product_heavy = 2 * h->n_gen > h->nnz;
+        const bool fat_shadow = !(v & 2) && !(h->variant < 0 && product_heavy);
+        const bool park = (v & 4) || (h->variant < 0 && product_heavy);
         if ((h->kernels_mask & 2) && h->n_fat_rows) {
             cudaStream_t fs = h->side_stream;  // joined below: the check is complete on h->stream when the call returns
             const int fgrid_small = std::min(fat_grid, h->sm_count);
