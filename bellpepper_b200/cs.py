@@ -291,6 +291,7 @@ class _Device:
         self._cols: List[int] = []
         self._coeffs: List[int] = []
         self.n_rows = 0
+        self._structure = bytearray()  # serialised LCs for TestConstraintSystem.hash (test_cs.rs:64-115)
 
     def close(self):
         if getattr(self, "h", None):
@@ -320,6 +321,11 @@ class _Device:
             self._lens.append(len(cols))
             self._cols.extend(cols)
             self._coeffs.extend(coeffs)
+            # hash_lc (test_cs.rs:89-115): proc_lc drops zero coefficients; inputs sort before aux, ascending -- the flat order
+            kept = [(col, co) for col, co in zip(cols, coeffs) if co != 0]
+            self._structure += len(kept).to_bytes(8, "big")
+            for col, co in kept:
+                self._structure += (b"A" if col & ffi.COL_AUX else b"I") + (col & 0x7FFFFFFF).to_bytes(8, "big") + co.to_bytes(32, "big")
         self.n_rows += 1
         if len(self._cols) >= self.FLUSH_TERMS:
             self.flush()
@@ -549,6 +555,15 @@ class TestConstraintSystem(_ConstraintSystemBase):
 
     def scalar_aux(self) -> List[int]:
         return self.dev.witness(AUX)
+
+    def hash(self) -> str:
+        """`TestConstraintSystem::hash` (test_cs.rs:214-237): Blake2s over the counts and every constraint's three LCs."""
+        import hashlib
+
+        h = hashlib.blake2s()
+        h.update(self.dev._count[0].to_bytes(8, "big") + self.dev._count[1].to_bytes(8, "big") + self.dev.n_rows.to_bytes(8, "big"))
+        h.update(bytes(self.dev._structure))
+        return h.hexdigest()
 
     def num_constraints(self) -> int:
         return len(self.constraint_paths)

@@ -184,3 +184,27 @@ def test_witness_cs():  # crates/bellpepper/src/util_cs/witness_cs.rs:94-201
     assert w.is_witness_generator() and WitnessCS.is_extensible()
     w2 = WitnessCS.from_assignments(0, [1, 2, 3], [4, 5])
     assert w2.to_assignments() == ([1, 2, 3], [4, 5])
+
+
+def test_structure_hash_equals_oracle():  # test_cs.rs:64-115, 214-237: TestConstraintSystem::hash
+    """Same little circuit through the product's mirror and through the oracle's: identical Blake2s structure fingerprints;
+    a zero coefficient (x - x) is dropped by proc_lc, a changed coefficient changes the hash, witness values do not."""
+    from oracle.fields import FIELDS
+    from oracle import r1cs_py as O
+
+    def build(mod, cs, one, coeff=3):
+        a = cs.alloc("a", lambda: 10)
+        b = cs.alloc_input("b", lambda: 4)
+        c = cs.alloc("c", lambda: 40)
+        cs.enforce("mult", lambda lc: lc + a, lambda lc: lc + b, lambda lc: lc + c)
+        cs.enforce("lin", lambda lc: lc + (coeff, a) + one - one, lambda lc: lc + one, lambda lc: lc + (coeff, a) + b - b)
+        cs.enforce("empty", lambda lc: lc, lambda lc: lc, lambda lc: lc)
+        return cs
+
+    got = build(None, TestConstraintSystem.new(), ONE)
+    want = build(None, O.TestConstraintSystem(FIELDS[0]), O.ONE)
+    assert got.hash() == want.hash()
+    assert build(None, TestConstraintSystem.new(), ONE, coeff=5).hash() != got.hash()
+    h0 = got.hash()
+    got.set("a", 11)
+    assert got.hash() == h0
