@@ -36,7 +36,7 @@ SEED = 0x5962BE3D763D318D
 N_INPUTS = 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one check (all its kernels) from the committed ncu capture of the same
 # workload (profiles/); None where no capture exists.  sha256 x4096 = 8 x the x512 capture (same per-block structure).
-NCU_TRAFFIC = {"sha256_chain_512_pallas": 537_500_000, "sha256_chain_4096_pallas": 4_300_000_000}
+NCU_TRAFFIC = {"sha256_chain_512_pallas": 546_200_000, "sha256_chain_4096_pallas": 4_370_000_000}
 
 WORKLOADS = {
     # name: (kind, field, params) -- BASELINE.json configs
