@@ -963,8 +963,8 @@ int bp_cs_first_unsatisfied(bp_cs* h, int64_t* row) {
     return BP_OK;
 }
 
-int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* row) {
-    if (!h || !row || (!aux_u8 && h->n_aux)) return BP_E_ARG;
+// Core of bp_cs_recheck_u8[_async]: dev_first_bad receives the first failing GLOBAL row (INT64_MAX = satisfied).
+static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, long long* dev_first_bad) {
     CU(h, cudaSetDevice(h->device));
     int rc;
     if (inputs_u8 && (rc = bp_cs_set_range_u8(h, 0, 0, h->n_inputs, inputs_u8)) != BP_OK) return rc;
@@ -977,7 +977,7 @@ int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, 
     const bool pipelined = dma_able && n >= (4u << 20) && h->n_plain_rows > 0 && h->variant < 0 && h->kernels_mask == 3 && h->n_rows > 0;
     if (!pipelined) {
         if (n && (rc = bp_cs_set_range_u8(h, 1, 0, n, aux_u8)) != BP_OK) return rc;
-        return bp_cs_first_unsatisfied(h, row);
+        return launch_check(h, dev_first_bad, nullptr, nullptr, nullptr);
     }
     // Pipelined: the copy of aux chunk i+1 (side stream) overlaps the widening of chunk i and the check of the rows that
     // became ready with it (handle's stream); the full-width kernels take the generic / deferred / undecided rows at the end.
@@ -989,8 +989,8 @@ int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, 
     CsrView m = view(h);
     h->wide_valid = false;
     m.wide_valid = 0;
-    CheckOut o{h->d_result, h->d_err, nullptr, nullptr, nullptr};
-    init_result<<<1, 1, 0, h->stream>>>(h->d_result, h->d_err, h->d_ndef);
+    CheckOut o{dev_first_bad, h->d_err, nullptr, nullptr, nullptr};
+    init_result<<<1, 1, 0, h->stream>>>(dev_first_bad, h->d_err, h->d_ndef);
     h->launches++;
     CU(h, cudaFuncSetAttribute(check_small<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
     CU(h, cudaEventRecord(h->ev_fork, h->stream));
@@ -1045,12 +1045,24 @@ int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, 
         }
     }
     CU(h, cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* row) {
+    if (!h || !row || (!aux_u8 && h->n_aux)) return BP_E_ARG;
+    int rc = recheck_u8(h, inputs_u8, aux_u8, h->d_result);
+    if (rc != BP_OK) return rc;
     long long fb;
     unsigned int e;
     if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;
     if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
     *row = fb == 0x7fffffffffffffffLL ? -1 : (int64_t)(fb - (long long)h->row_base);
     return BP_OK;
+}
+
+int bp_cs_recheck_u8_async(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* dev_result) {
+    if (!h || !dev_result || (!aux_u8 && h->n_aux)) return BP_E_ARG;
+    return recheck_u8(h, inputs_u8, aux_u8, (long long*)dev_result);
 }
 
 int bp_cs_eval_async(bp_cs* h, uint64_t* az, uint64_t* bz, uint64_t* cz) {

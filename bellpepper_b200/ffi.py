@@ -35,6 +35,7 @@ SIGNATURES = {
     "bp_cs_counts": (ctypes.c_int, [vp, u64p, u64p, u64p, u64p]),
     "bp_cs_first_unsatisfied": (ctypes.c_int, [vp, i64p]),
     "bp_cs_recheck_u8": (ctypes.c_int, [vp, vp, vp, i64p]),
+    "bp_cs_recheck_u8_async": (ctypes.c_int, [vp, vp, vp, vp]),
     "bp_cs_check_async": (ctypes.c_int, [vp, vp]),
     "bp_cs_eval": (ctypes.c_int, [vp, vp, vp, vp]),
     "bp_cs_eval_async": (ctypes.c_int, [vp, vp, vp, vp]),

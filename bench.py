@@ -344,16 +344,18 @@ def main():
                     assert L.bp_cs_recheck_u8(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()),
                                               ctypes.byref(row)) == 0, L.bp_cs_last_error(h)
                     return row.value
-                assert L.bp_cs_set_range_u8(h, 0, 0, info["n_inputs"], ctypes.c_void_p(b_in.data_ptr())) == 0, L.bp_cs_last_error(h)
-                assert L.bp_cs_set_range_u8(h, 1, 0, info["n_aux"], ctypes.c_void_p(b_aux.data_ptr())) == 0, L.bp_cs_last_error(h)
-                return finish_step()
+                # row-sharded: every rank uploads the new witness (pipelined with its shard's check), then one min-all-reduce
+                assert L.bp_cs_recheck_u8_async(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()),
+                                                ctypes.c_void_p(result.data_ptr())) == 0, L.bp_cs_last_error(h)
+                reduce_first_unsatisfied(result, world)
+                return int(result.item())
 
             e2e_s = time_e2e(step_e2e_packed)
             e2e_h2d = n_vars
             e2e_what = ("witness as 1 byte per element in pinned host memory -> bp_cs_recheck_u8 (chunked H2D, widened on the device, rows "
                         "checked as their variables arrive) -> result to host; matrices resident (ingested once)" if world == 1 else
-                        "witness as 1 byte per element in pinned host memory -> bp_cs_set_range_u8 (H2D + widen on device) -> check -> "
-                        "all-reduce -> result to host; matrices resident (ingested once)")
+                        "witness as 1 byte per element in pinned host memory on every rank -> bp_cs_recheck_u8_async (chunked H2D pipelined "
+                        "with the shard's check) -> min-all-reduce -> result to host; matrices resident (ingested once)")
         else:
             e2e_s, e2e_h2d = e2e_full_s, n_vars * 32
             e2e_what = "witness (pinned host, 32 B per element) -> bp_cs_set_range -> check -> result to host; matrices resident (ingested once)"

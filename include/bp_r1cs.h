@@ -112,6 +112,9 @@ int bp_cs_first_unsatisfied(bp_cs* cs, int64_t* row);
  * The SizedWitness / WitnessCS flow (witness_cs.rs:7-41): same circuit, next witness.  When aux_u8 is pinned host memory the
  * upload is pipelined with the check: rows are checked as soon as the variables they read have arrived. */
 int bp_cs_recheck_u8(bp_cs* cs, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* row);
+/* Same, leaving the first failing GLOBAL row in DEVICE memory like bp_cs_check_async (row-sharded multi-GPU use: every rank
+ * uploads the new witness, then one min-all-reduce).  The host buffers must stay valid until the stream has consumed them. */
+int bp_cs_recheck_u8_async(bp_cs* cs, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* dev_result);
 
 /* Same check, asynchronous: enqueue on the handle's stream and leave the result in DEVICE memory as one
  * int64 (first failing GLOBAL row = row_base + local row; INT64_MAX when satisfied) so that a row-sharded
