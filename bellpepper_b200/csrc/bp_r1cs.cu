@@ -10,6 +10,8 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -53,11 +55,13 @@ struct bp_cs {
     bool wide_valid = true;    // false after a packed upload: inputs/aux are current only where the shadow says "big"
     // plan of the pipelined re-check: after aux chunk i has arrived, rows [0, rows[i]) / fat list [0, fat[i]) are ready
     struct {
-        bool valid = false;
-        uint64_t n_aux = 0, chunk = 0;
-        int n_chunks = 0;
+        bool valid = false, sparse = false;
+        uint64_t n_aux = 0;
+        int n_pieces = 0;                  // the aux witness arrives as up to 16 pieces [off, off+len), ascending
+        uint64_t off[16], len[16];
         uint32_t rows[16], fat[16], gen[16];
     } chunk_plan;
+    bool sparse_upload = false;  // recheck uploads only the aux chunks this handle's rows read (row-sharded use)
     DevBuf scan_tmp, scratch;  // CUB temp; ad-hoc LC scratch
     DevBuf u8_stage;           // packed witness uploads land here before widen_u8
     DevBuf row_meta;           // plan: offset + lengths + RowKind per row (kernels.cuh: meta_pack)
@@ -361,45 +365,94 @@ struct MaxU32 {
     __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
 };
 
-// Which rows / fat-list entries are ready after each of the n_chunks aux chunks of `chunk` elements has arrived.
-int ensure_chunk_plan(bp_cs* h, uint64_t chunk, int n_chunks) {
+// The pieces a new aux witness is uploaded in (all of it, or with "sparse_upload" only the 2^16-element chunks some row of
+// this handle reads), and which rows / fat-list entries are ready after each piece has arrived.
+int ensure_chunk_plan(bp_cs* h) {
     auto& cp = h->chunk_plan;
-    if (cp.valid && cp.n_aux == h->n_aux && cp.chunk == chunk && cp.n_chunks == n_chunks) return BP_OK;
+    if (cp.valid && cp.n_aux == h->n_aux && cp.sparse == h->sparse_upload) return BP_OK;
+    const uint64_t n_aux = h->n_aux;
     const uint32_t n = (uint32_t)h->n_rows;
     const size_t off_small = (((size_t)n * 4) + 255) & ~size_t(255);  // [row_max | bounds 16 | out 48]
-    int rc = ensure(h, h->scratch, off_small + 64 * 4, 0);
+    const size_t n_need = (size_t)((n_aux + (1u << kNeedChunkLog2) - 1) >> kNeedChunkLog2);
+    int rc = ensure(h, h->scratch, std::max(off_small + 64 * 4, n_need + 256), 0);
     if (rc != BP_OK) return rc;
-    uint32_t* row_max = (uint32_t*)h->scratch.p;
-    uint32_t* d_bounds = (uint32_t*)((char*)h->scratch.p + off_small);
-    uint32_t* d_out = d_bounds + 16;
-    row_max_aux<<<grid_for(h, (uint64_t)n * 32, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p, n, row_max);
-    size_t tmp_bytes = 0;
-    CU(h, cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, row_max, row_max, MaxU32(), (int)n, h->stream));
-    if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
-    CU(h, cub::DeviceScan::InclusiveScan(h->scan_tmp.p, tmp_bytes, row_max, row_max, MaxU32(), (int)n, h->stream));
-    uint32_t* hb = (uint32_t*)((char*)h->h_pinned_small + 64);  // 16 words of bounds out, 48 words back: needs 256 B
-    for (int i = 0; i < n_chunks; ++i) hb[i] = (uint32_t)std::min<uint64_t>(h->n_aux, (uint64_t)(i + 1) * chunk);
-    CU(h, cudaMemcpyAsync(d_bounds, hb, n_chunks * 4, cudaMemcpyHostToDevice, h->stream));
-    ready_rows<<<1, 32, 0, h->stream>>>(row_max, n, (const uint32_t*)h->fat_rows.p, (uint32_t)h->n_fat_rows, (const uint32_t*)h->gen_rows.p,
-                                        (uint32_t)(h->n_plain_rows ? h->n_gen_rows : 0), d_bounds, (uint32_t)n_chunks, d_out);
-    h->launches += 2;
-    CU(h, cudaGetLastError());
-    CU(h, cudaMemcpyAsync(hb + 16, d_out, n_chunks * 12, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < n_chunks; ++i) {
-        cp.rows[i] = hb[16 + 3 * i];
-        cp.fat[i] = hb[16 + 3 * i + 1];
-        cp.gen[i] = hb[16 + 3 * i + 2];
+    // ---- pieces ----
+    std::vector<std::pair<uint64_t, uint64_t>> ranges;  // [begin, end) in elements
+    if (h->sparse_upload && n_need) {
+        uint8_t* d_need = (uint8_t*)h->scratch.p;
+        CU(h, cudaMemsetAsync(d_need, 0, n_need, h->stream));
+        mark_needed_aux<<<grid_for(h, h->nnz, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->cols.p, (size_t)h->nnz, d_need);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        std::vector<uint8_t> need(n_need);
+        CU(h, cudaMemcpyAsync(need.data(), d_need, n_need, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        for (size_t c = 0; c < n_need; ++c) {
+            if (!need[c]) continue;
+            const uint64_t b = (uint64_t)c << kNeedChunkLog2, e = std::min<uint64_t>(n_aux, b + (1ull << kNeedChunkLog2));
+            if (!ranges.empty() && ranges.back().second == b) ranges.back().second = e;
+            else ranges.push_back({b, e});
+        }
+        while (ranges.size() > 16) {  // too many islands: bridge the smallest gap (uploads a little that nobody reads)
+            size_t best = 1;
+            for (size_t i = 2; i < ranges.size(); ++i)
+                if (ranges[i].first - ranges[i - 1].second < ranges[best].first - ranges[best - 1].second) best = i;
+            ranges[best - 1].second = ranges[best].second;
+            ranges.erase(ranges.begin() + best);
+        }
+    } else if (n_aux) {
+        ranges.push_back({0, n_aux});
     }
-    // a value >= bound means "reads an element that has not arrived": the strict comparison in ready_rows is on indices, so
-    // rows reading index bound-1 are ready; after the LAST chunk everything is
-    cp.rows[n_chunks - 1] = n;
-    cp.fat[n_chunks - 1] = (uint32_t)h->n_fat_rows;
-    cp.gen[n_chunks - 1] = (uint32_t)(h->n_plain_rows ? h->n_gen_rows : 0);
+    while (!ranges.empty() && ranges.size() < 16) {  // split the largest range: finer pipelining (pieces of >= 1 Mi elements)
+        size_t big = 0;
+        for (size_t i = 1; i < ranges.size(); ++i)
+            if (ranges[i].second - ranges[i].first > ranges[big].second - ranges[big].first) big = i;
+        const uint64_t b = ranges[big].first, e = ranges[big].second;
+        if (e - b < (2u << 20)) break;
+        const uint64_t mid = (b + (e - b) / 2 + 255) & ~uint64_t(255);
+        ranges[big].second = mid;
+        ranges.insert(ranges.begin() + big + 1, {mid, e});
+    }
+    cp.n_pieces = (int)ranges.size();
+    for (int i = 0; i < cp.n_pieces; ++i) {
+        cp.off[i] = ranges[i].first;
+        cp.len[i] = ranges[i].second - ranges[i].first;
+    }
+    // ---- readiness ----
+    if (cp.n_pieces && n) {
+        uint32_t* row_max = (uint32_t*)h->scratch.p;
+        uint32_t* d_bounds = (uint32_t*)((char*)h->scratch.p + off_small);
+        uint32_t* d_out = d_bounds + 16;
+        row_max_aux<<<grid_for(h, (uint64_t)n * 32, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p, n,
+                                                                                  row_max);
+        size_t tmp_bytes = 0;
+        CU(h, cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, row_max, row_max, MaxU32(), (int)n, h->stream));
+        if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
+        CU(h, cub::DeviceScan::InclusiveScan(h->scan_tmp.p, tmp_bytes, row_max, row_max, MaxU32(), (int)n, h->stream));
+        uint32_t* hb = (uint32_t*)((char*)h->h_pinned_small + 64);  // 16 words of bounds out, 48 words back
+        // rows whose largest aux index is below the end of piece i only read elements of pieces 0..i (or of chunks nobody
+        // uploads because nobody reads them)
+        for (int i = 0; i < cp.n_pieces; ++i) hb[i] = (uint32_t)(cp.off[i] + cp.len[i]);
+        CU(h, cudaMemcpyAsync(d_bounds, hb, cp.n_pieces * 4, cudaMemcpyHostToDevice, h->stream));
+        ready_rows<<<1, 32, 0, h->stream>>>(row_max, n, (const uint32_t*)h->fat_rows.p, (uint32_t)h->n_fat_rows, (const uint32_t*)h->gen_rows.p,
+                                            (uint32_t)(h->n_plain_rows ? h->n_gen_rows : 0), d_bounds, (uint32_t)cp.n_pieces, d_out);
+        h->launches += 2;
+        CU(h, cudaGetLastError());
+        CU(h, cudaMemcpyAsync(hb + 16, d_out, cp.n_pieces * 12, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < cp.n_pieces; ++i) {
+            cp.rows[i] = hb[16 + 3 * i];
+            cp.fat[i] = hb[16 + 3 * i + 1];
+            cp.gen[i] = hb[16 + 3 * i + 2];
+        }
+        // after the LAST piece everything is ready
+        cp.rows[cp.n_pieces - 1] = n;
+        cp.fat[cp.n_pieces - 1] = (uint32_t)h->n_fat_rows;
+        cp.gen[cp.n_pieces - 1] = (uint32_t)(h->n_plain_rows ? h->n_gen_rows : 0);
+    }
     cp.valid = true;
-    cp.n_aux = h->n_aux;
-    cp.chunk = chunk;
-    cp.n_chunks = n_chunks;
+    cp.n_aux = n_aux;
+    cp.sparse = h->sparse_upload;
     return BP_OK;
 }
 
@@ -676,6 +729,10 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
         h->fat_ctas_per_sm = v;
         return BP_OK;
     }
+    if (!std::strcmp(key, "sparse_upload")) {
+        h->sparse_upload = v != 0;
+        return BP_OK;
+    }
     if (!std::strcmp(key, "kernels_mask")) {
         h->kernels_mask = v & 3;
         return BP_OK;
@@ -708,6 +765,16 @@ int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
         int rc = ensure_plan(h);
         if (rc != BP_OK) return rc;
         *v = (int64_t)h->n_terms_kind[key[0] == 'f' ? kRowFat : (key[0] == 'p' ? kRowPlain : kRowGeneric)];
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "recheck_upload_bytes")) {  // bytes one bp_cs_recheck_u8 copies to the device (inputs + aux pieces)
+        CU(h, cudaSetDevice(h->device));
+        int rc = ensure_plan(h);
+        if (rc == BP_OK) rc = ensure_chunk_plan(h);
+        if (rc != BP_OK) return rc;
+        uint64_t b = h->n_inputs;
+        for (int i = 0; i < h->chunk_plan.n_pieces; ++i) b += h->chunk_plan.len[i];
+        *v = (int64_t)b;
         return BP_OK;
     }
     // plain rows / fat rows the last check handed on to the full-width kernels
@@ -981,9 +1048,8 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
     }
     // Pipelined: the copy of aux chunk i+1 (side stream) overlaps the widening of chunk i and the check of the rows that
     // became ready with it (handle's stream); the full-width kernels take the generic / deferred / undecided rows at the end.
-    const uint64_t chunk = (((n + 15) / 16) + 255) & ~uint64_t(255);
-    const int n_chunks = (int)((n + chunk - 1) / chunk);
-    if ((rc = ensure_chunk_plan(h, chunk, n_chunks)) != BP_OK) return rc;
+    if ((rc = ensure_chunk_plan(h)) != BP_OK) return rc;
+    const int n_chunks = h->chunk_plan.n_pieces;
     if ((rc = ensure(h, h->u8_stage, (size_t)n, 0)) != BP_OK) return rc;
     const auto& cp = h->chunk_plan;
     CsrView m = view(h);
@@ -998,7 +1064,7 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
     const uint32_t n_blocks = (uint32_t)((h->n_rows + kSmallRows - 1) / kSmallRows);
     uint32_t blk_done = 0, fat_done = 0;
     for (int i = 0; i < n_chunks; ++i) {
-        const uint64_t off = (uint64_t)i * chunk, len = std::min(chunk, n - off);
+        const uint64_t off = cp.off[i], len = cp.len[i];
         CU(h, cudaMemcpyAsync((char*)h->u8_stage.p + off, aux_u8 + off, len, cudaMemcpyHostToDevice, h->side_stream));
         CU(h, cudaEventRecord(h->ev_chunk[i], h->side_stream));
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0));

@@ -471,6 +471,15 @@ __global__ void row_max_aux(const uint32_t* __restrict__ row_ptr, const uint32_t
         if (lane == 0) row_max[row] = mx;
     }
 }
+// needed[c] = 1 when some row of this handle reads an aux element of chunk c (2^16 elements): a row shard only has to
+// receive those chunks of a new witness (bp_cs_set_option "sparse_upload").
+constexpr uint32_t kNeedChunkLog2 = 16;
+__global__ void mark_needed_aux(const uint32_t* __restrict__ cols, size_t nnz, uint8_t* __restrict__ needed) {
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nnz; k += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t col = cols[k];
+        if ((col & kColAux) && ((col >> kColClsShift) & 7u) != kClsZero) needed[(col & kColIdxMask) >> kNeedChunkLog2] = 1;
+    }
+}
 // out[3*i + 0] = number of leading rows whose aux reads are all below bounds[i]; [1], [2] = how many entries of the
 // (ascending) fat / generic row lists lie below that row.
 __global__ void ready_rows(const uint32_t* __restrict__ prefix_max, uint32_t n_rows, const uint32_t* __restrict__ fat_rows, uint32_t n_fat,

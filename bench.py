@@ -350,12 +350,17 @@ def main():
                 reduce_first_unsatisfied(result, world)
                 return int(result.item())
 
+            if world > 1:  # a row shard only needs the part of the witness its rows read
+                assert L.bp_cs_set_option(h, b"sparse_upload", 1) == 0
             e2e_s = time_e2e(step_e2e_packed)
-            e2e_h2d = n_vars
+            up = ctypes.c_int64()
+            assert L.bp_cs_get_option(h, b"recheck_upload_bytes", ctypes.byref(up)) == 0
+            e2e_h2d = up.value  # this rank's bytes per step
             e2e_what = ("witness as 1 byte per element in pinned host memory -> bp_cs_recheck_u8 (chunked H2D, widened on the device, rows "
                         "checked as their variables arrive) -> result to host; matrices resident (ingested once)" if world == 1 else
-                        "witness as 1 byte per element in pinned host memory on every rank -> bp_cs_recheck_u8_async (chunked H2D pipelined "
-                        "with the shard's check) -> min-all-reduce -> result to host; matrices resident (ingested once)")
+                        "witness as 1 byte per element in pinned host memory on every rank -> bp_cs_recheck_u8_async with sparse_upload "
+                        "(each rank copies only the chunks its row shard reads; chunked H2D pipelined with the shard's check) -> "
+                        "min-all-reduce -> result to host; matrices resident (ingested once); h2d_bytes_per_step is rank 0's")
         else:
             e2e_s, e2e_h2d = e2e_full_s, n_vars * 32
             e2e_what = "witness (pinned host, 32 B per element) -> bp_cs_set_range -> check -> result to host; matrices resident (ingested once)"

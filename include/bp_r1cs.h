@@ -138,7 +138,10 @@ int bp_cs_set_stream(bp_cs* cs, void* cuda_stream);
 int bp_cs_set_row_base(bp_cs* cs, uint64_t row_base);
 /* Block until all enqueued work of this handle is complete. */
 int bp_cs_sync(bp_cs* cs);
-/* Tuning / introspection knobs: "fat_terms" (rows with more terms use the warp-per-row kernel; default 96);
+/* "sparse_upload" (0/1): bp_cs_recheck_u8[_async] uploads only the 2^16-element chunks of the aux witness that some row of
+ * THIS handle reads -- for row shards, whose rows read a fraction of the witness; elements no row of the handle reads keep
+ * their previous values.
+ * Tuning / introspection knobs: "fat_terms" (rows with more terms use the warp-per-row kernel; default 96);
  * "variant" (-1 = default; else bit 0: no small-operand kernel, bit 1: no witness shadows in the warp-per-row kernel,
  * bit 2: park A.w/B.w in shared memory, bit 3: no integer pass over the fat rows -- every variant returns the same
  * results, the parity tests run them all);

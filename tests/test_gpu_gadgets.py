@@ -210,3 +210,58 @@ def test_pipelined_recheck_equals_plain_recheck():
         # the last rows of the chain: the final blocks' rows only become ready with the last chunk
         b_aux[n_aux - 2000] = 1 - int(b_aux[n_aux - 2000])
         assert pipelined() == plain() > t.num_constraints() - 30000
+
+
+def test_sparse_upload_on_row_shards():
+    """Row shards with "sparse_upload": each shard copies only the witness chunks its rows read, and the minimum over the
+    shards still equals the whole system's first failing row."""
+    import torch
+
+    fid, blocks = 1, 170
+    msg = fixtures.chain_message(blocks)
+    L = ffi.load()
+    with fixtures.Tcs(fid, device=0, named=False) as t:
+        t.sha256(msg)
+        h = ffi.vp(t.handle)
+        n_in, n_aux = t.num_inputs(), t.num_aux()
+        w = np.zeros((n_aux, 4), np.uint64)
+        assert L.bp_cs_witness(h, 1, 0, n_aux, w.ctypes.data) == 0
+        b_aux = torch.from_numpy(w[:, 0].astype(np.uint8)).pin_memory()
+        b_in = torch.ones(n_in, dtype=torch.uint8).pin_memory()
+        row = ctypes.c_int64()
+        victims = [n_aux // 3, n_aux - 5000, 2_000_000 + 7]
+        want = []
+        for v in victims:
+            b_aux[v] = 1 - int(b_aux[v])
+            assert L.bp_cs_recheck_u8(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()), ctypes.byref(row)) == 0
+            want.append(row.value)
+            b_aux[v] = 1 - int(b_aux[v])
+        assert all(x >= 0 for x in want)
+    shards = []
+    for b0, b1 in ((0, 60), (60, 120), (120, blocks)):
+        s = fixtures.Tcs(fid, device=0, named=False)
+        _, before = s.sha256(msg, b0, b1)
+        hs = ffi.vp(s.handle)
+        assert L.bp_cs_set_row_base(hs, before) == 0
+        assert L.bp_cs_set_option(hs, b"sparse_upload", 1) == 0
+        up = ctypes.c_int64()
+        assert L.bp_cs_get_option(hs, b"recheck_upload_bytes", ctypes.byref(up)) == 0
+        assert up.value < 0.6 * n_aux  # a third of the blocks (+ the message bits): far less than the whole witness
+        shards.append((s, hs, before))
+    try:
+        for v, expect in zip(victims, want):
+            b_aux[v] = 1 - int(b_aux[v])
+            got = []
+            for s, hs, before in shards:
+                assert L.bp_cs_recheck_u8(hs, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()), ctypes.byref(row)) == 0, \
+                    L.bp_cs_last_error(hs)
+                if row.value >= 0:
+                    got.append(row.value + before)
+            assert min(got) == expect, (v, got, expect)
+            b_aux[v] = 1 - int(b_aux[v])
+        for s, hs, before in shards:
+            assert L.bp_cs_recheck_u8(hs, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()), ctypes.byref(row)) == 0
+            assert row.value == -1
+    finally:
+        for s, _, _ in shards:
+            s.close()
