@@ -292,8 +292,25 @@ def main():
         l0 = launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(a.steps):
-            step_device()
+        if world == 1:
+            for _ in range(a.steps):
+                step_device()
+        else:
+            # consecutive checks are independent: the one-word all-reduce of step k (NCCL's stream) overlaps the kernels of
+            # step k+1; two result words alternate, a word is reused only after its all-reduce has completed
+            results = [result, torch.zeros_like(result)]
+            pending = [None, None]
+            for k in range(a.steps):
+                r = results[k & 1]
+                if pending[k & 1] is not None:
+                    pending[k & 1].wait()
+                rc = L.bp_cs_check_async(h, ctypes.c_void_p(r.data_ptr()))
+                assert rc == 0, L.bp_cs_last_error(h)
+                pending[k & 1] = dist.all_reduce(r, op=dist.ReduceOp.MIN, async_op=True)
+            for w in pending:
+                if w is not None:
+                    w.wait()
+            result = results[(a.steps - 1) & 1]
         e1.record(stream)
         barrier()
         n_launch = launches() - l0
