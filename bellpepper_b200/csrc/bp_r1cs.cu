@@ -873,15 +873,31 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
 int bp_cs_set(bp_cs* h, int is_aux, uint64_t idx, const uint64_t v[4]) { return bp_cs_set_range(h, is_aux, idx, 1, v); }
 
 // bytes -> device staging -> widen_u8 into elements [first, first+n) of the index space (capacity already ensured)
-static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals) {
+// Launch the kernel that turns packed values (one byte each, or one bit each) of the staging buffer into shadows.
+static void launch_widen(bp_cs* h, bool bits, uint64_t stage_elem_off, uint64_t len, uint32_t* shadow_dst) {
+    if (bits) {
+        widen_bits<<<grid_for(h, len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + stage_elem_off / 8, len, shadow_dst);
+    } else {
+        widen_u8<<<grid_for(h, len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + stage_elem_off, len, shadow_dst);
+    }
+    h->launches++;
+}
+
+static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals, bool bits = false) {
+    if (bits) {  // small path only: element offsets inside the staging buffer are those of `vals`
+        const size_t nbytes = (size_t)((n + 7) / 8);
+        int rc = ensure(h, h->u8_stage, nbytes, 0);
+        if (rc != BP_OK) return rc;
+        h->wide_valid = false;
+        if ((rc = upload(h, h->u8_stage.p, vals, nbytes)) != BP_OK) return rc;
+        launch_widen(h, true, 0, n, shadow_ptr(h, is_aux) + first);
+        CU(h, cudaGetLastError());
+        return BP_OK;
+    }
     int rc = ensure(h, h->u8_stage, (size_t)n, 0);
     if (rc != BP_OK) return rc;
     h->wide_valid = false;  // only the shadows are written (kernels.cuh: ld_witness)
-    auto widen = [&](uint64_t off, uint64_t len) {
-        widen_u8<<<grid_for(h, len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len,
-                                                                   shadow_ptr(h, is_aux) + first + off);
-        h->launches++;
-    };
+    auto widen = [&](uint64_t off, uint64_t len) { launch_widen(h, false, off, len, shadow_ptr(h, is_aux) + first + off); };
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, vals);
     if (e != cudaSuccess) (void)cudaGetLastError();
@@ -931,6 +947,16 @@ int bp_cs_set_range_u8(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const u
                                                    (unsigned long long)n, (unsigned long long)cnt);
     if (!n) return BP_OK;
     return widen_into(h, is_aux, first, n, vals);
+}
+
+int bp_cs_set_range_bits(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* bits) {
+    if (!h || (!bits && n)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
+    if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "set_range_bits [%llu,+%llu) exceeds %llu", (unsigned long long)first,
+                                                   (unsigned long long)n, (unsigned long long)cnt);
+    if (!n) return BP_OK;
+    return widen_into(h, is_aux, first, n, bits, true);
 }
 
 int bp_cs_witness(bp_cs* h, int is_aux, uint64_t first, uint64_t n, uint64_t* out) {
@@ -1031,10 +1057,10 @@ int bp_cs_first_unsatisfied(bp_cs* h, int64_t* row) {
 }
 
 // Core of bp_cs_recheck_u8[_async]: dev_first_bad receives the first failing GLOBAL row (INT64_MAX = satisfied).
-static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, long long* dev_first_bad) {
+static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, long long* dev_first_bad, bool bits = false) {
     CU(h, cudaSetDevice(h->device));
     int rc;
-    if (inputs_u8 && (rc = bp_cs_set_range_u8(h, 0, 0, h->n_inputs, inputs_u8)) != BP_OK) return rc;
+    if (inputs_u8 && (rc = (bits ? bp_cs_set_range_bits : bp_cs_set_range_u8)(h, 0, 0, h->n_inputs, inputs_u8)) != BP_OK) return rc;
     const uint64_t n = h->n_aux;
     if ((rc = ensure_plan(h)) != BP_OK) return rc;
     cudaPointerAttributes at;
@@ -1043,7 +1069,7 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
     const bool dma_able = pe == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
     const bool pipelined = dma_able && n >= (4u << 20) && h->n_plain_rows > 0 && h->variant < 0 && h->kernels_mask == 3 && h->n_rows > 0;
     if (!pipelined) {
-        if (n && (rc = bp_cs_set_range_u8(h, 1, 0, n, aux_u8)) != BP_OK) return rc;
+        if (n && (rc = (bits ? bp_cs_set_range_bits : bp_cs_set_range_u8)(h, 1, 0, n, aux_u8)) != BP_OK) return rc;
         return launch_check(h, dev_first_bad, nullptr, nullptr, nullptr);
     }
     // Pipelined: the copy of aux chunk i+1 (side stream) overlaps the widening of chunk i and the check of the rows that
@@ -1064,12 +1090,12 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
     const uint32_t n_blocks = (uint32_t)((h->n_rows + kSmallRows - 1) / kSmallRows);
     uint32_t blk_done = 0, fat_done = 0;
     for (int i = 0; i < n_chunks; ++i) {
-        const uint64_t off = cp.off[i], len = cp.len[i];
-        CU(h, cudaMemcpyAsync((char*)h->u8_stage.p + off, aux_u8 + off, len, cudaMemcpyHostToDevice, h->side_stream));
+        const uint64_t off = cp.off[i], len = cp.len[i];  // (piece offsets are multiples of 256 elements: whole bytes in either form)
+        const uint64_t boff = bits ? off / 8 : off, blen = bits ? (len + 7) / 8 : len;
+        CU(h, cudaMemcpyAsync((char*)h->u8_stage.p + boff, aux_u8 + boff, blen, cudaMemcpyHostToDevice, h->side_stream));
         CU(h, cudaEventRecord(h->ev_chunk[i], h->side_stream));
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[i], 0));
-        widen_u8<<<grid_for(h, len, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->u8_stage.p + off, len, shadow_ptr(h, 1) + off);
-        h->launches++;
+        launch_widen(h, bits, off, len, shadow_ptr(h, 1) + off);
         const uint32_t blk_ready = i == n_chunks - 1 ? n_blocks : cp.rows[i] / kSmallRows;  // whole 64-row blocks only
         if (blk_ready > blk_done) {
             const uint32_t nb = blk_ready - blk_done;
@@ -1129,6 +1155,23 @@ int bp_cs_recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, 
 int bp_cs_recheck_u8_async(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* dev_result) {
     if (!h || !dev_result || (!aux_u8 && h->n_aux)) return BP_E_ARG;
     return recheck_u8(h, inputs_u8, aux_u8, (long long*)dev_result);
+}
+
+int bp_cs_recheck_bits(bp_cs* h, const uint8_t* inputs_bits, const uint8_t* aux_bits, int64_t* row) {
+    if (!h || !row || (!aux_bits && h->n_aux)) return BP_E_ARG;
+    int rc = recheck_u8(h, inputs_bits, aux_bits, h->d_result, true);
+    if (rc != BP_OK) return rc;
+    long long fb;
+    unsigned int e;
+    if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;
+    if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
+    *row = fb == 0x7fffffffffffffffLL ? -1 : (int64_t)(fb - (long long)h->row_base);
+    return BP_OK;
+}
+
+int bp_cs_recheck_bits_async(bp_cs* h, const uint8_t* inputs_bits, const uint8_t* aux_bits, int64_t* dev_result) {
+    if (!h || !dev_result || (!aux_bits && h->n_aux)) return BP_E_ARG;
+    return recheck_u8(h, inputs_bits, aux_bits, (long long*)dev_result, true);
 }
 
 int bp_cs_eval_async(bp_cs* h, uint64_t* az, uint64_t* bz, uint64_t* cz) {

@@ -1372,6 +1372,12 @@ template <int F> __global__ void validate_canonical(const uint4* __restrict__ v,
 __global__ void widen_u8(const uint8_t* __restrict__ bytes, uint64_t n, uint32_t* __restrict__ shadow) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) shadow[i] = bytes[i];
 }
+// Same for the 1-bit-per-value form (bp_cs_set_range_bits / bp_cs_recheck_bits): element i = bit i of the byte string,
+// least significant bit of a byte first.
+__global__ void widen_bits(const uint8_t* __restrict__ bytes, uint64_t n, uint32_t* __restrict__ shadow) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        shadow[i] = (bytes[i >> 3] >> (i & 7u)) & 1u;
+}
 __global__ void materialize_wide(const uint32_t* __restrict__ shadow, uint64_t n, uint4* __restrict__ out) {
     for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < 2 * n; j += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t s = shadow[j >> 1];

@@ -36,6 +36,9 @@ SIGNATURES = {
     "bp_cs_first_unsatisfied": (ctypes.c_int, [vp, i64p]),
     "bp_cs_recheck_u8": (ctypes.c_int, [vp, vp, vp, i64p]),
     "bp_cs_recheck_u8_async": (ctypes.c_int, [vp, vp, vp, vp]),
+    "bp_cs_set_range_bits": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp]),
+    "bp_cs_recheck_bits": (ctypes.c_int, [vp, vp, vp, i64p]),
+    "bp_cs_recheck_bits_async": (ctypes.c_int, [vp, vp, vp, vp]),
     "bp_cs_check_async": (ctypes.c_int, [vp, vp]),
     "bp_cs_eval": (ctypes.c_int, [vp, vp, vp, vp]),
     "bp_cs_eval_async": (ctypes.c_int, [vp, vp, vp, vp]),

@@ -352,32 +352,45 @@ def main():
         e2e_full_s = time_e2e(step_e2e_full)
         packable = bool((w_in[:, 1:] == 0).all() and (w_aux[:, 1:] == 0).all() and (w_in[:, 0] >= 0).all() and (w_in[:, 0] < 256).all()
                         and (w_aux[:, 0] >= 0).all() and (w_aux[:, 0] < 256).all())
+        e2e_u8 = None
         if packable:
             b_in = w_in[:, 0].to(torch.uint8).pin_memory()
             b_aux = w_aux[:, 0].to(torch.uint8).pin_memory()
-
-            def step_e2e_packed():
-                if world == 1:  # one call: upload pipelined with the check (rows are checked as their variables arrive)
-                    assert L.bp_cs_recheck_u8(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()),
-                                              ctypes.byref(row)) == 0, L.bp_cs_last_error(h)
-                    return row.value
-                # row-sharded: every rank uploads the new witness (pipelined with its shard's check), then one min-all-reduce
-                assert L.bp_cs_recheck_u8_async(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()),
-                                                ctypes.c_void_p(result.data_ptr())) == 0, L.bp_cs_last_error(h)
-                reduce_first_unsatisfied(result, world)
-                return int(result.item())
-
             if world > 1:  # a row shard only needs the part of the witness its rows read
                 assert L.bp_cs_set_option(h, b"sparse_upload", 1) == 0
-            e2e_s = time_e2e(step_e2e_packed)
+            all_bits = bool((b_in <= 1).all() and (b_aux <= 1).all())
+
+            def make_step(fn_sync, fn_async, src_in, src_aux):
+                def step():
+                    if world == 1:  # one call: upload pipelined with the check (rows are checked as their variables arrive)
+                        assert fn_sync(h, ctypes.c_void_p(src_in.data_ptr()), ctypes.c_void_p(src_aux.data_ptr()), ctypes.byref(row)) == 0, \
+                            L.bp_cs_last_error(h)
+                        return row.value
+                    # row-sharded: every rank uploads what its shard reads (pipelined with its check), then one min-all-reduce
+                    assert fn_async(h, ctypes.c_void_p(src_in.data_ptr()), ctypes.c_void_p(src_aux.data_ptr()),
+                                    ctypes.c_void_p(result.data_ptr())) == 0, L.bp_cs_last_error(h)
+                    reduce_first_unsatisfied(result, world)
+                    return int(result.item())
+                return step
+
             up = ctypes.c_int64()
+            e2e_u8_s = time_e2e(make_step(L.bp_cs_recheck_u8, L.bp_cs_recheck_u8_async, b_in, b_aux))
             assert L.bp_cs_get_option(h, b"recheck_upload_bytes", ctypes.byref(up)) == 0
-            e2e_h2d = up.value  # this rank's bytes per step
-            e2e_what = ("witness as 1 byte per element in pinned host memory -> bp_cs_recheck_u8 (chunked H2D, widened on the device, rows "
-                        "checked as their variables arrive) -> result to host; matrices resident (ingested once)" if world == 1 else
-                        "witness as 1 byte per element in pinned host memory on every rank -> bp_cs_recheck_u8_async with sparse_upload "
-                        "(each rank copies only the chunks its row shard reads; chunked H2D pipelined with the shard's check) -> "
-                        "min-all-reduce -> result to host; matrices resident (ingested once); h2d_bytes_per_step is rank 0's")
+            how = ("chunked H2D, widened into the witness shadows on the device, rows checked as their variables arrive"
+                   + ("; each rank copies only the chunks its row shard reads (sparse_upload), then one min-all-reduce; bytes are rank 0's"
+                      if world > 1 else ""))
+            e2e_u8 = {"ms_per_step": e2e_u8_s * 1e3, "h2d_bytes_per_step": up.value,
+                      "what": "witness as 1 BYTE per value in pinned host memory -> bp_cs_recheck_u8: " + how}
+            if all_bits:
+                import numpy as np
+
+                p_in = torch.from_numpy(np.packbits(b_in.numpy(), bitorder="little")).pin_memory()
+                p_aux = torch.from_numpy(np.packbits(b_aux.numpy(), bitorder="little")).pin_memory()
+                e2e_s = time_e2e(make_step(L.bp_cs_recheck_bits, L.bp_cs_recheck_bits_async, p_in, p_aux))
+                e2e_h2d = (up.value + 7) // 8
+                e2e_what = "witness as 1 BIT per value (every value is 0 or 1) in pinned host memory -> bp_cs_recheck_bits: " + how
+            else:
+                e2e_s, e2e_h2d, e2e_what = e2e_u8_s, up.value, e2e_u8["what"]
         else:
             e2e_s, e2e_h2d = e2e_full_s, n_vars * 32
             e2e_what = "witness (pinned host, 32 B per element) -> bp_cs_set_range -> check -> result to host; matrices resident (ingested once)"
@@ -425,10 +438,14 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / a.steps
-    t_ms = torch.tensor([ms_step, e2e_s * 1e3, e2e_full_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    t_ms = torch.tensor([ms_step, e2e_s * 1e3, e2e_full_s * 1e3, e2e_u8["ms_per_step"] if e2e_u8 else 0.0], dtype=torch.float64,
+                        device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_step, e2e_ms, e2e_full_ms = float(t_ms[0]), float(t_ms[1]), float(t_ms[2])
+    if e2e_u8:
+        e2e_u8["ms_per_step"] = float(t_ms[3])
+        e2e_u8["value"] = info.get("rows_total", info["rows"]) / (float(t_ms[3]) * 1e-3)
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
@@ -455,6 +472,7 @@ def main():
             "ms_per_step": ms_step,
             "e2e": {"value": n_rows_total / (e2e_ms * 1e-3), "unit": "constraints/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": 12 if world == 1 else 8, "what": e2e_what,
+                    "packed_u8": e2e_u8,
                     "full_width": {"value": n_rows_total / (e2e_full_ms * 1e-3), "ms_per_step": e2e_full_ms, "h2d_bytes_per_step": n_vars * 32,
                                    "what": "same with canonical 32-byte elements through bp_cs_set_range"}},
             "gpu_launches": n_launch,

@@ -116,6 +116,13 @@ int bp_cs_recheck_u8(bp_cs* cs, const uint8_t* inputs_u8, const uint8_t* aux_u8,
  * uploads the new witness, then one min-all-reduce).  The host buffers must stay valid until the stream has consumed them. */
 int bp_cs_recheck_u8_async(bp_cs* cs, const uint8_t* inputs_u8, const uint8_t* aux_u8, int64_t* dev_result);
 
+/* The densest form, for witnesses made of bits only (Boolean / AllocatedBit values: what sha256, blake2s, uint32 circuits
+ * allocate): value i = bit i of the byte string, least significant bit of a byte first (the gadgets' own little-endian bit
+ * order, boolean.rs:307-366 / blake2s.rs:520).  A value that is not 0 or 1 is patched afterwards with bp_cs_set. */
+int bp_cs_set_range_bits(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, const uint8_t* bits);
+int bp_cs_recheck_bits(bp_cs* cs, const uint8_t* inputs_bits, const uint8_t* aux_bits, int64_t* row);
+int bp_cs_recheck_bits_async(bp_cs* cs, const uint8_t* inputs_bits, const uint8_t* aux_bits, int64_t* dev_result);
+
 /* Same check, asynchronous: enqueue on the handle's stream and leave the result in DEVICE memory as one
  * int64 (first failing GLOBAL row = row_base + local row; INT64_MAX when satisfied) so that a row-sharded
  * multi-GPU caller can min-all-reduce it without a host round trip.  No host synchronisation. */

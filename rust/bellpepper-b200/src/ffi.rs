@@ -36,6 +36,9 @@ extern "C" {
     pub fn bp_cs_first_unsatisfied(cs: *mut bp_cs, row: *mut i64) -> c_int;
     pub fn bp_cs_recheck_u8(cs: *mut bp_cs, inputs_u8: *const u8, aux_u8: *const u8, row: *mut i64) -> c_int;
     pub fn bp_cs_recheck_u8_async(cs: *mut bp_cs, inputs_u8: *const u8, aux_u8: *const u8, dev_result: *mut i64) -> c_int;
+    pub fn bp_cs_set_range_bits(cs: *mut bp_cs, is_aux: c_int, first: u64, n: u64, bits: *const u8) -> c_int;
+    pub fn bp_cs_recheck_bits(cs: *mut bp_cs, inputs_bits: *const u8, aux_bits: *const u8, row: *mut i64) -> c_int;
+    pub fn bp_cs_recheck_bits_async(cs: *mut bp_cs, inputs_bits: *const u8, aux_bits: *const u8, dev_result: *mut i64) -> c_int;
     pub fn bp_cs_check_async(cs: *mut bp_cs, dev_result: *mut i64) -> c_int;
     pub fn bp_cs_eval(cs: *mut bp_cs, az: *mut u64, bz: *mut u64, cz: *mut u64) -> c_int;
     pub fn bp_cs_eval_async(cs: *mut bp_cs, dev_az: *mut u64, dev_bz: *mut u64, dev_cz: *mut u64) -> c_int;

@@ -265,3 +265,45 @@ def test_sparse_upload_on_row_shards():
     finally:
         for s, _, _ in shards:
             s.close()
+
+
+def test_bit_packed_recheck_equals_byte_packed():
+    """bp_cs_recheck_bits / bp_cs_set_range_bits (1 bit per value) vs the byte-packed calls: same verdicts, pipelined and not."""
+    import torch
+
+    fid, blocks = 1, 170
+    L = ffi.load()
+    with fixtures.Tcs(fid, device=0, named=False) as t:
+        t.sha256(fixtures.chain_message(blocks))
+        h = ffi.vp(t.handle)
+        n_in, n_aux = t.num_inputs(), t.num_aux()
+        w = np.zeros((n_aux, 4), np.uint64)
+        assert L.bp_cs_witness(h, 1, 0, n_aux, w.ctypes.data) == 0
+        vals = w[:, 0].astype(np.uint8)
+        b_in = torch.ones(n_in, dtype=torch.uint8).pin_memory()
+        p_in = torch.from_numpy(np.packbits(b_in.numpy(), bitorder="little")).pin_memory()
+        row = ctypes.c_int64()
+        rng = random.Random(3)
+        for victim in [None, 11, n_aux - 1, rng.randrange(n_aux), (n_aux // 16 + 255) // 256 * 256]:
+            cur = vals.copy()
+            if victim is not None:
+                cur[victim] ^= 1
+            b_aux = torch.from_numpy(cur).pin_memory()
+            p_aux = torch.from_numpy(np.packbits(cur, bitorder="little")).pin_memory()
+            assert L.bp_cs_recheck_u8(h, ctypes.c_void_p(b_in.data_ptr()), ctypes.c_void_p(b_aux.data_ptr()), ctypes.byref(row)) == 0
+            want = row.value
+            assert (want == -1) == (victim is None)
+            assert L.bp_cs_recheck_bits(h, ctypes.c_void_p(p_in.data_ptr()), ctypes.c_void_p(p_aux.data_ptr()), ctypes.byref(row)) == 0, \
+                L.bp_cs_last_error(h)
+            assert row.value == want
+            # not pipelined: pageable source, and a sub-range that does not start on a byte boundary of the whole witness
+            pageable = np.packbits(cur, bitorder="little")
+            assert L.bp_cs_recheck_bits(h, p_in.numpy().ctypes.data, pageable.ctypes.data, ctypes.byref(row)) == 0
+            assert row.value == want
+            first, n = 1003, 70001
+            sub = np.packbits(cur[first: first + n], bitorder="little")
+            assert L.bp_cs_set_range_bits(h, 1, first, n, sub.ctypes.data) == 0
+            assert L.bp_cs_first_unsatisfied(h, ctypes.byref(row)) == 0 and row.value == want
+            back = np.zeros((n, 4), np.uint64)
+            assert L.bp_cs_witness(h, 1, first, n, back.ctypes.data) == 0
+            assert (back[:, 0] == cur[first: first + n]).all() and not back[:, 1:].any()
