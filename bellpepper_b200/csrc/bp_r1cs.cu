@@ -57,6 +57,7 @@ struct bp_cs {
     struct {
         bool valid = false, sparse = false;
         uint64_t n_aux = 0;
+        int max_pieces = 16;
         int n_pieces = 0;                  // the aux witness arrives as up to 16 pieces [off, off+len), ascending
         uint64_t off[16], len[16];
         uint32_t rows[16], fat[16], gen[16];
@@ -367,9 +368,10 @@ struct MaxU32 {
 
 // The pieces a new aux witness is uploaded in (all of it, or with "sparse_upload" only the 2^16-element chunks some row of
 // this handle reads), and which rows / fat-list entries are ready after each piece has arrived.
-int ensure_chunk_plan(bp_cs* h) {
+int ensure_chunk_plan(bp_cs* h, int max_pieces = 16) {
     auto& cp = h->chunk_plan;
-    if (cp.valid && cp.n_aux == h->n_aux && cp.sparse == h->sparse_upload) return BP_OK;
+    max_pieces = std::max(1, std::min(16, max_pieces));
+    if (cp.valid && cp.n_aux == h->n_aux && cp.sparse == h->sparse_upload && cp.max_pieces == max_pieces) return BP_OK;
     const uint64_t n_aux = h->n_aux;
     const uint32_t n = (uint32_t)h->n_rows;
     const size_t off_small = (((size_t)n * 4) + 255) & ~size_t(255);  // [row_max | bounds 16 | out 48]
@@ -393,7 +395,7 @@ int ensure_chunk_plan(bp_cs* h) {
             if (!ranges.empty() && ranges.back().second == b) ranges.back().second = e;
             else ranges.push_back({b, e});
         }
-        while (ranges.size() > 16) {  // too many islands: bridge the smallest gap (uploads a little that nobody reads)
+        while ((int)ranges.size() > max_pieces) {  // too many islands: bridge the smallest gap (uploads a little that nobody reads)
             size_t best = 1;
             for (size_t i = 2; i < ranges.size(); ++i)
                 if (ranges[i].first - ranges[i - 1].second < ranges[best].first - ranges[best - 1].second) best = i;
@@ -403,7 +405,7 @@ int ensure_chunk_plan(bp_cs* h) {
     } else if (n_aux) {
         ranges.push_back({0, n_aux});
     }
-    while (!ranges.empty() && ranges.size() < 16) {  // split the largest range: finer pipelining (pieces of >= 1 Mi elements)
+    while (!ranges.empty() && (int)ranges.size() < max_pieces) {  // split the largest range: finer pipelining (pieces of >= 1 Mi elements)
         size_t big = 0;
         for (size_t i = 1; i < ranges.size(); ++i)
             if (ranges[i].second - ranges[i].first > ranges[big].second - ranges[big].first) big = i;
@@ -453,6 +455,7 @@ int ensure_chunk_plan(bp_cs* h) {
     cp.valid = true;
     cp.n_aux = n_aux;
     cp.sparse = h->sparse_upload;
+    cp.max_pieces = max_pieces;
     return BP_OK;
 }
 
@@ -1067,14 +1070,33 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
     cudaError_t pe = cudaPointerGetAttributes(&at, aux_u8);
     if (pe != cudaSuccess) (void)cudaGetLastError();
     const bool dma_able = pe == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
-    const bool pipelined = dma_able && n >= (4u << 20) && h->n_plain_rows > 0 && h->variant < 0 && h->kernels_mask == 3 && h->n_rows > 0;
+    // pipelining pays when the copy is long next to the check (>= 4 MB here; the 1-bit form of a 10^8-variable witness is a
+    // 0.25 ms copy: cheaper to finish it and run the check with its thin / fat kernels side by side)
+    const uint64_t xfer = bits ? n / 8 : n;
+    const bool pipelined = dma_able && xfer >= (4u << 20) * (bits ? 8u : 1u) && h->n_plain_rows > 0 && h->variant < 0 && h->kernels_mask == 3 &&
+                           h->n_rows > 0;
     if (!pipelined) {
-        if (n && (rc = (bits ? bp_cs_set_range_bits : bp_cs_set_range_u8)(h, 1, 0, n, aux_u8)) != BP_OK) return rc;
+        if (n && h->sparse_upload && h->n_rows) {  // only the chunks this handle's rows read, then the ordinary check
+            if ((rc = ensure_chunk_plan(h, 16)) != BP_OK) return rc;
+            if ((rc = ensure(h, h->u8_stage, (size_t)n, 0)) != BP_OK) return rc;
+            h->wide_valid = false;
+            for (int i = 0; i < h->chunk_plan.n_pieces; ++i) {
+                const uint64_t off = h->chunk_plan.off[i], len = h->chunk_plan.len[i];
+                const uint64_t boff = bits ? off / 8 : off, blen = bits ? (len + 7) / 8 : len;
+                if ((rc = upload(h, (char*)h->u8_stage.p + boff, aux_u8 + boff, (size_t)blen)) != BP_OK) return rc;
+                launch_widen(h, bits, off, len, shadow_ptr(h, 1) + off);
+            }
+            CU(h, cudaGetLastError());
+        } else if (n && (rc = (bits ? bp_cs_set_range_bits : bp_cs_set_range_u8)(h, 1, 0, n, aux_u8)) != BP_OK) {
+            return rc;
+        }
         return launch_check(h, dev_first_bad, nullptr, nullptr, nullptr);
     }
     // Pipelined: the copy of aux chunk i+1 (side stream) overlaps the widening of chunk i and the check of the rows that
     // became ready with it (handle's stream); the full-width kernels take the generic / deferred / undecided rows at the end.
-    if ((rc = ensure_chunk_plan(h)) != BP_OK) return rc;
+    // Pieces of >= 4 MB of transfer (~75 us of PCIe): finer pieces only add launches and tails once the copy is shorter than
+    // the check (the 1-bit form of a 10^8-variable witness is 14 MB: three pieces; its 1-byte form 109 MB: sixteen).
+    if ((rc = ensure_chunk_plan(h, (int)std::min<uint64_t>(16, std::max<uint64_t>(1, xfer >> 22)))) != BP_OK) return rc;
     const int n_chunks = h->chunk_plan.n_pieces;
     if ((rc = ensure(h, h->u8_stage, (size_t)n, 0)) != BP_OK) return rc;
     const auto& cp = h->chunk_plan;
