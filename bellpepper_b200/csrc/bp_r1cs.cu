@@ -1,7 +1,8 @@
 // libbp_r1cs.so -- C ABI (include/bp_r1cs.h) over the CUDA kernels in kernels.cuh.
 //
-// Host-side responsibilities: device buffer growth, pinned staging for H2D of enforce/alloc batches,
-// ingest conversion launches, result read-back.  No evaluation ever happens on the CPU.
+// Host-side responsibilities: device buffer growth, pinned staging for H2D of enforce/alloc batches, ingest conversion
+// launches, the plan (row kinds, term words, row lists, readiness of rows for pipelined uploads), the choice and order of
+// the check kernels (two streams, fork/join), result read-back.  No evaluation ever happens on the CPU.
 #include "../../include/bp_r1cs.h"
 
 #include <cuda_runtime.h>

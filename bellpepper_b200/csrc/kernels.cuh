@@ -1,29 +1,35 @@
 // CUDA kernels of the R1CS evaluation engine (sm_100a).  DESIGN.md has the layout and the per-kernel rooflines.
 //
-//   K1 check_rows<F,false> / check_fat_rows<F,false>   which_is_unsatisfied      test_cs.rs:239-253 (+ eval_lc :137-155)
-//   K2 check_rows<F,true>  / check_fat_rows<F,true>    batched LinearCombination::eval   lc.rs:245-267
-//   K3 classify_lcs<F> + convert_terms<F>              canonical coefficient -> device-internal form + class
-//      validate_canonical<F>                           value < p check for witness uploads
-//   K5 synth_*                                         synthetic instance generator (measurement fixture)
-//      eval_lc_kernel<F>                               one ad-hoc LinearCombination::eval
+//   K1  which_is_unsatisfied (test_cs.rs:239-253 + eval_lc :137-155), one check =
+//         check_small            plain rows whose operands are small: 64-bit integer arithmetic on the witness shadows
+//         check_rows<LIST>       generic rows + rows check_small deferred: full-width lazy-reduction arithmetic, thread per row
+//         check_fat_int          fat rows (> fat_terms terms): exact integers from per-lane buckets, warp per row
+//         check_fat_rows         fat rows check_fat_int left undecided: full-width, warp per row
+//   K2  batched LinearCombination::eval (lc.rs:245-267): the same four kernels with EMIT = true
+//   K3  classify_lcs<F> + convert_terms<F>      ingest: canonical coefficient -> class + device-internal form (+ exponents)
+//       validate_canonical<F>, widen_u8/_bits   witness upload: value < p, shadow; packed forms -> shadows
+//       build_row_meta, build_fat_words, ...    the plan: row kinds, term words of the integer kernels, readiness of rows
+//   K5  synth_*                                 synthetic instance generator (measurement fixture)
+//       eval_lc_kernel<F>                       one ad-hoc LinearCombination::eval
 //
 // Device layout (per handle == per row shard):
 //   row_ptr : u32[3N+1]   LC offsets; LC 3i, 3i+1, 3i+2 are A_i, B_i, C_i; a row's terms are contiguous
 //   cols    : u32[nnz]    bit 31 = aux index space, bits 30..28 = coefficient class, bits 27..0 = index
 //   vals    : uint4[2nnz] coefficient, 8 x u32 limbs, INTERNAL form (below)
-//   inputs  : uint4[2*n_inputs], aux : uint4[2*n_aux]   canonical witness
+//   kexp    : u16[nnz]    exponents k1 | k2 << 8 of the terms whose coefficient is +-(2^k1 [+ 2^k2])
+//   inputs  : uint4[2*n_inputs], aux : uint4[2*n_aux]   canonical witness;  shadow : u32 per element (see ld_witness)
+//   row_meta, scols, fat_rows, gen_rows                  the plan (see build_row_meta / build_fat_words)
 //
 // Internal coefficient form.  Evaluation never reduces per term:
-//   * general A/B LC  : stored = c * 2^288 mod p, class GEN.  acc (17 limbs) += stored * w ; value = redc(acc) in [0,2p)
-//   * plain   A/B LC  : every coefficient is a small signed integer and sum|c| <= 7: classes P1/M1/P2/M2/PS/MS/ZERO,
+//   * general A/B LC  : stored = c * 2^288 mod p, class GEN (or POW2P/POW2M: same storage, the class is a hint).
+//                       acc (17 limbs) += stored * w ; value = redc(acc) in [0,2p)
+//   * plain   A/B LC  : every coefficient is +-1, +-2 or 0 and sum|c| <= 7: classes P1/M1/P2/M2/ZERO,
 //                       acc (9 limbs) += |c| * (w or p-w) ; value = acc mod p by three conditional subtractions
-//   * C terms         : the NEGATED coefficient, unscaled: stored = p - c (class GEN) or its small class.
+//   * C terms         : the NEGATED coefficient, unscaled: stored = p - c, with the class of that value.
 // Row check:  X = Az*Bz + sum_C (-c)*w  (unreduced, 17 limbs);  satisfied  <=>  redc(X) in {0, p}
 // (the zero test is invariant under redc's 2^-288 factor).  Per row: T_gen + 1 products, <= 3 reductions.
-//
-// Rows with more than `fat_terms` terms (MultiEq rows, num.rs unpacking rows) are skipped by the thread-per-row
-// kernel and done by check_fat_rows, one warp per row: lanes stride the terms (coalesced 1 KB segments), partial
-// sums are combined with a 17-limb xor-shuffle butterfly.
+// The integer kernels decide a row from 4-byte shadows whenever every operand it touches is < 2^24; any other row goes
+// to the full-width kernels in the same check, so every witness gets the verdict of the general arithmetic.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
