@@ -392,3 +392,38 @@ def test_row_base_and_device_result():
         torch.cuda.synchronize()
         assert int(out.item()) == 1_000_000  # random rows: row 0 fails
         assert h.first_unsatisfied() == 0
+
+
+@pytest.mark.parametrize("fid", FIDS)
+@pytest.mark.parametrize("sparse", [0, 1])
+def test_recheck_small_instance_all_forms(fid, sparse):
+    """bp_cs_recheck_u8 / bp_cs_recheck_bits on an instance far below the pipelining threshold (pageable host memory, optional
+    sparse_upload) against the 32-byte upload + bp_cs_first_unsatisfied, for several random bit witnesses."""
+    rng = random.Random(40 + fid)
+    lens, cols, coeffs, inputs, aux, _ = _gadget_like_instance(fid, 91 + fid, 1200, 2500, 0)
+    n_aux = aux.shape[0]
+    n_in = inputs.shape[0]
+    with Handle(fid) as href, Handle(fid) as h:
+        for hh in (href, h):
+            hh.load_instance(lens, cols, coeffs, inputs, aux)
+        h.opt("sparse_upload", sparse)
+        in_bits = np.ones(n_in, np.uint8)  # ONE must stay 1 for the comparison below; the other inputs become 1 too
+        full_in = c_api.ints_to_limbs([1] * n_in)
+        href.ok(href.L.bp_cs_set_range(href.h, 0, 0, n_in, full_in.ctypes.data))
+        row = ctypes.c_int64()
+        for _ in range(4):
+            bits = np.asarray([rng.getrandbits(1) for _ in range(n_aux)], np.uint8)
+            full = c_api.ints_to_limbs([int(b) for b in bits])
+            href.ok(href.L.bp_cs_set_range(href.h, 1, 0, n_aux, full.ctypes.data))
+            want = href.first_unsatisfied()
+            h.ok(h.L.bp_cs_recheck_u8(h.h, in_bits.ctypes.data, bits.ctypes.data, ctypes.byref(row)))
+            assert row.value == want
+            pin, paux = np.packbits(in_bits, bitorder="little"), np.packbits(bits, bitorder="little")
+            # scramble first so that the bit form has to rewrite everything it is responsible for
+            h.ok(h.L.bp_cs_recheck_u8(h.h, in_bits.ctypes.data, (1 - bits).astype(np.uint8).ctypes.data, ctypes.byref(row)))
+            h.ok(h.L.bp_cs_recheck_bits(h.h, pin.ctypes.data, paux.ctypes.data, ctypes.byref(row)))
+            assert row.value == want
+            if not sparse:  # with sparse_upload, elements no row reads keep older values: read back only the full form
+                got = np.zeros((n_aux, 4), np.uint64)
+                h.ok(h.L.bp_cs_witness(h.h, 1, 0, n_aux, got.ctypes.data))
+                assert (got[:, 0] == bits).all() and not got[:, 1:].any()
