@@ -1071,8 +1071,9 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
     cudaError_t pe = cudaPointerGetAttributes(&at, aux_u8);
     if (pe != cudaSuccess) (void)cudaGetLastError();
     const bool dma_able = pe == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
-    // pipelining pays when the copy is long next to the check (>= 4 MB here; the 1-bit form of a 10^8-variable witness is a
-    // 0.25 ms copy: cheaper to finish it and run the check with its thin / fat kernels side by side)
+    // interleaving pays when the copy is long next to the check: from 4 MB in the 1-byte form, from 32 MB in the 1-bit form
+    // (the 1-bit form of a 10^8-variable witness is a 0.25 ms copy: cheaper to finish it and run the check with its thin and
+    // fat kernels side by side)
     const uint64_t xfer = bits ? n / 8 : n;
     const bool pipelined = dma_able && xfer >= (4u << 20) * (bits ? 8u : 1u) && h->n_plain_rows > 0 && h->variant < 0 && h->kernels_mask == 3 &&
                            h->n_rows > 0;
