@@ -16,6 +16,7 @@ from .cs import (  # noqa: F401
     LinearCombination,
     Namespace,
     NativeError,
+    SizedWitness,
     SynthesisError,
     TestConstraintSystem,
     Unsatisfiable,

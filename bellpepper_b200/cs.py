@@ -606,6 +606,38 @@ class TestConstraintSystem(_ConstraintSystemBase):
         return "\n".join(self.pretty_print_list())
 
 
+class SizedWitness:
+    """`SizedWitness` (witness_cs.rs:7-41): a bulk witness producer of known size.  Subclasses give the three counts and
+    `generate_witness_into(aux, inputs) -> result`, which fills the two lists in place (the reference's `&mut [Scalar]`)."""
+
+    def num_constraints(self) -> int:
+        raise NotImplementedError
+
+    def num_inputs(self) -> int:
+        raise NotImplementedError
+
+    def num_aux(self) -> int:
+        raise NotImplementedError
+
+    def generate_witness_into(self, aux: List[int], inputs: List[int]) -> int:
+        raise NotImplementedError
+
+    def generate_witness(self):  # witness_cs.rs:13-26
+        aux, inputs = [0] * self.num_aux(), [0] * self.num_inputs()
+        result = self.generate_witness_into(aux, inputs)
+        return aux, inputs, result
+
+    def generate_witness_into_cs(self, cs) -> int:  # witness_cs.rs:28-40
+        assert cs.is_witness_generator()
+        aux_count, inputs_count = self.num_aux(), self.num_inputs()
+        a0, i0 = cs.allocate_empty(aux_count, inputs_count)
+        aux, inputs = [0] * aux_count, [0] * inputs_count
+        result = self.generate_witness_into(aux, inputs)
+        cs.fill_aux(a0, aux)        # one bulk upload each: the flat-buffer equivalent of writing through the slices
+        cs.fill_inputs(i0, inputs)
+        return result
+
+
 class WitnessCS(_ConstraintSystemBase):
     """`WitnessCS` (witness_cs.rs:45-201) with its two flat assignment vectors held in HBM.
 

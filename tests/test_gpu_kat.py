@@ -208,3 +208,35 @@ def test_structure_hash_equals_oracle():  # test_cs.rs:64-115, 214-237: TestCons
     h0 = got.hash()
     got.set("a", 11)
     assert got.hash() == h0
+
+
+def test_sized_witness_into_witness_cs():  # witness_cs.rs:7-41, 179-193: SizedWitness::generate_witness_into_cs
+    from bellpepper_b200 import SizedWitness
+
+    class Squares(SizedWitness):
+        """aux[i] = (i + 2)^2, inputs = [sum of the aux values]; result = that sum."""
+
+        def num_constraints(self):
+            return 0
+
+        def num_inputs(self):
+            return 1
+
+        def num_aux(self):
+            return 300
+
+        def generate_witness_into(self, aux, inputs):
+            assert len(aux) == 300 and len(inputs) == 1
+            for i in range(300):
+                aux[i] = (i + 2) ** 2
+            inputs[0] = sum(aux)
+            return inputs[0]
+
+    w = WitnessCS.new()
+    w.alloc("first", lambda: 7)
+    gen = Squares()
+    result = gen.generate_witness_into_cs(w)
+    aux, inputs = w.aux_slice(), w.inputs_slice()
+    assert inputs == [1, result] and aux[0] == 7 and aux[1:] == [(i + 2) ** 2 for i in range(300)]
+    assert gen.generate_witness() == (aux[1:], [result], result)
+    w.close()
