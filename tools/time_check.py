@@ -17,7 +17,7 @@ ap.add_argument("--log-rows", type=int, default=22)
 ap.add_argument("--t", type=int, default=6)
 ap.add_argument("--log-vars", type=int, default=None)
 ap.add_argument("--iters", type=int, default=5)
-ap.add_argument("--kernels", default="96", help="comma list of fat_terms values")
+ap.add_argument("--kernels", default="0", help="comma list of fat_terms values (0 = the library's default threshold)")
 ap.add_argument("--opts", default="")
 a = ap.parse_args()
 
@@ -45,7 +45,8 @@ for kv in filter(None, a.opts.split(",")):
     k, v = kv.split("=")
     assert L.bp_cs_set_option(h, k.encode(), int(v)) == 0, L.bp_cs_last_error(h)
 for kern in [int(k) for k in a.kernels.split(",")]:
-    assert L.bp_cs_set_option(h, b"fat_terms", kern) == 0
+    if kern:
+        assert L.bp_cs_set_option(h, b"fat_terms", kern) == 0
     for _ in range(3):
         assert L.bp_cs_check_async(h, ctypes.c_void_p(out.data_ptr())) == 0, L.bp_cs_last_error(h)
     torch.cuda.synchronize()
