@@ -179,6 +179,47 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
         }
     }
 
+    /// Same circuit, next witness (the `SizedWitness` flow, witness_cs.rs:7-41): replace every input and aux value and
+    /// return the first unsatisfied constraint.  `inputs` includes ONE.  Values are sent one bit each when they are all
+    /// 0 or 1, else one byte each; a value that does not fit a byte is patched with `bp_cs_set` before the check.
+    pub fn recheck(&mut self, inputs: &[Scalar], aux: &[Scalar]) -> Option<&str> {
+        self.flush();
+        assert_eq!(inputs.len(), self.input_names.len());
+        assert_eq!(aux.len(), self.aux_names.len());
+        let mut bytes: [Vec<u8>; 2] = [Vec::with_capacity(inputs.len()), Vec::with_capacity(aux.len())];
+        let mut wide: [Vec<(u64, [u64; 4])>; 2] = [vec![], vec![]];
+        for v in inputs { stage_value(v, &mut bytes[0], &mut wide[0]); }
+        for v in aux { stage_value(v, &mut bytes[1], &mut wide[1]); }
+        let mut row = 0i64;
+        if wide[0].is_empty() && wide[1].is_empty() {
+            let all_bits = bytes.iter().all(|b| b.iter().all(|&x| x <= 1));
+            let rc = if all_bits {
+                let pack = |b: &Vec<u8>| -> Vec<u8> {
+                    let mut out = vec![0u8; (b.len() + 7) / 8];
+                    for (i, &x) in b.iter().enumerate() { out[i >> 3] |= x << (i & 7); }
+                    out
+                };
+                let (pi, pa) = (pack(&bytes[0]), pack(&bytes[1]));
+                unsafe { ffi::bp_cs_recheck_bits(self.h, pi.as_ptr(), pa.as_ptr(), &mut row) }
+            } else {
+                unsafe { ffi::bp_cs_recheck_u8(self.h, bytes[0].as_ptr(), bytes[1].as_ptr(), &mut row) }
+            };
+            self.check(rc);
+        } else {
+            for k in 0..2 {
+                let rc = unsafe { ffi::bp_cs_set_range_u8(self.h, k as i32, 0, bytes[k].len() as u64, bytes[k].as_ptr()) };
+                self.check(rc);
+                for (pos, limbs) in &wide[k] {
+                    let rc = unsafe { ffi::bp_cs_set(self.h, k as i32, *pos, limbs.as_ptr()) };
+                    self.check(rc);
+                }
+            }
+            let rc = unsafe { ffi::bp_cs_first_unsatisfied(self.h, &mut row) };
+            self.check(rc);
+        }
+        if row < 0 { None } else { Some(&self.constraint_paths[row as usize]) }
+    }
+
     pub fn num_constraints(&self) -> usize { self.constraint_paths.len() }
     pub fn num_inputs(&self) -> usize { self.input_names.len() }
 
