@@ -23,6 +23,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../../include/bp_r1cs.h"
@@ -303,6 +304,100 @@ template <bool kNamed> class TestConstraintSystemT {
     std::vector<uint64_t> coeffs_;
     std::unordered_map<std::string, NamedObject> named_;
     std::vector<std::string> ns_, row_paths_, input_names_, aux_names_;
+};
+
+// ---- WitnessCS (crates/bellpepper/src/util_cs/witness_cs.rs:45-201) ------------------------------------------------
+// The flat witness container: no names, no constraints (`enforce` is a no-op and never runs its closures,
+// witness_cs.rs:125-134), values appended in allocation order.  The two assignment vectors live in HBM behind the
+// handle; allocations are staged packed like in TestConstraintSystemT.
+class WitnessCS {
+  public:
+    using Root = WitnessCS;
+    // `new()` (witness_cs.rs:94-101): input_assignment = [ONE], aux_assignment = []: exactly a fresh handle
+    WitnessCS(int field, bp_cs* handle) : field_(field), h_(handle) { count_[0] = 1; count_[1] = 0; }
+    static Variable one() { return one_var(); }
+    const Field* field() const { return &field_; }
+
+    template <class N, class V> Variable alloc(N&&, V&& value) { return push(1, value()); }        // witness_cs.rs:103-112
+    template <class N, class V> Variable alloc_input(N&&, V&& value) { return push(0, value()); }  // witness_cs.rs:114-123
+    template <class N, class A, class B, class C> void enforce(N&&, A&&, B&&, C&&) {}              // witness_cs.rs:125-134
+    template <class N> void push_namespace(N&&) {}
+    void pop_namespace() {}
+    Root& get_root() { return *this; }
+    template <class N> Namespace<Root> ns(N&&) { return Namespace<Root>(*this); }
+
+    static bool is_extensible() { return true; }  // witness_cs.rs:150-152
+    void extend(WitnessCS& other) {               // witness_cs.rs:154-163: other's inputs without its ONE, then its aux
+        const std::vector<Fr> in = other.inputs_slice(), ax = other.aux_slice();
+        extend_inputs(in.data() + 1, in.size() - 1);
+        extend_aux(ax.data(), ax.size());
+    }
+    static bool is_witness_generator() { return true; }  // witness_cs.rs:167-169
+    void extend_inputs(const Fr* v, size_t n) {          // witness_cs.rs:171-173
+        for (size_t i = 0; i < n; ++i) push(0, v[i]);
+    }
+    void extend_aux(const Fr* v, size_t n) {  // witness_cs.rs:175-177
+        for (size_t i = 0; i < n; ++i) push(1, v[i]);
+    }
+    // witness_cs.rs:179-193: both vectors grow by zeros; the reference returns the two new tails (aux first) as mutable
+    // slices -- here their first indices, to be filled with fill_aux / fill_inputs (one bulk upload each)
+    std::pair<uint64_t, uint64_t> allocate_empty(size_t aux_n, size_t inputs_n) {
+        const uint64_t a0 = count_[1], i0 = count_[0];
+        for (size_t i = 0; i < aux_n; ++i) push(1, Fr::zero());
+        for (size_t i = 0; i < inputs_n; ++i) push(0, Fr::zero());
+        return {a0, i0};
+    }
+    void fill_aux(uint64_t first, const Fr* v, size_t n) { fill(1, first, v, n); }
+    void fill_inputs(uint64_t first, const Fr* v, size_t n) { fill(0, first, v, n); }
+    std::vector<Fr> inputs_slice() { return slice(0); }  // witness_cs.rs:195-197
+    std::vector<Fr> aux_slice() { return slice(1); }     // witness_cs.rs:199-201
+    uint64_t num_inputs() const { return count_[0]; }
+    uint64_t num_aux() const { return count_[1]; }
+
+    void flush() {
+        for (int k = 0; k < 2; ++k) {
+            if (pend_[k].empty()) continue;
+            uint64_t first;
+            if (bp_cs_alloc_u8(h_, k, pend_[k].data(), pend_[k].size(), &first) != BP_OK) fail();
+            for (size_t i = 0; i < wide_pos_[k].size(); ++i)
+                if (bp_cs_set(h_, k, first + wide_pos_[k][i], wide_vals_[k].data() + 4 * i) != BP_OK) fail();
+            pend_[k].clear();
+            wide_pos_[k].clear();
+            wide_vals_[k].clear();
+        }
+    }
+
+  private:
+    Variable push(int is_aux, const Fr& v) {
+        const uint64_t idx = count_[is_aux]++;
+        if ((v.l[0] >> 8) == 0 && (v.l[1] | v.l[2] | v.l[3]) == 0) {
+            pend_[is_aux].push_back((uint8_t)v.l[0]);
+        } else {
+            wide_pos_[is_aux].push_back(pend_[is_aux].size());
+            wide_vals_[is_aux].insert(wide_vals_[is_aux].end(), v.l, v.l + 4);
+            pend_[is_aux].push_back(0);
+        }
+        if (pend_[is_aux].size() >= (4u << 20)) flush();
+        return is_aux ? Variable::aux((uint32_t)idx) : Variable::input((uint32_t)idx);
+    }
+    void fill(int is_aux, uint64_t first, const Fr* v, size_t n) {
+        flush();
+        static_assert(sizeof(Fr) == 32, "Fr is 4 limbs");
+        if (n && bp_cs_set_range(h_, is_aux, first, n, v[0].l) != BP_OK) fail();
+    }
+    std::vector<Fr> slice(int is_aux) {
+        flush();
+        std::vector<Fr> out(count_[is_aux]);
+        if (!out.empty() && bp_cs_witness(h_, is_aux, 0, out.size(), out[0].l) != BP_OK) fail();
+        return out;
+    }
+    [[noreturn]] void fail() { throw SynthesisError(SynthesisError::Native, bp_cs_last_error(h_)); }
+
+    Field field_;
+    bp_cs* h_;
+    uint64_t count_[2];
+    std::vector<uint8_t> pend_[2];
+    std::vector<uint64_t> wide_pos_[2], wide_vals_[2];
 };
 
 using TestConstraintSystem = TestConstraintSystemT<true>;

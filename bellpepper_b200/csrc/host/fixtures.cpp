@@ -210,6 +210,45 @@ int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t pe
     });
 }
 
+// Scripted exercise of the C++ WitnessCS against the reference's own test (witness_cs.rs tests + :94-201); returns 0 or the
+// number of the first failed expectation.
+int bp_wcs_selftest(int field, int device) {
+    bp_cs *h1 = nullptr, *h2 = nullptr;
+    if (bp_cs_new(field, device, 0, 0, 0, &h1) != BP_OK || bp_cs_new(field, device, 0, 0, 0, &h2) != BP_OK) return -1;
+    int bad = 0;
+    try {
+        const FieldParams& fp = field_params(field);
+        Fr pm1{{fp.p[0] - 1, fp.p[1], fp.p[2], fp.p[3]}};
+        WitnessCS w(field, h1), other(field, h2);
+        auto nm = [] { return std::string(); };
+        Variable a = w.alloc(nm, [] { return Fr::from_u64(2); });
+        Variable b = w.alloc_input(nm, [&] { return pm1; });
+        w.enforce(nm, [](LinearCombination lc) { return lc; }, [](LinearCombination lc) { return lc; }, [](LinearCombination lc) { return lc; });
+        if (!bad && !(a == Variable::aux(0) && b == Variable::input(1))) bad = 1;
+        other.alloc_input(nm, [] { return Fr::from_u64(7); });
+        other.alloc(nm, [] { return Fr::from_u64(300); });
+        other.alloc(nm, [] { return Fr::from_u64(1); });
+        w.extend(other);  // inputs: [1, p-1, 7]; aux: [2, 300, 1]
+        auto fresh = w.allocate_empty(3, 1);  // aux first
+        if (!bad && !(fresh.first == 3 && fresh.second == 3)) bad = 2;
+        Fr fill_a[3] = {Fr::from_u64(10), pm1, Fr::from_u64(12)}, fill_i[1] = {Fr::from_u64(99)};
+        w.fill_aux(fresh.first, fill_a, 3);
+        w.fill_inputs(fresh.second, fill_i, 1);
+        const std::vector<Fr> in = w.inputs_slice(), ax = w.aux_slice();
+        const Fr want_in[4] = {Fr::one(), pm1, Fr::from_u64(7), Fr::from_u64(99)};
+        const Fr want_ax[6] = {Fr::from_u64(2), Fr::from_u64(300), Fr::one(), Fr::from_u64(10), pm1, Fr::from_u64(12)};
+        if (!bad && !(in.size() == 4 && ax.size() == 6)) bad = 3;
+        for (size_t i = 0; !bad && i < 4; ++i) if (in[i] != want_in[i]) bad = 10 + (int)i;
+        for (size_t i = 0; !bad && i < 6; ++i) if (ax[i] != want_ax[i]) bad = 20 + (int)i;
+        if (!bad && !(WitnessCS::is_extensible() && WitnessCS::is_witness_generator())) bad = 4;
+    } catch (const std::exception&) {
+        bad = -2;
+    }
+    bp_cs_free(h1);
+    bp_cs_free(h2);
+    return bad;
+}
+
 int64_t bp_tcs_which_is_unsatisfied(bp_tcs* t, char* path, uint64_t cap) {
     if (!t) return -5;
     int64_t row = -1;

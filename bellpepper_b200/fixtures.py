@@ -21,6 +21,7 @@ _SIGS = {
     "bp_tcs_sha256_block": (ctypes.c_int, [vp, vp, vp]),
     "bp_tcs_sha256": (ctypes.c_int, [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, u64p]),
     "bp_tcs_blake2s": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, vp]),
+    "bp_wcs_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "bp_tcs_which_is_unsatisfied": (ctypes.c_int64, [vp, vp, ctypes.c_uint64]),
     "bp_tcs_set": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
     "bp_tcs_get": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
@@ -177,6 +178,10 @@ class Tcs:
 def chain_message(blocks: int) -> bytes:
     """Message whose sha256() circuit has exactly `blocks` compression calls (the last one holds the padding)."""
     return xorshift_bytes(64 * blocks - 9)
+
+
+def witness_cs_selftest(field: int, device: int = 0) -> int:
+    return int(_lib().bp_wcs_selftest(field, device))
 
 
 def blake2s_into_new_handle(field: int, device: int, n_bytes: int):

@@ -43,6 +43,10 @@ int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t block_be
  * output bytes (the gadget's output bits are little-endian per byte). */
 int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint8_t digest[32]);
 
+/* Scripted self-test of the C++ `WitnessCS` mirror (csrc/host/cs.hpp; witness_cs.rs:94-201: alloc / alloc_input / no-op
+ * enforce / extend / allocate_empty / slices) on a device.  Returns 0, or the number of the first expectation that failed. */
+int bp_wcs_selftest(int field, int device);
+
 /* TestConstraintSystem surface (test_cs.rs:239-323).  which_is_unsatisfied: returns the row (>= 0), -1 when
  * satisfied, < -1 on error; `path` (cap bytes) receives the constraint's path when named. */
 int64_t bp_tcs_which_is_unsatisfied(bp_tcs* t, char* path, uint64_t cap);

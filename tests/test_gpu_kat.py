@@ -240,3 +240,10 @@ def test_sized_witness_into_witness_cs():  # witness_cs.rs:7-41, 179-193: SizedW
     assert inputs == [1, result] and aux[0] == 7 and aux[1:] == [(i + 2) ** 2 for i in range(300)]
     assert gen.generate_witness() == (aux[1:], [result], result)
     w.close()
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2])
+def test_cpp_witness_cs_mirror(fid):  # witness_cs.rs:94-201 through the C++ host mirror (csrc/host/cs.hpp)
+    from bellpepper_b200 import fixtures
+
+    assert fixtures.witness_cs_selftest(fid, 0) == 0
