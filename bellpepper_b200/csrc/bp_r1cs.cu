@@ -731,6 +731,131 @@ int bp_cs_sync(bp_cs* h) {
     return BP_OK;
 }
 
+// ---- checkpoint / resume of an ingested system ---------------------------------------------------------------------------
+// File = header (magic, ABI version, field, counts) followed by the device arrays as they are: row_ptr, cols (with class
+// bits), vals (internal form), kexp, then the canonical witness (inputs, aux).  Loading is a plain copy plus the witness
+// validation pass that also rebuilds the shadows; the plan is rebuilt lazily as after any structural change.
+namespace {
+struct FileHeader {
+    char magic[8];  // "BPR1CS\0\1"
+    uint32_t abi, field;
+    uint64_t n_rows, nnz, n_inputs, n_aux, n_gen, row_base;
+};
+const char kMagic[8] = {'B', 'P', 'R', '1', 'C', 'S', 0, 1};
+
+int dump(bp_cs* h, FILE* f, const void* dev, size_t bytes) {
+    size_t off = 0;
+    while (off < bytes) {
+        const size_t n = std::min(kStageBytes, bytes - off);
+        CU(h, cudaMemcpyAsync(h->h_stage[0], (const char*)dev + off, n, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (fwrite(h->h_stage[0], 1, n, f) != n) return fail(h, BP_E_STATE, "short write");
+        off += n;
+    }
+    return BP_OK;
+}
+int slurp(bp_cs* h, FILE* f, void* dev, size_t bytes) {
+    size_t off = 0;
+    while (off < bytes) {
+        const int s = h->stage_next;
+        h->stage_next = (s + 1) % kNumStage;
+        const size_t n = std::min(kStageBytes, bytes - off);
+        CU(h, cudaEventSynchronize(h->stage_ev[s]));
+        if (fread(h->h_stage[s], 1, n, f) != n) return fail(h, BP_E_STATE, "short read: truncated file");
+        CU(h, cudaMemcpyAsync((char*)dev + off, h->h_stage[s], n, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaEventRecord(h->stage_ev[s], h->stream));
+        off += n;
+    }
+    return BP_OK;
+}
+}  // namespace
+
+int bp_cs_save(bp_cs* h, const char* path) {
+    if (!h || !path) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->wide_valid) {  // small values live in the shadows only: write their 32-byte form first
+        for (int k = 0; k < 2; ++k) {
+            const uint64_t n = k ? h->n_aux : h->n_inputs;
+            if (!n) continue;
+            materialize_wide<<<grid_for(h, 2 * n, 256, 8), 256, 0, h->stream>>>(shadow_ptr(h, k), n, (uint4*)(k ? h->aux.p : h->inputs.p));
+            h->launches++;
+        }
+        CU(h, cudaGetLastError());
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(h, BP_E_STATE, "cannot open %s for writing", path);
+    FileHeader hd;
+    std::memcpy(hd.magic, kMagic, 8);
+    hd.abi = BP_ABI_VERSION;
+    hd.field = (uint32_t)h->field;
+    hd.n_rows = h->n_rows; hd.nnz = h->nnz; hd.n_inputs = h->n_inputs; hd.n_aux = h->n_aux; hd.n_gen = h->n_gen; hd.row_base = h->row_base;
+    int rc = fwrite(&hd, sizeof hd, 1, f) == 1 ? BP_OK : fail(h, BP_E_STATE, "short write");
+    if (rc == BP_OK) rc = dump(h, f, h->row_ptr.p, (3 * (size_t)h->n_rows + 1) * 4);
+    if (rc == BP_OK) rc = dump(h, f, h->cols.p, (size_t)h->nnz * 4);
+    if (rc == BP_OK) rc = dump(h, f, h->vals.p, (size_t)h->nnz * 32);
+    if (rc == BP_OK) rc = dump(h, f, h->kexp.p, (size_t)h->nnz * 2);
+    if (rc == BP_OK) rc = dump(h, f, h->inputs.p, (size_t)h->n_inputs * 32);
+    if (rc == BP_OK) rc = dump(h, f, h->aux.p, (size_t)h->n_aux * 32);
+    if (fclose(f) != 0 && rc == BP_OK) rc = fail(h, BP_E_STATE, "close failed");
+    return rc;
+}
+
+int bp_cs_load(const char* path, int device, bp_cs** out) {
+    if (!path || !out) return BP_E_ARG;
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return BP_E_STATE;
+    FileHeader hd;
+    if (fread(&hd, sizeof hd, 1, f) != 1 || std::memcmp(hd.magic, kMagic, 8) != 0 || hd.abi != BP_ABI_VERSION || hd.field > 2 ||
+        hd.n_inputs < 1 || hd.nnz >= 0xffffffffull || 3 * hd.n_rows + 1 >= 0xffffffffull) {
+        fclose(f);
+        return BP_E_ARG;
+    }
+    bp_cs* h = nullptr;
+    int rc = bp_cs_new((int)hd.field, device, hd.n_rows, hd.nnz, hd.n_aux, &h);
+    if (rc != BP_OK) {
+        fclose(f);
+        return rc;
+    }
+    auto done = [&](int code) -> int {
+        fclose(f);
+        if (code != BP_OK) {
+            bp_cs_free(h);
+            return code;
+        }
+        *out = h;
+        return BP_OK;
+    };
+    if ((rc = ensure(h, h->row_ptr, (3 * (size_t)hd.n_rows + 1) * 4, 0)) != BP_OK) return done(rc);
+    if ((rc = ensure(h, h->cols, (size_t)hd.nnz * 4, 0)) != BP_OK) return done(rc);
+    if ((rc = ensure(h, h->vals, (size_t)hd.nnz * 32, 0)) != BP_OK) return done(rc);
+    if ((rc = ensure(h, h->kexp, (size_t)hd.nnz * 2, 0)) != BP_OK) return done(rc);
+    if ((rc = ensure(h, h->inputs, (size_t)hd.n_inputs * 32, 0)) != BP_OK) return done(rc);
+    if ((rc = ensure(h, h->aux, std::max<size_t>((size_t)hd.n_aux * 32, 32), 0)) != BP_OK) return done(rc);
+    h->n_inputs = h->n_aux = 0;  // nothing to carry over when the shadows are sized
+    if ((rc = ensure_shadow(h, hd.n_inputs, hd.n_aux)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->row_ptr.p, (3 * (size_t)hd.n_rows + 1) * 4)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->cols.p, (size_t)hd.nnz * 4)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->vals.p, (size_t)hd.nnz * 32)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->kexp.p, (size_t)hd.nnz * 2)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->inputs.p, (size_t)hd.n_inputs * 32)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->aux.p, (size_t)hd.n_aux * 32)) != BP_OK) return done(rc);
+    if ((rc = clear_err(h)) != BP_OK) return done(rc);
+    for (int k = 0; k < 2; ++k) {
+        const uint64_t n = k ? hd.n_aux : hd.n_inputs;
+        if (!n) continue;
+        DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint4*)(k ? h->aux.p : h->inputs.p), n,
+                                                                                              h->d_err, shadow_ptr(h, k))));
+        h->launches++;
+    }
+    if (cudaGetLastError() != cudaSuccess) return done(BP_E_CUDA);
+    h->n_rows = hd.n_rows; h->nnz = hd.nnz; h->n_inputs = hd.n_inputs; h->n_aux = hd.n_aux; h->n_gen = hd.n_gen; h->row_base = hd.row_base;
+    h->wide_valid = true;
+    h->plan_valid = false;
+    if ((rc = check_err_word(h, "bp_cs_load")) != BP_OK) return done(rc);  // (also waits for the uploads)
+    return done(BP_OK);
+}
+
 int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
     if (!h || !key) return BP_E_ARG;
     if (!std::strcmp(key, "variant")) {

@@ -137,6 +137,14 @@ int bp_cs_eval_async(bp_cs* cs, uint64_t* dev_az, uint64_t* dev_bz, uint64_t* de
 /* LinearCombination::eval for one ad-hoc LC (lc.rs:245-267). */
 int bp_cs_eval_lc(bp_cs* cs, const uint32_t* cols, const uint64_t* coeffs_le, uint32_t n_terms, uint64_t out[4]);
 
+/* ---- checkpoint / resume ---------------------------------------------------------------------------
+ * Not a reference interface (LinearCombination is not serialisable there, lc.rs:34): write an ingested system -- matrices in
+ * their device-internal form, canonical witness, row base -- to a file, and create a handle from such a file, so that a
+ * 10^8-row synthesis is paid once.  bp_cs_load returns BP_E_ARG for a file that is not one of ours (magic / ABI version),
+ * BP_E_STATE for an unreadable or truncated one, BP_E_RANGE when its witness is not canonical. */
+int bp_cs_save(bp_cs* cs, const char* path);
+int bp_cs_load(const char* path, int device, bp_cs** out);
+
 /* ---- execution control -----------------------------------------------------------------------------*/
 /* Use an existing CUDA stream (cudaStream_t as void*) for all work.  NULL = the handle's own non-blocking
  * stream; the legacy default stream is cudaStreamLegacy, i.e. (void*)0x1. */

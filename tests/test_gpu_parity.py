@@ -427,3 +427,51 @@ def test_recheck_small_instance_all_forms(fid, sparse):
                 got = np.zeros((n_aux, 4), np.uint64)
                 h.ok(h.L.bp_cs_witness(h.h, 1, 0, n_aux, got.ctypes.data))
                 assert (got[:, 0] == bits).all() and not got[:, 1:].any()
+
+
+def test_save_and_load_round_trip(tmp_path):
+    """bp_cs_save / bp_cs_load: an ingested system (gadget-shaped rows, small and full-width witness values, a packed upload on
+    top) comes back with the same counts, verdict, witness and A.w/B.w/C.w; foreign and truncated files are refused."""
+    from bellpepper_b200 import ffi
+
+    fid = 2
+    lens, cols, coeffs, inputs, aux, _ = _gadget_like_instance(fid, 123, 1500, 2500, 7)
+    n_rows, n_aux = lens.size // 3, aux.shape[0]
+    path = str(tmp_path / "system.bpr1cs").encode()
+    L = ffi.load()
+    with Handle(fid) as h:
+        h.load_instance(lens, cols, coeffs, inputs, aux)
+        h.ok(h.L.bp_cs_set_row_base(h.h, 1000))
+        bits = np.asarray([i % 2 for i in range(300)], np.uint8)
+        h.ok(h.L.bp_cs_set_range_u8(h.h, 1, 50, 300, bits.ctypes.data))  # leaves wide_valid = 0: save must materialise
+        want_row = h.first_unsatisfied()
+        want = h.eval(n_rows)
+        w = np.zeros((n_aux, 4), np.uint64)
+        h.ok(h.L.bp_cs_witness(h.h, 1, 0, n_aux, w.ctypes.data))
+        h.ok(h.L.bp_cs_save(h.h, path))
+    h2 = ffi.vp()
+    assert L.bp_cs_load(path, 0, ctypes.byref(h2)) == 0
+    try:
+        g = Handle.__new__(Handle)
+        g.L, g.h, g.field = L, h2, fid
+        assert g.counts() == (inputs.shape[0], n_aux, n_rows, cols.size)
+        assert g.first_unsatisfied() == want_row
+        got = g.eval(n_rows)
+        assert all((x == y).all() for x, y in zip(got, want))
+        w2 = np.zeros((n_aux, 4), np.uint64)
+        g.ok(L.bp_cs_witness(h2, 1, 0, n_aux, w2.ctypes.data))
+        assert (w2 == w).all()
+        out = __import__("torch").zeros(1, dtype=__import__("torch").int64, device="cuda:0")
+        g.ok(L.bp_cs_check_async(h2, ctypes.c_void_p(out.data_ptr())))
+        g.ok(L.bp_cs_sync(h2))
+        assert int(out.item()) == (want_row + 1000 if want_row >= 0 else 0x7FFFFFFFFFFFFFFF)  # the row base travels too
+    finally:
+        L.bp_cs_free(h2)
+    raw = open(path, "rb").read()
+    bad = str(tmp_path / "bad.bin").encode()
+    open(bad, "wb").write(b"NOTOURS!" + raw[8:])
+    h3 = ffi.vp()
+    assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -5 and not h3.value
+    open(bad, "wb").write(raw[: len(raw) // 2])
+    assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -4 and not h3.value
+    assert L.bp_cs_load(str(tmp_path / "missing").encode(), 0, ctypes.byref(h3)) == -4
