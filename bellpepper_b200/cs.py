@@ -292,6 +292,7 @@ class _Device:
         self._coeffs: List[int] = []
         self.n_rows = 0
         self._structure = bytearray()  # serialised LCs for TestConstraintSystem.hash (test_cs.rs:64-115)
+        self._row_digests: List[bytes] = []  # one digest per constraint over its three raw LCs, for `delta`
 
     def close(self):
         if getattr(self, "h", None):
@@ -316,8 +317,14 @@ class _Device:
         return idx
 
     def push_row(self, a: LinearCombination, b: LinearCombination, c: LinearCombination) -> int:
+        import hashlib
+
+        raw = hashlib.blake2s(digest_size=16)
         for lc in (a, b, c):
             cols, coeffs = lc.flat()
+            # LinearCombination == (derived PartialEq, lc.rs:34-46): the term lists as they are, zero coefficients included
+            raw.update(len(cols).to_bytes(4, "little") + b"".join(col.to_bytes(4, "little") + co.to_bytes(32, "little")
+                                                                  for col, co in zip(cols, coeffs)))
             self._lens.append(len(cols))
             self._cols.extend(cols)
             self._coeffs.extend(coeffs)
@@ -326,6 +333,7 @@ class _Device:
             self._structure += len(kept).to_bytes(8, "big")
             for col, co in kept:
                 self._structure += (b"A" if col & ffi.COL_AUX else b"I") + (col & 0x7FFFFFFF).to_bytes(8, "big") + co.to_bytes(32, "big")
+        self._row_digests.append(raw.digest())
         self.n_rows += 1
         if len(self._cols) >= self.FLUSH_TERMS:
             self.flush()
@@ -564,6 +572,28 @@ class TestConstraintSystem(_ConstraintSystemBase):
         h.update(self.dev._count[0].to_bytes(8, "big") + self.dev._count[1].to_bytes(8, "big") + self.dev.n_rows.to_bytes(8, "big"))
         h.update(bytes(self.dev._structure))
         return h.hexdigest()
+
+    def delta(self, other: "TestConstraintSystem", ignore_counts: bool = False):
+        """`Comparable::delta` (util_cs/mod.rs:39-76): ("Equal",), ("InputCountMismatch", a, b), ("ConstraintCountMismatch", a, b),
+        ("ConstraintMismatch", index, path_here, path_there) for the first constraint that differs (LCs or path), or ("Different",)."""
+        mine = [d + p.encode() for d, p in zip(self.dev._row_digests, self.constraint_paths)]
+        theirs = [d + p.encode() for d, p in zip(other.dev._row_digests, other.constraint_paths)]
+        input_count_matches = self.num_inputs() == other.num_inputs()
+        constraint_count_matches = self.num_constraints() == other.num_constraints()
+        inputs_match = self.input_names == other.input_names
+        constraints_match = mine == theirs
+        if not ignore_counts and not input_count_matches:
+            return ("InputCountMismatch", self.num_inputs(), other.num_inputs())
+        if not ignore_counts and not constraint_count_matches:
+            return ("ConstraintCountMismatch", self.num_constraints(), other.num_constraints())
+        if not constraints_match:
+            for i, (x, y) in enumerate(zip(mine, theirs)):
+                if x != y:
+                    return ("ConstraintMismatch", i, self.constraint_paths[i], other.constraint_paths[i])
+            raise IndexError("constraint lists differ only in length")  # the reference unwraps a None here (mod.rs:66)
+        if input_count_matches and constraint_count_matches and inputs_match:
+            return ("Equal",)
+        return ("Different",)
 
     def num_constraints(self) -> int:
         return len(self.constraint_paths)

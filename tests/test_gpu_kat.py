@@ -247,3 +247,25 @@ def test_cpp_witness_cs_mirror(fid):  # witness_cs.rs:94-201 through the C++ hos
     from bellpepper_b200 import fixtures
 
     assert fixtures.witness_cs_selftest(fid, 0) == 0
+
+
+def test_delta():  # crates/bellpepper-core/src/util_cs/mod.rs:39-76: Comparable::delta
+    def build(extra_input=False, coeff=1, second=True, name="second"):
+        cs = TestConstraintSystem.new()
+        a = cs.alloc("a", lambda: 3)
+        b = cs.alloc_input("b", lambda: 3)
+        if extra_input:
+            cs.alloc_input("c", lambda: 0)
+        cs.enforce("first", lambda lc: lc + a, lambda lc: lc + ONE, lambda lc: lc + b)
+        if second:
+            cs.enforce(name, lambda lc: lc + (coeff, a), lambda lc: lc + ONE, lambda lc: lc + (coeff, b))
+        return cs
+
+    base = build()
+    assert base.delta(build()) == ("Equal",)
+    assert base.delta(build(extra_input=True)) == ("InputCountMismatch", 2, 3)
+    assert base.delta(build(second=False)) == ("ConstraintCountMismatch", 2, 1)
+    assert base.delta(build(coeff=5)) == ("ConstraintMismatch", 1, "second", "second")
+    assert base.delta(build(name="renamed")) == ("ConstraintMismatch", 1, "second", "renamed")
+    assert base.delta(build(extra_input=True, coeff=5), ignore_counts=True) == ("ConstraintMismatch", 1, "second", "second")
+    assert base.delta(build(extra_input=True), ignore_counts=True) == ("Different",)
