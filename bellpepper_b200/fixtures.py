@@ -209,18 +209,9 @@ def sha256_chain_into_new_handle(field: int, device: int, blocks: int, rank: int
     """BASELINE configs[1]: sha256 gadget over `blocks` chained compression blocks, rows of this rank's block range
     streamed into a fresh device handle.  Returns (bp_cs handle as c_void_p, info); the caller frees via `info['tcs']`."""
     # rows are what is balanced: the shard holding block 0 also holds the 8 * len(msg) boolean rows of the input bits
-    msg_len = 64 * blocks - 9
-    rows_per_block, input_rows = 26192, 8 * msg_len
-    total = input_rows + blocks * rows_per_block
+    from .sharding import split_units_by_rows
 
-    def cut(k):  # first block of rank k
-        if k <= 0:
-            return 0
-        if k >= world:
-            return blocks
-        return min(blocks, max(0, round((k * total / world - input_rows) / rows_per_block)))
-
-    b0, b1 = cut(rank), cut(rank + 1)
+    b0, b1 = split_units_by_rows(blocks, 26192, 8 * (64 * blocks - 9), rank, world)
     per_block_rows, per_block_terms, per_block_vars = 26400, 170000, 26500
     t = Tcs(field, device, named=False,
             reserve=((b1 - b0) * per_block_rows + 4096, (b1 - b0) * per_block_terms + 65536, blocks * per_block_vars + 4096))

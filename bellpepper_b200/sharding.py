@@ -14,6 +14,22 @@ def split_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return rank * n // world, (rank + 1) * n // world
 
 
+def split_units_by_rows(n_units: int, rows_per_unit: int, leading_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of `n_units` equal units (e.g. sha256 compression blocks of `rows_per_unit` rows) that balances ROWS
+    when `leading_rows` extra rows (e.g. the boolean rows of the input bits) come before unit 0 and belong to its shard."""
+    assert 0 <= rank < world
+    total = leading_rows + n_units * rows_per_unit
+
+    def cut(k: int) -> int:  # first unit of rank k
+        if k <= 0:
+            return 0
+        if k >= world:
+            return n_units
+        return min(n_units, max(0, round((k * total / world - leading_rows) / rows_per_unit)))
+
+    return cut(rank), cut(rank + 1)
+
+
 def to_global(local_row: int, row_base: int) -> int:
     """Local first-unsatisfied row (-1 = satisfied) -> all-reduce operand."""
     return SATISFIED if local_row < 0 else row_base + local_row

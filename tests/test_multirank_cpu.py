@@ -79,3 +79,18 @@ def test_two_rank_sharding_matches_single_rank(tmp_path):
     for k in ("clean", "early", "late", "rows_total"):
         assert got[k] == want[k], (k, got, want)
     assert got["row_base"] == 0
+
+
+def test_split_units_by_rows_balances_rows():
+    """The sha256 chain's shards: contiguous, exhaustive, and balanced in ROWS although rank 0 also owns the input-bit rows."""
+    from bellpepper_b200.sharding import split_units_by_rows
+
+    for blocks, world in ((4096, 8), (4096, 2), (170, 3), (5, 8), (64, 1)):
+        rpb, lead = 26192, 8 * (64 * blocks - 9)
+        cuts = [split_units_by_rows(blocks, rpb, lead, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == blocks
+        assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))  # contiguous, nothing lost
+        rows = [(b1 - b0) * rpb + (lead if r == 0 else 0) for r, (b0, b1) in enumerate(cuts)]
+        assert sum(rows) == lead + blocks * rpb
+        if blocks >= 8 * world:
+            assert max(rows) - min(rows) <= rpb  # within one block of each other
