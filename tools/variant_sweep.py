@@ -1,4 +1,6 @@
-"""Time the experimental kernel variants (library built with BP_EXPERIMENTAL_VARIANTS=1) on one workload."""
+"""Time kernel variants on one workload: bp_cs_set_option("variant") -1 = default, bit 0 no small-operand kernel, bit 1 no
+shadows in the fat kernels, bit 2 park, bit 3 no integer pass over the fat rows; 100+k = the experimental template variants of a
+library built with BP_EXPERIMENTAL_VARIANTS=1.  --masks: 1 thin-row kernels only, 2 fat-row kernels only, 3 both."""
 import argparse
 import ctypes
 import json
