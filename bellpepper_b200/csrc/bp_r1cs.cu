@@ -10,7 +10,11 @@
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time (dlopen), see NcclApi
+
 #include <algorithm>
+#include <thread>
 #include <utility>
 #include <vector>
 #include <cstdarg>
@@ -90,6 +94,26 @@ struct bp_cs {
     int stage_next = 0;
     FieldConsts fc;
     int64_t launches = 0;
+    // One check = init_result + up to four kernels on two streams (+ the group's exchange kernel): captured once into a CUDA
+    // graph and replayed while nothing the kernels' arguments depend on has changed (see check_graphed).
+    struct {
+        cudaGraphExec_t exec = nullptr;
+        bp::CsrView view;
+        long long* out = nullptr;
+        const void* group = nullptr;
+        int64_t variant = 0, kernels_mask = 0;
+        uint64_t plan_gen = 0;
+        int64_t launches = 0;  // kernels one replay launches
+    } graph;
+    bool use_graph = true;      // bp_cs_set_option("graph", 0) turns it off
+    uint64_t plan_gen = 0;      // bumped whenever the plan is rebuilt
+    int64_t graph_replays = 0, graph_captures = 0;
+    void* h_pack = nullptr;       // pinned: bit-packed witness produced by bp_cs_recheck_scalars (inputs, then aux 64-byte aligned)
+    size_t h_pack_cap = 0;
+    void* h_patch = nullptr;      // pinned: exception list of the same call / batch of bp_cs_set_many (indices, then values)
+    size_t h_patch_cap = 0;
+    DevBuf patch_stage;           // device copy of h_patch
+    bool caller_dma_pending = false;  // an H2D copy enqueued by upload() still reads the caller's own pinned memory
 };
 
 namespace {
@@ -219,6 +243,7 @@ int grid_for(const bp_cs* h, uint64_t n, int block, int per_sm) {
 
 CsrView view(const bp_cs* h) {
     CsrView m;
+    std::memset(&m, 0, sizeof m);  // (compared bytewise by the graph cache: no indeterminate padding)
     m.row_ptr = (const uint32_t*)h->row_ptr.p;
     m.cols = (const uint32_t*)h->cols.p;
     m.vals = (const uint4*)h->vals.p;
@@ -252,6 +277,7 @@ int upload(bp_cs* h, void* dst, const void* src, size_t bytes) {
     }
     if (e == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged)) {
         CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        h->caller_dma_pending = true;  // the copy reads the caller's buffer: see settle()
         return BP_OK;
     }
     size_t off = 0;
@@ -268,11 +294,22 @@ int upload(bp_cs* h, void* dst, const void* src, size_t bytes) {
     return BP_OK;
 }
 
+// "The caller owns every buffer it passes; the library copies before returning": the synchronous entry points call this
+// before they return, so that a DMA straight out of pinned caller memory has finished (pageable memory was already copied
+// into the staging ring).  The *_async / recheck entry points document that their buffers must outlive the stream's use.
+int settle(bp_cs* h) {
+    if (!h->caller_dma_pending) return BP_OK;
+    h->caller_dma_pending = false;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return BP_OK;
+}
+
 int read_flags(bp_cs* h, long long* first_bad, unsigned int* err) {
     char* hp = (char*)h->h_pinned_small;
     CU(h, cudaMemcpyAsync(hp + 32, h->d_result, 8, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(hp + 40, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    h->caller_dma_pending = false;
     std::memcpy(first_bad, hp + 32, 8);
     std::memcpy(err, hp + 40, 4);
     return BP_OK;
@@ -287,11 +324,13 @@ int check_err_word(bp_cs* h, const char* what) {
     char* hp = (char*)h->h_pinned_small;
     CU(h, cudaMemcpyAsync(hp + 40, h->d_err, 8, cudaMemcpyDeviceToHost, h->stream));  // [40,44) err, [44,48) GEN counter
     CU(h, cudaStreamSynchronize(h->stream));
+    h->caller_dma_pending = false;
     unsigned int e;
     std::memcpy(&e, hp + 40, 4);
     if (e & 2u) return fail(h, BP_E_RANGE, "%s: a field element is not canonical (>= p)", what);
     if (e & 4u) return fail(h, BP_E_RANGE, "%s: a variable index does not fit 28 bits", what);
     if (e & 1u) return fail(h, BP_E_RANGE, "%s: a column index is out of range", what);
+    if (e & 8u) return fail(h, BP_E_STATE, "%s: row offsets are not a non-decreasing sequence from 0 to nnz", what);
     return BP_OK;
 }
 
@@ -369,6 +408,7 @@ int ensure_plan(bp_cs* h) {
         if ((rc = ensure(h, h->fat_undecided, std::max<size_t>((size_t)h->n_fat_rows * 4, 4), 0)) != BP_OK) return rc;
     }
     h->plan_valid = true;
+    h->plan_gen++;
     return BP_OK;
 }
 
@@ -526,9 +566,6 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
         }
         const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;
         const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
-        cudaError_t ae = cudaSuccess;
-        DISPATCH_FIELD(h, (ae = cudaFuncSetAttribute(check_small<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem)));
-        CU(h, ae);
         DISPATCH_FIELD(h, (check_small<F, true><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, 0u,
                                                                                              0xffffffffu)));
         const int lgrid = grid_for(h, h->n_gen_rows + (uint64_t)h->sm_count * block, block, 16);
@@ -591,7 +628,6 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             if (use_small) {
                 const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;  // one warp per block of rows
                 const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
-                CU(h, cudaFuncSetAttribute(check_small<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
                 check_small<0, false><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, 0u,
                                                                                        0xffffffffu);
                 h->launches++;
@@ -616,6 +652,157 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
     }
 #undef BP_LAUNCH
     CU(h, cudaGetLastError());
+    return BP_OK;
+}
+
+
+// ---- multi-GPU group: row shards, replicated witness, one MIN over the ranks' first-unsatisfied rows -----------
+// NCCL is bound at run time (dlopen): a single-GPU user needs no NCCL, and inside a process that already loaded a
+// libnccl.so.2 (PyTorch bundles one) the same copy is used.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+const NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return nullptr;
+#define BP_NCCL_SYM(field, sym)                                         \
+    *(void**)(&api.field) = dlsym(api.lib, sym);                        \
+    if (!api.field) { api.lib = nullptr; return nullptr; }
+    BP_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    BP_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    BP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    BP_NCCL_SYM(Broadcast, "ncclBroadcast")
+    BP_NCCL_SYM(AllGather, "ncclAllGather")
+    BP_NCCL_SYM(AllReduce, "ncclAllReduce")
+    BP_NCCL_SYM(GroupStart, "ncclGroupStart")
+    BP_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    BP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef BP_NCCL_SYM
+    return &api;
+}
+
+}  // namespace
+
+constexpr int kMaxGroup = 16;
+
+struct bp_group {
+    bp_cs* cs = nullptr;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    // Peer-memory transport of the one-word reduction: every rank owns a mailbox of 2 x world slots (double-buffered by the
+    // parity of the exchange count) in its own HBM, exported to the other ranks by CUDA IPC.  One exchange = every rank
+    // stores its word into slot [parity][rank] of EVERY mailbox over NVLink (system-scope stores, then the epoch as the
+    // release flag) and takes the minimum over its own mailbox once all epochs have arrived: no NCCL launch, no host.
+    bp::GroupSlot* box = nullptr;             // my mailbox (device memory)
+    bp::GroupSlot** d_peer_boxes = nullptr;   // device array [world]: every rank's mailbox as mapped here ([rank] = box)
+    void* peer_mapped[kMaxGroup] = {};        // what cudaIpcOpenMemHandle returned (to close)
+    unsigned long long* d_epoch = nullptr;    // exchanges done so far (device counter: a captured graph needs no new argument)
+    bool mailbox = false;
+    long long* h_result = nullptr;            // pinned host copy of the last synchronous result
+};
+
+namespace {
+
+#define NC(h, api, call)                                                                                      \
+    do {                                                                                                      \
+        ncclResult_t r__ = (call);                                                                            \
+        if (r__ != ncclSuccess) return fail(h, BP_E_CUDA, "%s: %s", #call, (api)->GetErrorString(r__));         \
+    } while (0)
+
+// MIN over the group of the int64 at `word` (device memory), in place, on the handle's stream.
+int enqueue_reduce(bp_group* g, long long* word) {
+    bp_cs* h = g->cs;
+    if (g->world == 1) return BP_OK;
+    if (g->mailbox) {
+        group_exchange<<<1, 32, 0, h->stream>>>(word, g->d_peer_boxes, g->box, g->d_epoch, g->rank, g->world);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return BP_OK;
+    }
+    const NcclApi* api = nccl_api();
+    NC(h, api, api->AllReduce(word, word, 1, ncclInt64, ncclMin, g->comm, h->stream));
+    return BP_OK;
+}
+
+void drop_graph(bp_cs* h) {
+    if (h->graph.exec) {
+        cudaGraphExecDestroy(h->graph.exec);
+        h->graph.exec = nullptr;
+    }
+}
+
+// One check (and, for a group, the exchange that follows it) as a single graph launch.  The graph is captured from the very
+// same launch_check / enqueue_reduce code and replayed for as long as the kernels' arguments are what they were: the view
+// (every pointer, count and flag the kernels read), the result word, the plan, the variant.  Anything else re-captures.
+int check_graphed(bp_cs* h, long long* dev_first_bad, bp_group* g) {
+    const bool mailbox_or_single = !g || g->world == 1 || g->mailbox;  // (an NCCL all-reduce stays outside the graph)
+    if (!h->use_graph || h->n_rows == 0 || h->variant >= 100) {
+        int rc = launch_check(h, dev_first_bad, nullptr, nullptr, nullptr);
+        if (rc == BP_OK && g) rc = enqueue_reduce(g, dev_first_bad);
+        return rc;
+    }
+    int rc = ensure_plan(h);  // (synchronises when it has to rebuild: must not happen inside a capture)
+    if (rc != BP_OK) return rc;
+    const CsrView m = view(h);
+    auto& gc = h->graph;
+    const void* gkey = (g && mailbox_or_single) ? (const void*)g : nullptr;
+    if (gc.exec && std::memcmp(&gc.view, &m, sizeof m) == 0 && gc.out == dev_first_bad && gc.group == gkey && gc.variant == h->variant &&
+        gc.kernels_mask == h->kernels_mask && gc.plan_gen == h->plan_gen) {
+        CU(h, cudaGraphLaunch(gc.exec, h->stream));
+        h->launches += gc.launches;
+        h->graph_replays++;
+        if (g && !mailbox_or_single) return enqueue_reduce(g, dev_first_bad);
+        return BP_OK;
+    }
+    drop_graph(h);
+    const int64_t l0 = h->launches;
+    cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        rc = launch_check(h, dev_first_bad, nullptr, nullptr, nullptr);
+        if (rc == BP_OK && gkey) rc = enqueue_reduce(g, dev_first_bad);
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc == BP_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&gc.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+    }
+    const int64_t per_replay = h->launches - l0;
+    h->launches = l0;
+    if (rc != BP_OK || e != cudaSuccess || !gc.exec) {  // capture is an optimisation: fall back to plain launches for good
+        (void)cudaGetLastError();
+        gc.exec = nullptr;
+        h->use_graph = false;
+        rc = launch_check(h, dev_first_bad, nullptr, nullptr, nullptr);
+        if (rc == BP_OK && g) rc = enqueue_reduce(g, dev_first_bad);
+        return rc;
+    }
+    gc.view = m;
+    gc.out = dev_first_bad;
+    gc.group = gkey;
+    gc.variant = h->variant;
+    gc.kernels_mask = h->kernels_mask;
+    gc.plan_gen = h->plan_gen;
+    gc.launches = per_replay;
+    h->graph_captures++;
+    CU(h, cudaGraphLaunch(gc.exec, h->stream));
+    h->launches += gc.launches;
+    if (g && !mailbox_or_single) return enqueue_reduce(g, dev_first_bad);
     return BP_OK;
 }
 
@@ -664,6 +851,12 @@ int bp_cs_new(int field, int device, uint64_t reserve_rows, uint64_t reserve_nnz
         if (cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming) != cudaSuccess) return bail(BP_E_CUDA);
     }
     DISPATCH_FIELD(h, make_consts<F>(h->fc));
+    {  // check_small stages its term words in more than 48 KB of dynamic shared memory (set once: not inside captured regions)
+        cudaError_t ae = cudaFuncSetAttribute(check_small<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem);
+        DISPATCH_FIELD(h, { if (ae == cudaSuccess) ae = cudaFuncSetAttribute(check_small<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                              (int)kSmallSmem); });
+        if (ae != cudaSuccess) return bail(BP_E_CUDA);
+    }
     // inputs = [ONE]  (test_cs.rs:169, witness_cs.rs:95)
     const uint64_t one[4] = {1, 0, 0, 0};
     uint64_t idx = 0;
@@ -688,11 +881,15 @@ void bp_cs_free(bp_cs* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graph(h);
     for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->kexp, &h->inputs, &h->aux, &h->shadow, &h->scan_tmp, &h->scratch, &h->u8_stage,
                       &h->row_meta, &h->scols, &h->fat_rows, &h->gen_rows, &h->deferred, &h->fat_undecided})
         if (b->p) cudaFree(b->p);
     if (h->d_result) cudaFree(h->d_result);
     if (h->h_pinned_small) cudaFreeHost(h->h_pinned_small);
+    if (h->h_pack) cudaFreeHost(h->h_pack);
+    if (h->h_patch) cudaFreeHost(h->h_patch);
+    if (h->patch_stage.p) cudaFree(h->patch_stage.p);
     for (int s = 0; s < kNumStage; ++s) {
         if (h->h_stage[s]) cudaFreeHost(h->h_stage[s]);
         if (h->stage_ev[s]) cudaEventDestroy(h->stage_ev[s]);
@@ -737,24 +934,55 @@ int bp_cs_sync(bp_cs* h) {
 // validation pass that also rebuilds the shadows; the plan is rebuilt lazily as after any structural change.
 namespace {
 struct FileHeader {
-    char magic[8];  // "BPR1CS\0\1"
+    char magic[8];  // "BPR1CS\0\2"
     uint32_t abi, field;
+    uint32_t header_bytes, endian;  // sizeof(FileHeader); 0x01020304 as the writer's CPU stores it
     uint64_t n_rows, nnz, n_inputs, n_aux, n_gen, row_base;
 };
-const char kMagic[8] = {'B', 'P', 'R', '1', 'C', 'S', 0, 1};
+const char kMagic[8] = {'B', 'P', 'R', '1', 'C', 'S', 0, 2};
+constexpr uint32_t kEndianTag = 0x01020304u;
 
-int dump(bp_cs* h, FILE* f, const void* dev, size_t bytes) {
+// Payload checksum (the file ends with it): four interleaved 64-bit FNV-1a style lanes over the 8-byte words of everything
+// written after the header, folded at the end.  Every array's byte count is a multiple of 2; odd tails are zero-padded.
+struct Checksum {
+    uint64_t lane[4] = {0xcbf29ce484222325ull, 0x84222325cbf29ce4ull, 0x9e3779b97f4a7c15ull, 0xbf58476d1ce4e5b9ull};
+    uint64_t words = 0;
+    void add(const void* p, size_t bytes) {
+        const unsigned char* b = (const unsigned char*)p;
+        size_t i = 0;
+        for (; i + 8 <= bytes; i += 8) {
+            uint64_t w;
+            std::memcpy(&w, b + i, 8);
+            uint64_t& l = lane[words++ & 3];
+            l = (l ^ w) * 0x100000001b3ull;
+        }
+        if (i < bytes) {
+            uint64_t w = 0;
+            std::memcpy(&w, b + i, bytes - i);
+            uint64_t& l = lane[words++ & 3];
+            l = (l ^ w) * 0x100000001b3ull;
+        }
+    }
+    uint64_t value() const {
+        uint64_t h = words;
+        for (int i = 0; i < 4; ++i) h = (h ^ lane[i]) * 0x100000001b3ull;
+        return h;
+    }
+};
+
+int dump(bp_cs* h, FILE* f, const void* dev, size_t bytes, Checksum& ck) {
     size_t off = 0;
     while (off < bytes) {
         const size_t n = std::min(kStageBytes, bytes - off);
         CU(h, cudaMemcpyAsync(h->h_stage[0], (const char*)dev + off, n, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
+        ck.add(h->h_stage[0], n);
         if (fwrite(h->h_stage[0], 1, n, f) != n) return fail(h, BP_E_STATE, "short write");
         off += n;
     }
     return BP_OK;
 }
-int slurp(bp_cs* h, FILE* f, void* dev, size_t bytes) {
+int slurp(bp_cs* h, FILE* f, void* dev, size_t bytes, Checksum& ck) {
     size_t off = 0;
     while (off < bytes) {
         const int s = h->stage_next;
@@ -762,6 +990,7 @@ int slurp(bp_cs* h, FILE* f, void* dev, size_t bytes) {
         const size_t n = std::min(kStageBytes, bytes - off);
         CU(h, cudaEventSynchronize(h->stage_ev[s]));
         if (fread(h->h_stage[s], 1, n, f) != n) return fail(h, BP_E_STATE, "short read: truncated file");
+        ck.add(h->h_stage[s], n);
         CU(h, cudaMemcpyAsync((char*)dev + off, h->h_stage[s], n, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaEventRecord(h->stage_ev[s], h->stream));
         off += n;
@@ -785,17 +1014,23 @@ int bp_cs_save(bp_cs* h, const char* path) {
     FILE* f = fopen(path, "wb");
     if (!f) return fail(h, BP_E_STATE, "cannot open %s for writing", path);
     FileHeader hd;
+    std::memset(&hd, 0, sizeof hd);
     std::memcpy(hd.magic, kMagic, 8);
     hd.abi = BP_ABI_VERSION;
     hd.field = (uint32_t)h->field;
+    hd.header_bytes = (uint32_t)sizeof hd;
+    hd.endian = kEndianTag;
     hd.n_rows = h->n_rows; hd.nnz = h->nnz; hd.n_inputs = h->n_inputs; hd.n_aux = h->n_aux; hd.n_gen = h->n_gen; hd.row_base = h->row_base;
+    Checksum ck;
     int rc = fwrite(&hd, sizeof hd, 1, f) == 1 ? BP_OK : fail(h, BP_E_STATE, "short write");
-    if (rc == BP_OK) rc = dump(h, f, h->row_ptr.p, (3 * (size_t)h->n_rows + 1) * 4);
-    if (rc == BP_OK) rc = dump(h, f, h->cols.p, (size_t)h->nnz * 4);
-    if (rc == BP_OK) rc = dump(h, f, h->vals.p, (size_t)h->nnz * 32);
-    if (rc == BP_OK) rc = dump(h, f, h->kexp.p, (size_t)h->nnz * 2);
-    if (rc == BP_OK) rc = dump(h, f, h->inputs.p, (size_t)h->n_inputs * 32);
-    if (rc == BP_OK) rc = dump(h, f, h->aux.p, (size_t)h->n_aux * 32);
+    if (rc == BP_OK) rc = dump(h, f, h->row_ptr.p, (3 * (size_t)h->n_rows + 1) * 4, ck);
+    if (rc == BP_OK) rc = dump(h, f, h->cols.p, (size_t)h->nnz * 4, ck);
+    if (rc == BP_OK) rc = dump(h, f, h->vals.p, (size_t)h->nnz * 32, ck);
+    if (rc == BP_OK) rc = dump(h, f, h->kexp.p, (size_t)h->nnz * 2, ck);
+    if (rc == BP_OK) rc = dump(h, f, h->inputs.p, (size_t)h->n_inputs * 32, ck);
+    if (rc == BP_OK) rc = dump(h, f, h->aux.p, (size_t)h->n_aux * 32, ck);
+    const uint64_t sum = ck.value();
+    if (rc == BP_OK && fwrite(&sum, 8, 1, f) != 1) rc = fail(h, BP_E_STATE, "short write");
     if (fclose(f) != 0 && rc == BP_OK) rc = fail(h, BP_E_STATE, "close failed");
     return rc;
 }
@@ -806,8 +1041,10 @@ int bp_cs_load(const char* path, int device, bp_cs** out) {
     FILE* f = fopen(path, "rb");
     if (!f) return BP_E_STATE;
     FileHeader hd;
+    // not one of ours / another layout version / written on a CPU of the other byte order / counts this build cannot hold
     if (fread(&hd, sizeof hd, 1, f) != 1 || std::memcmp(hd.magic, kMagic, 8) != 0 || hd.abi != BP_ABI_VERSION || hd.field > 2 ||
-        hd.n_inputs < 1 || hd.nnz >= 0xffffffffull || 3 * hd.n_rows + 1 >= 0xffffffffull) {
+        hd.header_bytes != sizeof hd || hd.endian != kEndianTag || hd.n_inputs < 1 || hd.n_inputs > kColIdxMask || hd.n_aux > kColIdxMask ||
+        hd.nnz >= 0xffffffffull || 3 * hd.n_rows + 1 >= 0xffffffffull || hd.n_gen > hd.nnz) {
         fclose(f);
         return BP_E_ARG;
     }
@@ -834,13 +1071,21 @@ int bp_cs_load(const char* path, int device, bp_cs** out) {
     if ((rc = ensure(h, h->aux, std::max<size_t>((size_t)hd.n_aux * 32, 32), 0)) != BP_OK) return done(rc);
     h->n_inputs = h->n_aux = 0;  // nothing to carry over when the shadows are sized
     if ((rc = ensure_shadow(h, hd.n_inputs, hd.n_aux)) != BP_OK) return done(rc);
-    if ((rc = slurp(h, f, h->row_ptr.p, (3 * (size_t)hd.n_rows + 1) * 4)) != BP_OK) return done(rc);
-    if ((rc = slurp(h, f, h->cols.p, (size_t)hd.nnz * 4)) != BP_OK) return done(rc);
-    if ((rc = slurp(h, f, h->vals.p, (size_t)hd.nnz * 32)) != BP_OK) return done(rc);
-    if ((rc = slurp(h, f, h->kexp.p, (size_t)hd.nnz * 2)) != BP_OK) return done(rc);
-    if ((rc = slurp(h, f, h->inputs.p, (size_t)hd.n_inputs * 32)) != BP_OK) return done(rc);
-    if ((rc = slurp(h, f, h->aux.p, (size_t)hd.n_aux * 32)) != BP_OK) return done(rc);
+    Checksum ck;
+    if ((rc = slurp(h, f, h->row_ptr.p, (3 * (size_t)hd.n_rows + 1) * 4, ck)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->cols.p, (size_t)hd.nnz * 4, ck)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->vals.p, (size_t)hd.nnz * 32, ck)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->kexp.p, (size_t)hd.nnz * 2, ck)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->inputs.p, (size_t)hd.n_inputs * 32, ck)) != BP_OK) return done(rc);
+    if ((rc = slurp(h, f, h->aux.p, (size_t)hd.n_aux * 32, ck)) != BP_OK) return done(rc);
+    uint64_t sum = 0;
+    if (fread(&sum, 8, 1, f) != 1) return done(BP_E_STATE);
+    if (sum != ck.value()) return done(BP_E_STATE);  // corrupted payload: the kernels trust these offsets and class bits
     if ((rc = clear_err(h)) != BP_OK) return done(rc);
+    // the structure the kernels index with: row_ptr starts at 0, never decreases and ends at nnz
+    validate_row_ptr<<<grid_for(h, 3 * hd.n_rows + 1, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, 3 * hd.n_rows + 1,
+                                                                                     (uint32_t)hd.nnz, h->d_err);
+    h->launches++;
     for (int k = 0; k < 2; ++k) {
         const uint64_t n = k ? hd.n_aux : hd.n_inputs;
         if (!n) continue;
@@ -865,10 +1110,16 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
     if (!std::strcmp(key, "fat_ctas_per_sm")) {
         if (v < 1 || v > 32) return fail(h, BP_E_ARG, "fat_ctas_per_sm out of range");
         h->fat_ctas_per_sm = v;
+        drop_graph(h);  // (a launch dimension, not part of the graph key)
         return BP_OK;
     }
     if (!std::strcmp(key, "sparse_upload")) {
         h->sparse_upload = v != 0;
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "graph")) {
+        h->use_graph = v != 0;
+        if (!h->use_graph) drop_graph(h);
         return BP_OK;
     }
     if (!std::strcmp(key, "kernels_mask")) {
@@ -891,6 +1142,9 @@ int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
     if (!std::strcmp(key, "launches")) { *v = h->launches; return BP_OK; }
     if (!std::strcmp(key, "gen_terms")) { *v = (int64_t)h->n_gen; return BP_OK; }
     if (!std::strcmp(key, "sm_count")) { *v = h->sm_count; return BP_OK; }
+    if (!std::strcmp(key, "graph")) { *v = h->use_graph ? 1 : 0; return BP_OK; }
+    if (!std::strcmp(key, "graph_replays")) { *v = h->graph_replays; return BP_OK; }
+    if (!std::strcmp(key, "graph_captures")) { *v = h->graph_captures; return BP_OK; }
     // plan statistics (build the plan if needed): rows per kernel
     if (!std::strcmp(key, "fat_rows") || !std::strcmp(key, "plain_rows") || !std::strcmp(key, "generic_rows")) {
         CU(h, cudaSetDevice(h->device));
@@ -996,9 +1250,9 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
                               (const uint4*)((char*)b.p + first * 32), n, h->d_err, shadow_ptr(h, is_aux) + first)));
         h->launches++;
         CU(h, cudaGetLastError());
-        return BP_OK;
+        return settle(h);
     }
-    // bulk witness refresh: copy at link speed, validate on the device (on BP_E_RANGE the range's contents are unspecified)
+    // bulk witness refresh: copy at link speed, validate on the device; a rejected batch leaves the range ZERO (canonical)
     int rc = clear_err(h);
     if (rc != BP_OK) return rc;
     if ((rc = upload(h, (char*)b.p + first * 32, vals, (size_t)n * 32)) != BP_OK) return rc;
@@ -1006,7 +1260,15 @@ int bp_cs_set_range(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint
                                                                                           h->d_err, shadow_ptr(h, is_aux) + first)));
     h->launches++;
     CU(h, cudaGetLastError());
-    return check_err_word(h, "bp_cs_set_range");
+    rc = check_err_word(h, "bp_cs_set_range");
+    if (rc == BP_E_RANGE) {  // never leave values >= p behind: later checks assume canonical operands
+        const std::string msg = h->err;
+        CU(h, cudaMemsetAsync((char*)b.p + first * 32, 0, (size_t)n * 32, h->stream));
+        CU(h, cudaMemsetAsync(shadow_ptr(h, is_aux) + first, 0, (size_t)n * 4, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->err = msg + "; the range was zeroed";
+    }
+    return rc;
 }
 
 int bp_cs_set(bp_cs* h, int is_aux, uint64_t idx, const uint64_t v[4]) { return bp_cs_set_range(h, is_aux, idx, 1, v); }
@@ -1022,7 +1284,8 @@ static void launch_widen(bp_cs* h, bool bits, uint64_t stage_elem_off, uint64_t 
     h->launches++;
 }
 
-static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals, bool bits = false) {
+// sync_after: the synchronous entry points wait for copies that read the caller's pinned memory (settle)
+static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals, bool bits = false, bool sync_after = true) {
     if (bits) {  // small path only: element offsets inside the staging buffer are those of `vals`
         const size_t nbytes = (size_t)((n + 7) / 8);
         int rc = ensure(h, h->u8_stage, nbytes, 0);
@@ -1031,7 +1294,7 @@ static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const ui
         if ((rc = upload(h, h->u8_stage.p, vals, nbytes)) != BP_OK) return rc;
         launch_widen(h, true, 0, n, shadow_ptr(h, is_aux) + first);
         CU(h, cudaGetLastError());
-        return BP_OK;
+        return sync_after ? settle(h) : BP_OK;
     }
     int rc = ensure(h, h->u8_stage, (size_t)n, 0);
     if (rc != BP_OK) return rc;
@@ -1060,6 +1323,10 @@ static int widen_into(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const ui
         widen(0, n);
     }
     CU(h, cudaGetLastError());
+    if (sync_after) {
+        if (dma_able && n >= (8u << 20)) CU(h, cudaStreamSynchronize(h->stream));  // (the chunked copies went down the side stream)
+        return settle(h);
+    }
     return BP_OK;
 }
 
@@ -1078,24 +1345,24 @@ int bp_cs_alloc_u8(bp_cs* h, int is_aux, const uint8_t* vals, uint64_t n, uint64
     return BP_OK;
 }
 
-int bp_cs_set_range_u8(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals) {
-    if (!h || (!vals && n)) return BP_E_ARG;
+// Packed overwrite of [first, first+n) (one byte or one bit per value); the recheck entry points skip the final wait.
+static int set_range_packed(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals, bool bits, bool sync_after) {
     CU(h, cudaSetDevice(h->device));
     const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
-    if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "set_range_u8 [%llu,+%llu) exceeds %llu", (unsigned long long)first,
-                                                   (unsigned long long)n, (unsigned long long)cnt);
+    if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "set_range_%s [%llu,+%llu) exceeds %llu", bits ? "bits" : "u8",
+                                                   (unsigned long long)first, (unsigned long long)n, (unsigned long long)cnt);
     if (!n) return BP_OK;
-    return widen_into(h, is_aux, first, n, vals);
+    return widen_into(h, is_aux, first, n, vals, bits, sync_after);
+}
+
+int bp_cs_set_range_u8(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* vals) {
+    if (!h || (!vals && n)) return BP_E_ARG;
+    return set_range_packed(h, is_aux, first, n, vals, false, true);
 }
 
 int bp_cs_set_range_bits(bp_cs* h, int is_aux, uint64_t first, uint64_t n, const uint8_t* bits) {
     if (!h || (!bits && n)) return BP_E_ARG;
-    CU(h, cudaSetDevice(h->device));
-    const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
-    if (first > cnt || n > cnt - first) return fail(h, BP_E_RANGE, "set_range_bits [%llu,+%llu) exceeds %llu", (unsigned long long)first,
-                                                   (unsigned long long)n, (unsigned long long)cnt);
-    if (!n) return BP_OK;
-    return widen_into(h, is_aux, first, n, bits, true);
+    return set_range_packed(h, is_aux, first, n, bits, true, true);
 }
 
 int bp_cs_witness(bp_cs* h, int is_aux, uint64_t first, uint64_t n, uint64_t* out) {
@@ -1169,6 +1436,7 @@ int bp_cs_enforce(bp_cs* h, uint64_t n_rows, const uint32_t* lens, const uint32_
         }
     } else {
         CU(h, cudaGetLastError());
+        if ((rc = settle(h)) != BP_OK) return rc;  // (the lens may have been read straight from pinned caller memory)
     }
     h->n_rows += n_rows;
     h->nnz += add;
@@ -1179,13 +1447,13 @@ int bp_cs_enforce(bp_cs* h, uint64_t n_rows, const uint32_t* lens, const uint32_
 int bp_cs_check_async(bp_cs* h, int64_t* dev_result) {
     if (!h || !dev_result) return BP_E_ARG;
     CU(h, cudaSetDevice(h->device));
-    return launch_check(h, (long long*)dev_result, nullptr, nullptr, nullptr);
+    return check_graphed(h, (long long*)dev_result, nullptr);
 }
 
 int bp_cs_first_unsatisfied(bp_cs* h, int64_t* row) {
     if (!h || !row) return BP_E_ARG;
     CU(h, cudaSetDevice(h->device));
-    int rc = launch_check(h, h->d_result, nullptr, nullptr, nullptr);
+    int rc = check_graphed(h, h->d_result, nullptr);
     if (rc != BP_OK) return rc;
     long long fb;
     unsigned int e;
@@ -1199,7 +1467,7 @@ int bp_cs_first_unsatisfied(bp_cs* h, int64_t* row) {
 static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8, long long* dev_first_bad, bool bits = false) {
     CU(h, cudaSetDevice(h->device));
     int rc;
-    if (inputs_u8 && (rc = (bits ? bp_cs_set_range_bits : bp_cs_set_range_u8)(h, 0, 0, h->n_inputs, inputs_u8)) != BP_OK) return rc;
+    if (inputs_u8 && (rc = set_range_packed(h, 0, 0, h->n_inputs, inputs_u8, bits, false)) != BP_OK) return rc;
     const uint64_t n = h->n_aux;
     if ((rc = ensure_plan(h)) != BP_OK) return rc;
     cudaPointerAttributes at;
@@ -1224,7 +1492,7 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
                 launch_widen(h, bits, off, len, shadow_ptr(h, 1) + off);
             }
             CU(h, cudaGetLastError());
-        } else if (n && (rc = (bits ? bp_cs_set_range_bits : bp_cs_set_range_u8)(h, 1, 0, n, aux_u8)) != BP_OK) {
+        } else if (n && (rc = set_range_packed(h, 1, 0, n, aux_u8, bits, false)) != BP_OK) {
             return rc;
         }
         return launch_check(h, dev_first_bad, nullptr, nullptr, nullptr);
@@ -1243,7 +1511,6 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
     CheckOut o{dev_first_bad, h->d_err, nullptr, nullptr, nullptr};
     init_result<<<1, 1, 0, h->stream>>>(dev_first_bad, h->d_err, h->d_ndef);
     h->launches++;
-    CU(h, cudaFuncSetAttribute(check_small<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem));
     CU(h, cudaEventRecord(h->ev_fork, h->stream));
     CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     const uint32_t n_blocks = (uint32_t)((h->n_rows + kSmallRows - 1) / kSmallRows);
@@ -1450,6 +1717,445 @@ int bp_cs_synth_witness(bp_cs* h, uint64_t seed, uint64_t n_vars, uint64_t n_inp
     h->n_aux = n_vars - n_inputs;
     h->wide_valid = true;   // the whole witness was just written in both forms
     h->plan_valid = false;  // the plan vouches for column ranges
+    return BP_OK;
+}
+
+
+}  // extern "C"
+
+// ---- K4: batched set (test_cs.rs:270-282) ----------------------------------------------------------------------------------
+namespace {
+int ensure_pinned(bp_cs* h, void*& p, size_t& cap, size_t need) {
+    if (need <= cap) return BP_OK;
+    if (p) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    size_t want = std::max(need + need / 4, (size_t)4096);
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, BP_E_OOM, "cudaMallocHost(%zu bytes)", want);
+    }
+    cap = want;
+    return BP_OK;
+}
+
+bool limbs_below_p(const bp_cs* h, const uint64_t* v) {
+    uint32_t pl[8];
+    DISPATCH_FIELD(h, { for (int i = 0; i < 8; ++i) pl[i] = PL<F>(i); });
+    const uint32_t* x = (const uint32_t*)v;
+    for (int j = 7; j >= 0; --j) {
+        if (x[j] < pl[j]) return true;
+        if (x[j] > pl[j]) return false;
+    }
+    return false;
+}
+
+// n (index, value) pairs already in h_patch ([u32 idx x n, padded to 32 bytes][32-byte values x n]) -> device -> scatter
+int launch_patch(bp_cs* h, int is_aux, uint32_t n) {
+    if (!n) return BP_OK;
+    const size_t off_vals = ((size_t)n * 4 + 31) & ~size_t(31);
+    int rc = ensure(h, h->patch_stage, off_vals + (size_t)n * 32, 0);
+    if (rc != BP_OK) return rc;
+    CU(h, cudaMemcpyAsync(h->patch_stage.p, h->h_patch, off_vals + (size_t)n * 32, cudaMemcpyHostToDevice, h->stream));
+    patch_witness<<<grid_for(h, n, 256, 8), 256, 0, h->stream>>>((const uint32_t*)h->patch_stage.p, (const uint4*)((char*)h->patch_stage.p + off_vals),
+                                                               n, (uint4*)(is_aux ? h->aux.p : h->inputs.p), shadow_ptr(h, is_aux));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return BP_OK;
+}
+}  // namespace
+
+extern "C" int bp_cs_set_many(bp_cs* h, int is_aux, uint64_t n, const uint64_t* idx, const uint64_t* vals) {
+    if (!h || (n && (!idx || !vals))) return BP_E_ARG;
+    if (!n) return BP_OK;
+    if (n > 0x7fffffffull) return fail(h, BP_E_RANGE, "bp_cs_set_many: batch too large");
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
+    for (uint64_t i = 0; i < n; ++i) {  // validate everything first: a rejected batch changes nothing
+        if (idx[i] >= cnt) return fail(h, BP_E_RANGE, "bp_cs_set_many: index %llu >= %llu", (unsigned long long)idx[i], (unsigned long long)cnt);
+        if (!limbs_below_p(h, vals + 4 * i)) return fail(h, BP_E_RANGE, "bp_cs_set_many: element %llu is not canonical (>= p)", (unsigned long long)i);
+    }
+    const size_t off_vals = ((size_t)n * 4 + 31) & ~size_t(31);
+    CU(h, cudaStreamSynchronize(h->stream));  // (an earlier batch may still be on its way out of h_patch)
+    int rc = ensure_pinned(h, h->h_patch, h->h_patch_cap, off_vals + (size_t)n * 32);
+    if (rc != BP_OK) return rc;
+    uint32_t* pi = (uint32_t*)h->h_patch;
+    for (uint64_t i = 0; i < n; ++i) pi[i] = (uint32_t)idx[i];
+    std::memcpy((char*)h->h_patch + off_vals, vals, (size_t)n * 32);
+    return launch_patch(h, is_aux, (uint32_t)n);
+}
+
+// ---- same circuit, next witness, given as the reference holds it: 32-byte scalars (WitnessCS::input_assignment /
+// aux_assignment, witness_cs.rs:45-57) ---------------------------------------------------------------------------------------
+// The host packs before it sends: every value that is 0 or 1 becomes one bit, everything else goes to an exception list
+// (index + 32 bytes) that a scatter kernel applies after the bits have been widened.  A gadget witness of 10^8 bits is then
+// 14 MB of PCIe traffic instead of 3.5 GB; the packing pass (all host threads, one sequential read of the scalars) is the
+// cost of the call.  A witness with many non-bit values is sent as it is (bp_cs_set_range).
+extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result) {
+    if (!h || !dev_result || (!aux_le && h->n_aux)) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t n_in = inputs_le ? h->n_inputs : 0, n_aux = h->n_aux;
+    const size_t in_bytes = (size_t)((n_in + 7) / 8), aux_bytes = (size_t)((n_aux + 7) / 8);
+    const size_t aux_off = (in_bytes + 63) & ~size_t(63);
+    CU(h, cudaStreamSynchronize(h->stream));  // the pinned buffers of the previous call are free again
+    int rc = ensure_pinned(h, h->h_pack, h->h_pack_cap, aux_off + aux_bytes + 64);
+    if (rc != BP_OK) return rc;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char* e = getenv("BP_PACK_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+    nt = std::max(1u, std::min(nt, 64u));
+    struct Exc { uint64_t idx; uint64_t v[4]; };
+    uint8_t* bits_in = (uint8_t*)h->h_pack;
+    uint8_t* bits_aux = bits_in + aux_off;
+    std::vector<std::vector<Exc>> exc((size_t)nt * 2);
+    auto pack = [&](const uint64_t* src, uint64_t n, uint8_t* dst, unsigned t, std::vector<Exc>& out) {
+        // thread t takes the bytes [b0, b1) of the bit string, i.e. the elements [8*b0, min(8*b1, n))
+        const uint64_t nbytes = (n + 7) / 8, b0 = nbytes * t / nt, b1 = nbytes * (t + 1) / nt;
+        for (uint64_t b = b0; b < b1; ++b) {
+            uint8_t acc = 0;
+            const uint64_t e0 = 8 * b, e1 = std::min<uint64_t>(e0 + 8, n);
+            for (uint64_t i = e0; i < e1; ++i) {
+                const uint64_t* v = src + 4 * i;
+                if ((v[1] | v[2] | v[3]) == 0 && v[0] <= 1) {
+                    acc |= (uint8_t)(v[0] << (i - e0));
+                } else {
+                    out.push_back(Exc{i, {v[0], v[1], v[2], v[3]}});
+                }
+            }
+            dst[b] = acc;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t)
+            th.emplace_back([&, t] {
+                if (n_in) pack(inputs_le, n_in, bits_in, t, exc[2 * t]);
+                pack(aux_le, n_aux, bits_aux, t, exc[2 * t + 1]);
+            });
+        if (n_in) pack(inputs_le, n_in, bits_in, 0, exc[0]);
+        pack(aux_le, n_aux, bits_aux, 0, exc[1]);
+        for (auto& x : th) x.join();
+    }
+    size_t n_exc[2] = {0, 0};
+    for (unsigned t = 0; t < nt; ++t) {
+        n_exc[0] += exc[2 * t].size();
+        n_exc[1] += exc[2 * t + 1].size();
+    }
+    if (n_exc[0] + n_exc[1] > (n_in + n_aux) / 16 + 1024) {  // not a bit witness: send it as it is
+        if (n_in && (rc = bp_cs_set_range(h, 0, 0, n_in, inputs_le)) != BP_OK) return rc;
+        if (n_aux && (rc = bp_cs_set_range(h, 1, 0, n_aux, aux_le)) != BP_OK) return rc;
+        return check_graphed(h, (long long*)dev_result, nullptr);
+    }
+    for (int k = 0; k < 2; ++k)  // the exceptions must be field elements (the bits are by construction)
+        for (unsigned t = 0; t < nt; ++t)
+            for (const Exc& e : exc[2 * t + k])
+                if (!limbs_below_p(h, e.v))
+                    return fail(h, BP_E_RANGE, "bp_cs_recheck_scalars: %s element %llu is not canonical (>= p)", k ? "aux" : "input",
+                                (unsigned long long)e.idx);
+    if (n_in && (rc = set_range_packed(h, 0, 0, n_in, bits_in, true, false)) != BP_OK) return rc;
+    if (n_aux && (rc = set_range_packed(h, 1, 0, n_aux, bits_aux, true, false)) != BP_OK) return rc;
+    for (int k = 0; k < 2; ++k) {
+        const size_t n = n_exc[k];
+        if (!n) continue;
+        const size_t off_vals = (n * 4 + 31) & ~size_t(31);
+        CU(h, cudaStreamSynchronize(h->stream));  // (h_patch is reused for the second index space)
+        if ((rc = ensure_pinned(h, h->h_patch, h->h_patch_cap, off_vals + n * 32)) != BP_OK) return rc;
+        uint32_t* pi = (uint32_t*)h->h_patch;
+        uint64_t* pv = (uint64_t*)((char*)h->h_patch + off_vals);
+        size_t j = 0;
+        for (unsigned t = 0; t < nt; ++t)
+            for (const Exc& e : exc[2 * t + k]) {
+                pi[j] = (uint32_t)e.idx;
+                std::memcpy(pv + 4 * j, e.v, 32);
+                ++j;
+            }
+        if ((rc = launch_patch(h, k, (uint32_t)n)) != BP_OK) return rc;
+    }
+    return check_graphed(h, (long long*)dev_result, nullptr);
+}
+
+extern "C" int bp_cs_recheck_scalars(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row) {
+    if (!h || !row) return BP_E_ARG;
+    int rc = bp_cs_recheck_scalars_async(h, inputs_le, aux_le, (int64_t*)h->d_result);
+    if (rc != BP_OK) return rc;
+    long long fb;
+    unsigned int e;
+    if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;
+    if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
+    *row = fb == 0x7fffffffffffffffLL ? -1 : (int64_t)(fb - (long long)h->row_base);
+    return BP_OK;
+}
+
+extern "C" {
+
+// ---- multi-GPU group ----------------------------------------------------------------------------------------------------
+int bp_group_unique_id(uint8_t id[BP_GROUP_ID_BYTES]) {
+    if (!id) return BP_E_ARG;
+    const NcclApi* api = nccl_api();
+    if (!api) return BP_E_STATE;
+    static_assert(sizeof(ncclUniqueId) == BP_GROUP_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    if (api->GetUniqueId(&u) != ncclSuccess) return BP_E_CUDA;
+    std::memcpy(id, &u, sizeof u);
+    return BP_OK;
+}
+
+void bp_group_free(bp_group* g) {
+    if (!g) return;
+    bp_cs* h = g->cs;
+    if (h) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        if (h->graph.group == g) drop_graph(h);
+    }
+    for (int r = 0; r < g->world && r < kMaxGroup; ++r)
+        if (g->peer_mapped[r]) cudaIpcCloseMemHandle(g->peer_mapped[r]);
+    if (g->d_peer_boxes) cudaFree(g->d_peer_boxes);
+    if (g->box) cudaFree(g->box);
+    if (g->d_epoch) cudaFree(g->d_epoch);
+    if (g->h_result) cudaFreeHost(g->h_result);
+    if (g->comm) {
+        const NcclApi* api = nccl_api();
+        if (api) api->CommDestroy(g->comm);
+    }
+    (void)cudaGetLastError();
+    delete g;
+}
+
+int bp_group_init(bp_cs* h, const uint8_t id[BP_GROUP_ID_BYTES], int rank, int world, bp_group** out) {
+    if (!h || !out || world < 1 || world > kMaxGroup || rank < 0 || rank >= world || (world > 1 && !id)) return BP_E_ARG;
+    *out = nullptr;
+    CU(h, cudaSetDevice(h->device));
+    bp_group* g = new (std::nothrow) bp_group();
+    if (!g) return BP_E_OOM;
+    g->cs = h;
+    g->rank = rank;
+    g->world = world;
+    auto bail = [&](int code) {
+        bp_group_free(g);
+        return code;
+    };
+    if (cudaMallocHost((void**)&g->h_result, 64) != cudaSuccess) return bail(fail(h, BP_E_OOM, "cudaMallocHost"));
+    if (world == 1) {
+        *out = g;
+        return BP_OK;
+    }
+    const NcclApi* api = nccl_api();
+    if (!api) return bail(fail(h, BP_E_STATE, "libnccl.so.2 not found: a group of more than one rank needs NCCL"));
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof u);
+    {
+        ncclResult_t r = api->CommInitRank(&g->comm, world, u, rank);
+        if (r != ncclSuccess) return bail(fail(h, BP_E_CUDA, "ncclCommInitRank: %s", api->GetErrorString(r)));
+    }
+    // mailbox: allocate + zero, export, all-gather the IPC handles (the all-gather also orders every rank's memset before any
+    // peer's first store), map the peers.  Any failure on any rank -> everybody uses the NCCL all-reduce instead.
+    const size_t box_bytes = sizeof(GroupSlot) * 2 * world;
+    unsigned char* d_handles = nullptr;  // world x (64-byte handle + 8-byte ok flag), 128 bytes per rank
+    constexpr size_t kRec = 128;
+    bool ok = cudaMalloc((void**)&g->box, box_bytes) == cudaSuccess && cudaMalloc((void**)&g->d_epoch, 8) == cudaSuccess &&
+              cudaMalloc((void**)&g->d_peer_boxes, sizeof(GroupSlot*) * world) == cudaSuccess &&
+              cudaMalloc((void**)&d_handles, kRec * world) == cudaSuccess;
+    if (!ok) {
+        (void)cudaGetLastError();
+        if (d_handles) cudaFree(d_handles);
+        return bail(fail(h, BP_E_OOM, "group mailbox allocation"));
+    }
+    CU(h, cudaMemsetAsync(g->box, 0, box_bytes, h->stream));
+    CU(h, cudaMemsetAsync(g->d_epoch, 0, 8, h->stream));
+    unsigned char rec[kRec];
+    std::memset(rec, 0, sizeof rec);
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof mh <= 64, "cudaIpcMemHandle_t size");
+    uint64_t my_ok = cudaIpcGetMemHandle(&mh, g->box) == cudaSuccess ? 1 : 0;
+    if (!my_ok) (void)cudaGetLastError();
+    std::memcpy(rec, &mh, sizeof mh);
+    std::memcpy(rec + 64, &my_ok, 8);
+    CU(h, cudaMemcpyAsync(d_handles + kRec * rank, rec, kRec, cudaMemcpyHostToDevice, h->stream));
+    {
+        ncclResult_t r = api->AllGather(d_handles + kRec * rank, d_handles, kRec, ncclUint8, g->comm, h->stream);
+        if (r != ncclSuccess) {
+            cudaFree(d_handles);
+            return bail(fail(h, BP_E_CUDA, "ncclAllGather: %s", api->GetErrorString(r)));
+        }
+    }
+    std::vector<unsigned char> all(kRec * world);
+    CU(h, cudaMemcpyAsync(all.data(), d_handles, kRec * world, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::vector<GroupSlot*> peers(world, nullptr);
+    uint64_t mapped = 1;
+    for (int r = 0; r < world; ++r) {
+        uint64_t rok;
+        std::memcpy(&rok, all.data() + kRec * r + 64, 8);
+        if (!rok) { mapped = 0; continue; }
+        if (r == rank) { peers[r] = g->box; continue; }
+        cudaIpcMemHandle_t ph;
+        std::memcpy(&ph, all.data() + kRec * r, sizeof ph);
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            (void)cudaGetLastError();
+            mapped = 0;
+            continue;
+        }
+        g->peer_mapped[r] = p;
+        peers[r] = (GroupSlot*)p;
+    }
+    // everybody must agree on the transport: MIN over the ranks of "I mapped every peer" (reusing the handle buffer)
+    CU(h, cudaMemcpyAsync(d_handles, &mapped, 8, cudaMemcpyHostToDevice, h->stream));
+    {
+        ncclResult_t r = api->AllReduce(d_handles, d_handles, 1, ncclUint64, ncclMin, g->comm, h->stream);
+        if (r != ncclSuccess) {
+            cudaFree(d_handles);
+            return bail(fail(h, BP_E_CUDA, "ncclAllReduce: %s", api->GetErrorString(r)));
+        }
+    }
+    CU(h, cudaMemcpyAsync(&mapped, d_handles, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_handles);
+    g->mailbox = mapped != 0 && !getenv("BP_GROUP_NO_MAILBOX");
+    if (g->mailbox) CU(h, cudaMemcpyAsync(g->d_peer_boxes, peers.data(), sizeof(GroupSlot*) * world, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *out = g;
+    return BP_OK;
+}
+
+int bp_group_info(bp_group* g, int* rank, int* world, int* transport) {
+    if (!g) return BP_E_ARG;
+    if (rank) *rank = g->rank;
+    if (world) *world = g->world;
+    if (transport) *transport = g->world == 1 ? 0 : (g->mailbox ? 2 : 1);
+    return BP_OK;
+}
+
+int bp_group_reduce_async(bp_group* g, int64_t* dev_result) {
+    if (!g || !dev_result) return BP_E_ARG;
+    CU(g->cs, cudaSetDevice(g->cs->device));
+    return enqueue_reduce(g, (long long*)dev_result);
+}
+
+int bp_group_check_async(bp_group* g, int64_t* dev_result) {
+    if (!g || !dev_result) return BP_E_ARG;
+    CU(g->cs, cudaSetDevice(g->cs->device));
+    return check_graphed(g->cs, (long long*)dev_result, g);
+}
+
+int bp_group_check(bp_group* g, int64_t* row) {
+    if (!g || !row) return BP_E_ARG;
+    bp_cs* h = g->cs;
+    CU(h, cudaSetDevice(h->device));
+    int rc = check_graphed(h, h->d_result, g);
+    if (rc != BP_OK) return rc;
+    long long fb;
+    unsigned int e;
+    if ((rc = read_flags(h, &fb, &e)) != BP_OK) return rc;
+    if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
+    *row = fb == 0x7fffffffffffffffLL ? -1 : (int64_t)fb;  // GLOBAL row (row bases included), the same on every rank
+    return BP_OK;
+}
+
+// The witness of `root` replaces everybody's: inputs, aux and their shadows travel once over NVLink (ncclBroadcast); the
+// counts must agree (the witness is replicated).
+int bp_group_broadcast_witness(bp_group* g, int root) {
+    if (!g || root < 0 || root >= g->world) return BP_E_ARG;
+    bp_cs* h = g->cs;
+    CU(h, cudaSetDevice(h->device));
+    if (g->world == 1) return BP_OK;
+    const NcclApi* api = nccl_api();
+    // header: counts + wide_valid of the root, so that a mismatch is an error instead of a hang or a corrupted witness
+    unsigned long long hdr[4] = {h->n_inputs, h->n_aux, h->wide_valid ? 1ull : 0ull, 0ull};
+    int rc = ensure(h, h->scratch, 64, 0);
+    if (rc != BP_OK) return rc;
+    CU(h, cudaMemcpyAsync(h->scratch.p, hdr, 32, cudaMemcpyHostToDevice, h->stream));
+    NC(h, api, api->Broadcast(h->scratch.p, h->scratch.p, 32, ncclUint8, root, g->comm, h->stream));
+    unsigned long long got[4];
+    CU(h, cudaMemcpyAsync(got, h->scratch.p, 32, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // (every rank learns the verdict from the same header, so either all proceed or none does)
+    unsigned long long mine_ok = (got[0] == h->n_inputs && got[1] == h->n_aux) ? 1ull : 0ull;
+    CU(h, cudaMemcpyAsync(h->scratch.p, &mine_ok, 8, cudaMemcpyHostToDevice, h->stream));
+    NC(h, api, api->AllReduce(h->scratch.p, h->scratch.p, 1, ncclUint64, ncclMin, g->comm, h->stream));
+    CU(h, cudaMemcpyAsync(&mine_ok, h->scratch.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (!mine_ok) return fail(h, BP_E_STATE, "bp_group_broadcast_witness: the ranks hold different numbers of variables");
+    NC(h, api, api->GroupStart());
+    if (got[2]) {  // the 32-byte form is current on the root
+        NC(h, api, api->Broadcast(h->inputs.p, h->inputs.p, (size_t)h->n_inputs * 32, ncclUint8, root, g->comm, h->stream));
+        if (h->n_aux) NC(h, api, api->Broadcast(h->aux.p, h->aux.p, (size_t)h->n_aux * 32, ncclUint8, root, g->comm, h->stream));
+    }
+    NC(h, api, api->Broadcast(shadow_ptr(h, 0), shadow_ptr(h, 0), (size_t)h->n_inputs * 4, ncclUint8, root, g->comm, h->stream));
+    if (h->n_aux) NC(h, api, api->Broadcast(shadow_ptr(h, 1), shadow_ptr(h, 1), (size_t)h->n_aux * 4, ncclUint8, root, g->comm, h->stream));
+    NC(h, api, api->GroupEnd());
+    if (!got[2] && h->wide_valid) {
+        // the root's small values live in its shadows only; ours would now be stale where the shadow says "small"
+        h->wide_valid = false;
+    } else if (got[2]) {
+        h->wide_valid = true;
+    }
+    return BP_OK;
+}
+
+// Every rank uploads ONE SLICE of a new witness from its own host memory (rank r: elements [r*cnt/world, (r+1)*cnt/world) of
+// the index space; `slice` points at the first of them), the slices are all-gathered over NVLink, and the whole witness is
+// validated (canonical, shadows) everywhere: world PCIe links carry 1/world of the bytes each instead of every rank pulling
+// the whole witness through its own link.
+int bp_group_set_witness_sharded(bp_group* g, int is_aux, const uint64_t* slice) {
+    if (!g) return BP_E_ARG;
+    bp_cs* h = g->cs;
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t cnt = is_aux ? h->n_aux : h->n_inputs;
+    if (!cnt) return BP_OK;
+    DevBuf& b = is_aux ? h->aux : h->inputs;
+    const int W = g->world;
+    auto lo = [&](int r) { return (uint64_t)r * cnt / (uint64_t)W; };
+    const uint64_t my0 = lo(g->rank), my1 = lo(g->rank + 1);
+    if (my1 > my0 && !slice) return BP_E_ARG;
+    int rc = clear_err(h);
+    if (rc != BP_OK) return rc;
+    if (my1 > my0 && (rc = upload(h, (char*)b.p + my0 * 32, slice, (size_t)(my1 - my0) * 32)) != BP_OK) return rc;
+    if (W > 1) {
+        const NcclApi* api = nccl_api();
+        NC(h, api, api->GroupStart());
+        for (int r = 0; r < W; ++r) {
+            const uint64_t r0 = lo(r), r1 = lo(r + 1);
+            if (r1 > r0) NC(h, api, api->Broadcast((char*)b.p + r0 * 32, (char*)b.p + r0 * 32, (size_t)(r1 - r0) * 32, ncclUint8, r, g->comm, h->stream));
+        }
+        NC(h, api, api->GroupEnd());
+    }
+    DISPATCH_FIELD(h, (validate_canonical<F><<<grid_for(h, cnt, 256, 8), 256, 0, h->stream>>>((const uint4*)b.p, cnt, h->d_err,
+                                                                                            shadow_ptr(h, is_aux))));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    // (the other index space may still be shadow-only: wide_valid describes both, so it only goes up when that one is current)
+    rc = check_err_word(h, "bp_group_set_witness_sharded");
+    if (rc == BP_E_RANGE) {
+        const std::string msg = h->err;
+        CU(h, cudaMemsetAsync(b.p, 0, (size_t)cnt * 32, h->stream));
+        CU(h, cudaMemsetAsync(shadow_ptr(h, is_aux), 0, (size_t)cnt * 4, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->err = msg + "; the index space was zeroed";
+    }
+    return rc;
+}
+
+// Contiguous row shards balanced by TERMS: bounds[r] = first row of rank r, bounds[world] = n_rows.
+int bp_split_rows_by_nnz(const uint32_t* lens, uint64_t n_rows, int world, uint64_t* bounds) {
+    if (world < 1 || !bounds || (n_rows && !lens)) return BP_E_ARG;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < 3 * n_rows; ++i) total += lens[i];
+    total += n_rows;  // every row costs at least its offsets: keeps shards of empty rows apart
+    bounds[0] = 0;
+    uint64_t acc = 0, row = 0;
+    for (int r = 1; r < world; ++r) {
+        const uint64_t target = (uint64_t)((unsigned __int128)total * (unsigned)r / (unsigned)world);
+        while (row < n_rows && acc < target) {
+            acc += (uint64_t)lens[3 * row] + lens[3 * row + 1] + lens[3 * row + 2] + 1;
+            ++row;
+        }
+        bounds[r] = row;
+    }
+    bounds[world] = n_rows;
     return BP_OK;
 }
 

@@ -102,8 +102,14 @@ template <class Root> class Namespace {
     explicit Namespace(Root& r) : r_(&r) {}
     Namespace(const Namespace&) = delete;
     Namespace(Namespace&& o) noexcept : r_(o.r_) { o.r_ = nullptr; }
-    ~Namespace() {
-        if (r_) r_->pop_namespace();
+    // Never throws (a destructor that throws during unwinding is std::terminate): the stack cannot be empty here, since this
+    // object exists because of a push; a root whose stack was tampered with is left as it is.
+    ~Namespace() noexcept {
+        if (!r_) return;
+        try {
+            r_->pop_namespace();
+        } catch (...) {
+        }
     }
     static Variable one() { return one_var(); }
     const Field* field() { return r_->field(); }

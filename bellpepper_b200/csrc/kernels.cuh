@@ -692,7 +692,9 @@ __global__ void __launch_bounds__(kSmallThreads, 5) check_small(CsrView m, Check
                 if (any_plain) {
                     uint32_t* st = s_buf[wib][stage];
                     const uint32_t head = kb_cur & 3u, nt = ke_cur - kb_cur;
-                    const uint32_t len = ((ke_cur + 3u) & ~3u) - (kb_cur & ~3u);  // staged words (a multiple of 4)
+                    // staged words (a multiple of 4); nothing was copied for a block without terms (issue_copy), and the stage
+                    // must not be read then: its stale words would be used as shadow indices
+                    const uint32_t len = nt ? ((ke_cur + 3u) & ~3u) - (kb_cur & ~3u) : 0u;
                     // term words -> exclusive prefix sums of the contributions, in place; one more group holds the total
                     uint32_t carry = 0;
                     for (uint32_t t4 = 4u * lane; t4 - 4u * lane <= len; t4 += 128u) {
@@ -933,7 +935,10 @@ __device__ __forceinline__ void fold_lane_slow(uint32_t* acc, uint32_t k0, uint3
 // below 2^253 the difference is non-zero and smaller than p, so the row fails; anything else -- a full-width coefficient
 // that is not +-2^k, an operand >= 2^24, two wide LCs -- falls back to the modular path.  Per term: two coalesced loads
 // (column word, exponent byte), one 4-byte gather, ~20 instructions; the 32-byte coefficient is never read.
-constexpr uint32_t kIntMaxTerms = 16384;  // per LC: < 2^9 terms per lane, each < 2^55, so a lane's bucket cannot overflow
+// Per LC at most 4096 terms, i.e. 128 per lane.  One term adds less than 2^56 to a 64-bit bucket (two shifted operands
+// < 2^24 << 31 when both exponents fall into the same limb; a full-width coefficient adds < 2^32 per bucket and < 2^56 + 2^32
+// to bucket 7), so a lane's bucket stays below 128 * (2^56 + 2^32) < 2^64: no wrap, the sums are the exact integers.
+constexpr uint32_t kIntMaxTerms = 4096;
 __device__ __forceinline__ uint32_t bk_slot(uint32_t j, uint32_t lane) { return j * 33u + lane; }  // (33: conflict-free column reads)
 constexpr uint32_t kBucketWords = 16u * 33u;  // u64 per warp
 
@@ -1282,6 +1287,48 @@ __global__ void init_result(long long* first_bad, unsigned int* err, uint32_t* n
     if (n_deferred) { n_deferred[0] = 0; n_deferred[1] = 0; }  // thin rows deferred by check_small, fat rows left by check_fat_int
 }
 
+// ---- multi-GPU: the one-word MIN over the ranks, through peer-mapped mailboxes (no NCCL launch, no host) ------------------
+// Every rank owns a mailbox of 2 x world slots in its own HBM; `boxes[r]` is rank r's mailbox as mapped into this process
+// (CUDA IPC over NVLink; boxes[rank] is the local one).  Exchange number e (a device-side counter, the same on every rank
+// because the call is collective) uses the slots of parity e & 1: lane j stores this rank's word into slot [e&1][rank] of
+// rank j's mailbox -- the value, a system-scope fence, then the epoch as the release flag -- and waits until slot [e&1][j] of
+// its OWN mailbox carries epoch e, i.e. until rank j's word has arrived.  Parity is enough: a rank cannot start exchange e+2
+// before every other rank has finished reading exchange e (its e+1 needs their e+1, which they only start after their e).
+struct GroupSlot {
+    long long value;
+    unsigned long long epoch;
+};
+__global__ void group_exchange(long long* word, GroupSlot* const* __restrict__ boxes, GroupSlot* my_box, unsigned long long* epoch_ctr, int rank,
+                               int world) {
+    const int j = threadIdx.x;
+    const unsigned long long e = *epoch_ctr + 1ull;
+    const int par = (int)(e & 1ull);
+    const long long mine = *word;
+    __syncwarp();
+    long long got = 0x7fffffffffffffffLL;
+    if (j < world) {
+        GroupSlot* dst = boxes[j] + par * world + rank;
+        asm volatile("st.volatile.global.s64 [%0], %1;" ::"l"(&dst->value), "l"(mine) : "memory");
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
+        const GroupSlot* src = my_box + par * world + j;
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&src->epoch) : "memory");
+        } while (seen != e);
+        asm volatile("ld.volatile.global.s64 %0, [%1];" : "=l"(got) : "l"(&src->value) : "memory");
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const long long o = __shfl_xor_sync(0xffffffffu, got, d);
+        got = o < got ? o : got;
+    }
+    if (j == 0) {
+        *word = got;
+        *epoch_ctr = e;
+    }
+}
+
 // ---- K3: ingest conversion ------------------------------------------------------------------------------------------------
 // Pass 1, one thread per LC of the chunk: an A/B LC is "plain" when every coefficient is a small signed integer and the
 // magnitudes sum to <= 7 (so its value stays below 8p); C LCs are classed per term.  kind: 0 = general, 1 = plain.
@@ -1370,6 +1417,31 @@ template <int F> __global__ void validate_canonical(const uint4* __restrict__ v,
         if (!is_canonical<F>(x)) atomicOr(err, 2u);
         shadow[i] = shadow_of(x);
     }
+}
+
+// K4 witness_patch: scatter n updated elements (test_cs.rs:270-282 `set`, batched): element idx[i] of one index space becomes
+// vals[i] in both forms (32-byte element, shadow).  The host has validated the indices and values.
+__global__ void patch_witness(const uint32_t* __restrict__ idx, const uint4* __restrict__ vals, uint32_t n, uint4* __restrict__ elems,
+                              uint32_t* __restrict__ shadow) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t x[8];
+        ld8(x, vals + 2 * (size_t)i);
+        const uint32_t k = idx[i];
+        st8(elems + 2 * (size_t)k, x);
+        shadow[k] = shadow_of(x);
+    }
+}
+
+// bp_cs_load: the offsets every kernel indexes with.  err bit 3: row_ptr[0] != 0, a decrease, or row_ptr[last] != nnz.
+__global__ void validate_row_ptr(const uint32_t* __restrict__ row_ptr, uint64_t n /*entries*/, uint32_t nnz, unsigned int* err) {
+    bool bad = false;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = row_ptr[i];
+        if (i == 0 && v != 0u) bad = true;
+        if (i + 1 == n && v != nnz) bad = true;
+        if (i + 1 < n && row_ptr[i + 1] < v) bad = true;
+    }
+    if (bad) atomicOr(err, 8u);
 }
 
 // Packed witness upload (bp_cs_alloc_u8 / bp_cs_set_range_u8 / bp_cs_recheck_u8): element i = bytes[i].  Only the shadow is

@@ -50,6 +50,19 @@ SIGNATURES = {
     "bp_cs_sync": (ctypes.c_int, [vp]),
     "bp_cs_set_option": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_int64]),
     "bp_cs_get_option": (ctypes.c_int, [vp, ctypes.c_char_p, i64p]),
+    "bp_cs_set_many": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, vp, vp]),
+    "bp_cs_recheck_scalars": (ctypes.c_int, [vp, vp, vp, i64p]),
+    "bp_cs_recheck_scalars_async": (ctypes.c_int, [vp, vp, vp, vp]),
+    "bp_group_unique_id": (ctypes.c_int, [vp]),
+    "bp_group_init": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
+    "bp_group_free": (None, [vp]),
+    "bp_group_info": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "bp_group_check": (ctypes.c_int, [vp, i64p]),
+    "bp_group_check_async": (ctypes.c_int, [vp, vp]),
+    "bp_group_reduce_async": (ctypes.c_int, [vp, vp]),
+    "bp_group_broadcast_witness": (ctypes.c_int, [vp, ctypes.c_int]),
+    "bp_group_set_witness_sharded": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+    "bp_split_rows_by_nnz": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_int, u64p]),
     "bp_cs_synth_rows": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),
     "bp_cs_synth_witness": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),
 }

@@ -22,7 +22,8 @@
  *    boundary.  bp_cs_last_error() gives the message for the handle's last failure.
  *  - A handle is thread-compatible, not thread-safe (`ConstraintSystem: Send`, all mutation through
  *    `&mut self`).  Every call selects the handle's device itself; no reliance on the caller's current
- *    CUDA device.  The caller owns every buffer it passes; the library copies before returning.
+ *    CUDA device.  The caller owns every buffer it passes; the library copies before returning (the *_async and
+ *    bp_cs_recheck_* entry points say where a buffer must instead stay valid until the stream has consumed it).
  *  - There is no CPU fallback: without a usable CUDA device bp_cs_new fails with BP_E_CUDA.
  */
 #ifndef BP_R1CS_H
@@ -81,7 +82,9 @@ int bp_cs_set(bp_cs* cs, int is_aux, uint64_t idx, const uint64_t v[4]);
 int bp_cs_get(bp_cs* cs, int is_aux, uint64_t idx, uint64_t v[4]);
 
 /* Bulk overwrite of an existing range [first, first+n): SizedWitness::generate_witness_into
- * (witness_cs.rs:12, 28-40) writing into the slices returned by allocate_empty. */
+ * (witness_cs.rs:12, 28-40) writing into the slices returned by allocate_empty.  Up to 4096 elements are validated on
+ * the host first (a rejected value leaves the witness untouched); larger batches are validated on the device after the
+ * copy, and a batch holding a value >= p is rejected with BP_E_RANGE and leaves the whole range ZERO. */
 int bp_cs_set_range(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, const uint64_t* vals_le);
 
 /* Packed form of bp_cs_set_range (see bp_cs_alloc_u8). */
@@ -123,6 +126,20 @@ int bp_cs_set_range_bits(bp_cs* cs, int is_aux, uint64_t first, uint64_t n, cons
 int bp_cs_recheck_bits(bp_cs* cs, const uint8_t* inputs_bits, const uint8_t* aux_bits, int64_t* row);
 int bp_cs_recheck_bits_async(bp_cs* cs, const uint8_t* inputs_bits, const uint8_t* aux_bits, int64_t* dev_result);
 
+/* Batched `set` (test_cs.rs:270-282; the 255 x 2 x 200 set-and-recheck loop of num.rs:753-762): element idx[i] of one index
+ * space becomes vals[4i..4i+4) for i < n, by one copy and one scatter kernel.  Indices and values are validated first: a
+ * rejected batch (BP_E_RANGE) changes nothing.  Later entries win when an index repeats. */
+int bp_cs_set_many(bp_cs* cs, int is_aux, uint64_t n, const uint64_t* idx, const uint64_t* vals_le);
+
+/* Same circuit, next witness, in the REFERENCE's own format: 32-byte canonical scalars, n_inputs (incl. ONE; NULL keeps the
+ * inputs) and n_aux of them -- what WitnessCS holds (witness_cs.rs:45-57: input_assignment / aux_assignment).  The library
+ * packs on the host before it sends (every 0/1 value becomes one bit, anything else an (index, value) exception applied by a
+ * scatter kernel), so a gadget witness of 10^8 bits costs 14 MB of PCIe traffic instead of 3.5 GB; a witness that is not
+ * mostly bits is sent as it is.  Then which_is_unsatisfied.  The _async form leaves the first failing GLOBAL row in DEVICE
+ * memory (INT64_MAX = satisfied); the scalars are consumed before either form returns. */
+int bp_cs_recheck_scalars(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row);
+int bp_cs_recheck_scalars_async(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result);
+
 /* Same check, asynchronous: enqueue on the handle's stream and leave the result in DEVICE memory as one
  * int64 (first failing GLOBAL row = row_base + local row; INT64_MAX when satisfied) so that a row-sharded
  * multi-GPU caller can min-all-reduce it without a host round trip.  No host synchronisation. */
@@ -140,8 +157,11 @@ int bp_cs_eval_lc(bp_cs* cs, const uint32_t* cols, const uint64_t* coeffs_le, ui
 /* ---- checkpoint / resume ---------------------------------------------------------------------------
  * Not a reference interface (LinearCombination is not serialisable there, lc.rs:34): write an ingested system -- matrices in
  * their device-internal form, canonical witness, row base -- to a file, and create a handle from such a file, so that a
- * 10^8-row synthesis is paid once.  bp_cs_load returns BP_E_ARG for a file that is not one of ours (magic / ABI version),
- * BP_E_STATE for an unreadable or truncated one, BP_E_RANGE when its witness is not canonical. */
+ * 10^8-row synthesis is paid once.  The header records its own size, the writer's byte order and the counts; the file
+ * ends with a 64-bit checksum of the payload.  bp_cs_load returns BP_E_ARG for a file that is not one of ours (magic /
+ * layout / ABI version / byte order / counts out of range), BP_E_STATE for an unreadable, truncated or corrupted one
+ * (checksum mismatch, row offsets that are not a non-decreasing sequence from 0 to nnz), BP_E_RANGE when its witness is
+ * not canonical. */
 int bp_cs_save(bp_cs* cs, const char* path);
 int bp_cs_load(const char* path, int device, bp_cs** out);
 
@@ -159,12 +179,51 @@ int bp_cs_sync(bp_cs* cs);
  * Tuning / introspection knobs: "fat_terms" (rows with more terms use the warp-per-row kernel; default 96);
  * "variant" (-1 = default; else bit 0: no small-operand kernel, bit 1: no witness shadows in the warp-per-row kernel,
  * bit 2: park A.w/B.w in shared memory, bit 3: no integer pass over the fat rows -- every variant returns the same
- * results, the parity tests run them all);
+ * results, the parity tests run them all); "graph" (default 1: a check is replayed as one captured CUDA graph while its
+ * arguments are unchanged; read-only "graph_replays" / "graph_captures");
  * read-only: "launches" (kernels launched so far), "plain_rows" / "generic_rows" / "fat_rows" (rows per kernel),
  * "deferred_rows" / "fat_undecided_rows" (plain / fat rows the last check sent on to the full-width kernels), "gen_terms",
  * "sm_count". */
 int bp_cs_set_option(bp_cs* cs, const char* key, int64_t value);
 int bp_cs_get_option(bp_cs* cs, const char* key, int64_t* value);
+
+/* ---- multi-GPU: row shards on several GPUs of one node (one process per GPU) -------------------------------
+ * Not a reference interface (the reference is single-threaded); the hooks it would sit behind are `extend`
+ * (constraint_system.rs:138-148: sub-systems synthesized independently, concatenated in order) and the bulk witness
+ * ingress of `WitnessCS` (witness_cs.rs:171-193).  Rows are independent (test_cs.rs:240-250), so every rank holds a
+ * contiguous row range (bp_cs_set_row_base) and the WHOLE witness; the only exchange of a check is one MIN over the
+ * ranks' first-unsatisfied GLOBAL rows.  Inside the library that MIN does not launch a collective: the kernels leave the
+ * word in device memory and a one-warp kernel publishes it with system-scope stores into every peer's mailbox
+ * (peer memory mapped with CUDA IPC over NVLink) and reads the other ranks' words from its own; check + exchange replay as
+ * ONE captured CUDA graph.  NCCL (bound at run time) is used to create the group, to move witnesses, and as the
+ * fallback transport when peer mapping is unavailable.
+ *
+ * All bp_group_* calls are collective: every rank of the group makes the same calls in the same order. */
+typedef struct bp_group bp_group;
+#define BP_GROUP_ID_BYTES 128
+/* Rank 0 creates the id (an ncclUniqueId) and hands it to the other ranks by any channel it likes. */
+int bp_group_unique_id(uint8_t id[BP_GROUP_ID_BYTES]);
+/* Join `cs` (this rank's row shard) to the group.  world == 1 is valid (id may be NULL) and needs no NCCL. */
+int bp_group_init(bp_cs* cs, const uint8_t id[BP_GROUP_ID_BYTES], int rank, int world, bp_group** out);
+void bp_group_free(bp_group* g);
+/* *transport: 0 = single rank, 1 = NCCL all-reduce, 2 = peer-memory mailboxes. */
+int bp_group_info(bp_group* g, int* rank, int* world, int* transport);
+/* which_is_unsatisfied over ALL shards (test_cs.rs:239-253): *row = the first unsatisfied GLOBAL row or -1, the same
+ * value on every rank. */
+int bp_group_check(bp_group* g, int64_t* row);
+/* Same, asynchronous: the reduced word (INT64_MAX = satisfied) is left in DEVICE memory on the handle's stream. */
+int bp_group_check_async(bp_group* g, int64_t* dev_result);
+/* Just the exchange: MIN over the ranks of the int64 at dev_result, in place (after any *_async producer). */
+int bp_group_reduce_async(bp_group* g, int64_t* dev_result);
+/* "Witness broadcast once": the witness held by `root` (inputs, aux) replaces every rank's, over NVLink. */
+int bp_group_broadcast_witness(bp_group* g, int root);
+/* New witness from host memory with every PCIe link carrying 1/world of it: rank r passes the elements
+ * [r*cnt/world, (r+1)*cnt/world) of the index space (`slice` = the first of them; cnt = current size of the space); the
+ * slices are all-gathered over NVLink and validated everywhere.  A value >= p: BP_E_RANGE, the index space is zeroed. */
+int bp_group_set_witness_sharded(bp_group* g, int is_aux, const uint64_t* slice_le);
+/* Contiguous row shards balanced by TERMS, not rows (gadget circuits are skewed by their MultiEq rows): lens as for
+ * bp_cs_enforce; bounds[r] = first row of rank r, bounds[world] = n_rows.  Host-side helper, no device needed. */
+int bp_split_rows_by_nnz(const uint32_t* lens, uint64_t n_rows, int world, uint64_t* bounds);
 
 /* ---- measurement fixture: synthetic instances generated in HBM ----------------------------------------
  * Not a reference interface.  Appends rows [row0, row0+n_rows) of the counter-based synthetic R1CS

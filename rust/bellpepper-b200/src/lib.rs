@@ -8,9 +8,14 @@
 //!                               (tagged u32 column, 32-byte little-endian `to_repr()`) and flushed with `bp_cs_enforce`
 //!   * `which_is_unsatisfied` -> `bp_cs_first_unsatisfied`, row mapped back to its path
 //!
+//! The accessors take `&self` exactly like the reference's (`which_is_unsatisfied`, `is_satisfied`, `get`:
+//! test_cs.rs:239, 255, 311), so reference tests that call them on an immutable binding compile unchanged; the staging
+//! buffers they may have to flush sit behind a `RefCell`.
+//!
 //! NOT COMPILED in this repository (no Rust toolchain in the build image); kept in sync with include/bp_r1cs.h.
 pub mod ffi;
 
+use std::cell::RefCell;
 use std::collections::HashMap;
 use std::ffi::CStr;
 use std::marker::PhantomData;
@@ -18,10 +23,18 @@ use std::marker::PhantomData;
 use bellpepper_core::{ConstraintSystem, Index, LinearCombination, SynthesisError, Variable};
 use ff::PrimeField;
 
-/// Which of the three supported scalar fields `Scalar` is (checked against `Scalar::MODULUS` at construction).
+/// Which of the three supported scalar fields `Scalar` is.  `new_on` asserts that `Scalar::MODULUS` is the modulus the
+/// library uses for that id, so a wrong id cannot silently evaluate in another field.
 pub trait B200Field: PrimeField {
     const FIELD_ID: i32;
 }
+
+/// `PrimeField::MODULUS` (hex, `0x` prefix, big-endian) of the field each id stands for (include/bp_r1cs.h).
+const MODULI: [&str; 3] = [
+    "73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001", // BP_FIELD_BLS12_381_FR
+    "40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001", // BP_FIELD_PALLAS_FR (pasta Fq)
+    "40000000000000000000000000000000224698fc094cf91b992d30ed00000001", // BP_FIELD_VESTA_FR  (pasta Fp)
+];
 
 #[derive(Debug)]
 enum NamedObject {
@@ -37,16 +50,23 @@ pub struct B200ConstraintSystem<Scalar: B200Field> {
     constraint_paths: Vec<String>,
     input_names: Vec<String>,
     aux_names: Vec<String>,
-    // pending (not yet flushed) witness values, packed: one byte per value that fits a byte (AllocatedBit / Boolean
-    // witnesses, i.e. nearly everything a gadget circuit allocates); a value that does not fit leaves a 0 placeholder and
-    // goes to `pend_wide` as (position in pend_bytes, limbs), patched with bp_cs_set after the batch is appended
-    pend_bytes: [Vec<u8>; 2],
-    pend_wide: [Vec<(u64, [u64; 4])>; 2],
     count: [u64; 2],
+    // Staging buffers.  They sit behind a RefCell because the reference's accessors take `&self`
+    // (`which_is_unsatisfied`, `is_satisfied`, `get`: test_cs.rs:239, 255, 311) and must still be able to flush.
+    pend: RefCell<Pending>,
+    _s: PhantomData<Scalar>,
+}
+
+/// Pending (not yet flushed) data.  Witness values are packed: one byte per value that fits a byte (AllocatedBit / Boolean
+/// witnesses, i.e. nearly everything a gadget circuit allocates); a value that does not fit leaves a 0 placeholder and goes
+/// to `wide` as (position in `bytes`, limbs), patched with bp_cs_set after the batch is appended.
+#[derive(Default)]
+struct Pending {
+    bytes: [Vec<u8>; 2],
+    wide: [Vec<(u64, [u64; 4])>; 2],
     lens: Vec<u32>,
     cols: Vec<u32>,
     coeffs: Vec<u64>,
-    _s: PhantomData<Scalar>,
 }
 
 // The handle is thread-compatible (no TLS, every call selects its device): `ConstraintSystem: Send` holds.
@@ -85,8 +105,15 @@ fn compute_path(ns: &[String], this: &str) -> String {
 
 impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
     pub fn new_on(device: i32) -> Self {
+        let id = Scalar::FIELD_ID;
+        assert!((0..3).contains(&id), "unknown B200Field::FIELD_ID {id}");
+        assert!(
+            Scalar::MODULUS.trim_start_matches("0x").eq_ignore_ascii_case(MODULI[id as usize]),
+            "B200Field::FIELD_ID {id} does not name the field whose modulus is {}",
+            Scalar::MODULUS
+        );
         let mut h = std::ptr::null_mut();
-        let rc = unsafe { ffi::bp_cs_new(Scalar::FIELD_ID, device, 0, 0, 0, &mut h) };
+        let rc = unsafe { ffi::bp_cs_new(id, device, 0, 0, 0, &mut h) };
         assert_eq!(rc, ffi::BP_OK, "bp_cs_new failed ({rc}): no CUDA device? there is no CPU fallback");
         let mut named_objects = HashMap::new();
         named_objects.insert("ONE".into(), NamedObject::Var(Self::one()));
@@ -97,12 +124,8 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
             constraint_paths: vec![],
             input_names: vec!["ONE".into()],
             aux_names: vec![],
-            pend_bytes: [vec![], vec![]],
-            pend_wide: [vec![], vec![]],
             count: [1, 0],
-            lens: vec![],
-            cols: vec![],
-            coeffs: vec![],
+            pend: RefCell::new(Pending::default()),
             _s: PhantomData,
         }
     }
@@ -114,44 +137,44 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
         }
     }
 
-    pub fn flush(&mut self) {
+    /// Send everything staged so far to the device (`&self`: see `pend`).
+    pub fn flush(&self) {
+        let mut p = self.pend.borrow_mut();
         for k in 0..2 {
-            if !self.pend_bytes[k].is_empty() {
-                let n = self.pend_bytes[k].len() as u64;
+            if !p.bytes[k].is_empty() {
+                let n = p.bytes[k].len() as u64;
                 let mut first = 0u64;
-                let rc = unsafe { ffi::bp_cs_alloc_u8(self.h, k as i32, self.pend_bytes[k].as_ptr(), n, &mut first) };
+                let rc = unsafe { ffi::bp_cs_alloc_u8(self.h, k as i32, p.bytes[k].as_ptr(), n, &mut first) };
                 self.check(rc);
-                for (pos, limbs) in std::mem::take(&mut self.pend_wide[k]) {
+                for (pos, limbs) in std::mem::take(&mut p.wide[k]) {
                     let rc = unsafe { ffi::bp_cs_set(self.h, k as i32, first + pos, limbs.as_ptr()) };
                     self.check(rc);
                 }
-                self.pend_bytes[k].clear();
+                p.bytes[k].clear();
             }
         }
-        if !self.lens.is_empty() {
-            let rc = unsafe {
-                ffi::bp_cs_enforce(self.h, (self.lens.len() / 3) as u64, self.lens.as_ptr(), self.cols.as_ptr(), self.coeffs.as_ptr())
-            };
+        if !p.lens.is_empty() {
+            let rc = unsafe { ffi::bp_cs_enforce(self.h, (p.lens.len() / 3) as u64, p.lens.as_ptr(), p.cols.as_ptr(), p.coeffs.as_ptr()) };
             self.check(rc);
-            self.lens.clear();
-            self.cols.clear();
-            self.coeffs.clear();
+            p.lens.clear();
+            p.cols.clear();
+            p.coeffs.clear();
         }
     }
 
-    fn push_lc(&mut self, lc: &LinearCombination<Scalar>) {
+    fn push_lc(p: &mut Pending, lc: &LinearCombination<Scalar>) {
         let mut n = 0u32;
         for (i, c) in lc.iter_inputs() {
-            self.cols.push(*i as u32);
-            repr_to_limbs(c, &mut self.coeffs);
+            p.cols.push(*i as u32);
+            repr_to_limbs(c, &mut p.coeffs);
             n += 1;
         }
         for (i, c) in lc.iter_aux() {
-            self.cols.push(*i as u32 | ffi::BP_COL_AUX);
-            repr_to_limbs(c, &mut self.coeffs);
+            p.cols.push(*i as u32 | ffi::BP_COL_AUX);
+            repr_to_limbs(c, &mut p.coeffs);
             n += 1;
         }
-        self.lens.push(n);
+        p.lens.push(n);
     }
 
     fn set_named_obj(&mut self, path: String, to: NamedObject) {
@@ -160,7 +183,7 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
     }
 
     /// test_cs.rs:239-253
-    pub fn which_is_unsatisfied(&mut self) -> Option<&str> {
+    pub fn which_is_unsatisfied(&self) -> Option<&str> {
         self.flush();
         let mut row = 0i64;
         let rc = unsafe { ffi::bp_cs_first_unsatisfied(self.h, &mut row) };
@@ -169,7 +192,7 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
     }
 
     /// test_cs.rs:255-264
-    pub fn is_satisfied(&mut self) -> bool {
+    pub fn is_satisfied(&self) -> bool {
         match self.which_is_unsatisfied() {
             Some(b) => {
                 println!("fail: {:?}", b);
@@ -245,7 +268,7 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
     }
 
     /// test_cs.rs:311-323
-    pub fn get(&mut self, path: &str) -> Scalar {
+    pub fn get(&self, path: &str) -> Scalar {
         let (is_aux, idx) = match self.var_at(path).get_unchecked() {
             Index::Input(i) => (0, i),
             Index::Aux(i) => (1, i),
@@ -284,7 +307,10 @@ impl<Scalar: B200Field> ConstraintSystem<Scalar> for B200ConstraintSystem<Scalar
         let index = self.count[1] as usize;
         let path = compute_path(&self.current_namespace, &annotation().into());
         let value = f()?; // an Err leaves no variable behind (test_cs.rs:388)
-        stage_value(&value, &mut self.pend_bytes[1], &mut self.pend_wide[1]);
+        {
+            let p = self.pend.get_mut();
+            stage_value(&value, &mut p.bytes[1], &mut p.wide[1]);
+        }
         self.count[1] += 1;
         self.aux_names.push(path.clone());
         let var = Variable::new_unchecked(Index::Aux(index));
@@ -301,7 +327,10 @@ impl<Scalar: B200Field> ConstraintSystem<Scalar> for B200ConstraintSystem<Scalar
         let index = self.count[0] as usize;
         let path = compute_path(&self.current_namespace, &annotation().into());
         let value = f()?;
-        stage_value(&value, &mut self.pend_bytes[0], &mut self.pend_wide[0]);
+        {
+            let p = self.pend.get_mut();
+            stage_value(&value, &mut p.bytes[0], &mut p.wide[0]);
+        }
         self.count[0] += 1;
         self.input_names.push(path.clone());
         let var = Variable::new_unchecked(Index::Input(index));
@@ -323,11 +352,15 @@ impl<Scalar: B200Field> ConstraintSystem<Scalar> for B200ConstraintSystem<Scalar
         let a = a(LinearCombination::zero());
         let b = b(LinearCombination::zero());
         let c = c(LinearCombination::zero());
-        self.push_lc(&a);
-        self.push_lc(&b);
-        self.push_lc(&c);
+        let staged = {
+            let p = self.pend.get_mut();
+            Self::push_lc(p, &a);
+            Self::push_lc(p, &b);
+            Self::push_lc(p, &c);
+            p.cols.len()
+        };
         self.constraint_paths.push(path);
-        if self.cols.len() >= (1 << 20) {
+        if staged >= (1 << 20) {
             self.flush();
         }
     }

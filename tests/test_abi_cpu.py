@@ -47,4 +47,7 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
-                assert not re.search(r"#\s*include[^\n]*oracle|dlopen|libbp_oracle", src), f
+                assert not re.search(r"#\s*include[^\n]*oracle|libbp_oracle", src), f
+                # the only library the product may bind at run time is NCCL (multi-GPU groups)
+                for m in re.finditer(r"dlopen\s*\(", src):
+                    assert "libnccl" in src[max(0, m.start() - 400):m.start()], (f, "dlopen of something that is not NCCL")

@@ -475,3 +475,102 @@ def test_save_and_load_round_trip(tmp_path):
     open(bad, "wb").write(raw[: len(raw) // 2])
     assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -4 and not h3.value
     assert L.bp_cs_load(str(tmp_path / "missing").encode(), 0, ctypes.byref(h3)) == -4
+    # a flipped payload bit (here: inside the column words) fails the checksum; so does a lost trailer
+    hdr = 72
+    k = hdr + (3 * n_rows + 1) * 4 + 40
+    open(bad, "wb").write(raw[:k] + bytes([raw[k] ^ 0x10]) + raw[k + 1:])
+    assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -4 and not h3.value
+    open(bad, "wb").write(raw[:-8])
+    assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -4 and not h3.value
+    # a header of another layout version / byte order / impossible counts is not one of ours
+    for off, val in ((7, b"\x01"), (20, b"\x04\x03\x02\x01"), (16, b"\x10\x00\x00\x00")):
+        open(bad, "wb").write(raw[:off] + val + raw[off + len(val):])
+        assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -5 and not h3.value
+
+
+def test_load_rejects_inconsistent_row_offsets(tmp_path):
+    """a file whose checksum is right but whose row offsets are not monotone (a stale or hand-made file) must not
+    reach the kernels: bp_cs_load re-validates the structure on the device."""
+    import struct
+
+    from bellpepper_b200 import ffi
+
+    fid = 0
+    lens, cols, coeffs, inputs, aux, _ = _gadget_like_instance(fid, 5, 200, 300, 3)
+    n_rows = lens.size // 3
+    path = str(tmp_path / "s.bpr1cs").encode()
+    L = ffi.load()
+    with Handle(fid) as h:
+        h.load_instance(lens, cols, coeffs, inputs, aux)
+        h.ok(L.bp_cs_save(h.h, path))
+    raw = bytearray(open(path, "rb").read())
+    hdr = 72
+    # swap two row offsets (keeps the multiset of words, so a word-sum checksum would not notice; ours is positional, so
+    # recompute it the way the library does to isolate the structural check)
+    a, b = hdr + 4 * 10, hdr + 4 * 200
+    raw[a:a + 4], raw[b:b + 4] = raw[b:b + 4], raw[a:a + 4]
+
+    def checksum(payload):
+        lanes = [0xcbf29ce484222325, 0x84222325cbf29ce4, 0x9e3779b97f4a7c15, 0xbf58476d1ce4e5b9]
+        M = (1 << 64) - 1
+        words = 0
+        # each array is hashed separately padded to 8 bytes: arrays are row_ptr, cols, vals, kexp, inputs, aux
+        for chunk in payload:
+            for i in range(0, len(chunk), 8):
+                w = int.from_bytes(chunk[i:i + 8].ljust(8, b"\0"), "little")
+                lanes[words & 3] = ((lanes[words & 3] ^ w) * 0x100000001b3) & M
+                words += 1
+        hv = words
+        for l in lanes:
+            hv = ((hv ^ l) * 0x100000001b3) & M
+        return hv
+
+    nnz, n_in, n_aux = cols.size, inputs.shape[0], aux.shape[0]
+    sizes = [(3 * n_rows + 1) * 4, nnz * 4, nnz * 32, nnz * 2, n_in * 32, n_aux * 32]
+    assert hdr + sum(sizes) + 8 == len(raw)
+    chunks, off = [], hdr
+    for sz in sizes:
+        chunks.append(bytes(raw[off:off + sz]))
+        off += sz
+    good = bytes(open(path, "rb").read())
+    assert struct.unpack("<Q", good[-8:])[0] == checksum([good[hdr:hdr + sizes[0]]] + chunks[1:]), "test's checksum twin is off"
+    raw[-8:] = struct.pack("<Q", checksum(chunks))
+    bad = str(tmp_path / "bad.bin").encode()
+    open(bad, "wb").write(bytes(raw))
+    h3 = ffi.vp()
+    assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -4 and not h3.value
+
+
+@pytest.mark.parametrize("odd_terms", [1, 3, 6, 7])
+def test_blocks_of_empty_rows_after_unaligned_terms(odd_terms):
+    """a 64-row block without any term whose term offset is not a multiple of 4 must not make check_small read its
+    staging buffer (nothing was copied into it).  `0 * 0 = 0` rows are legal (boolean.rs:397-423 emits empty A and B)."""
+    fid = 1
+    # a few plain rows with `odd_terms` terms in total, then 200 empty rows (three whole 64-row blocks of them), then a tail
+    lens, cols, coeffs = [], [], []
+    one = [1, 0, 0, 0]
+    for i in range(odd_terms):  # rows  (1 * aux_i) * (0) = 0 : one term each
+        lens += [1, 0, 0]
+        cols.append(0x80000000 | i)
+        coeffs.append(one)
+    pad = (-len(lens) // 3) % 64
+    n_empty = pad + 200
+    lens += [0, 0, 0] * n_empty
+    lens += [1, 1, 1]  # a final row that fails unless aux_0 * aux_1 == aux_2
+    cols += [0x80000000, 0x80000001, 0x80000002]
+    coeffs += [one, one, one]
+    lens = np.asarray(lens, np.uint32)
+    cols = np.asarray(cols, np.uint32)
+    coeffs = np.asarray(coeffs, np.uint64)
+    inputs = np.asarray([one], np.uint64)
+    aux = np.zeros((max(odd_terms, 3), 4), np.uint64)
+    aux[0][0], aux[1][0], aux[2][0] = 3, 5, 15
+    n_rows = lens.size // 3
+    with Handle(fid) as h:
+        h.load_instance(lens, cols, coeffs, inputs, aux)
+        for _ in range(3):
+            assert h.first_unsatisfied() == -1
+        aux[2][0] = 16
+        h.ok(h.L.bp_cs_set(h.h, 1, 2, aux[2].ctypes.data))
+        assert h.first_unsatisfied() == n_rows - 1
+        assert h.opt("plain_rows") == n_rows
