@@ -9,6 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbp_r1cs.so")
+FRONTEND = os.path.join(HERE, "libbp_frontend.so")  # the gadget front-end alone, host recording only (g++, no CUDA)
 MICROBENCH = os.path.join(HERE, "bin", "microbench")
 
 NVCC_FLAGS = [
@@ -35,16 +36,21 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources()
     if force or _stale(LIB, srcs):
         cmd = ["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "bp_r1cs.cu"),
-               os.path.join(CSRC, "host", "fixtures.cpp")]
+               os.path.join(CSRC, "host", "fixtures.cpp"), "-ldl"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         if os.environ.get("BP_EXPERIMENTAL_VARIANTS") == "1":
             cmd.insert(1, "-DBP_EXPERIMENTAL_VARIANTS")
         subprocess.run(cmd, check=True, cwd=CSRC)
-    mb = os.path.join(CSRC, "microbench.cu")
-    if os.path.exists(mb) and (force or _stale(MICROBENCH, srcs)):
-        os.makedirs(os.path.dirname(MICROBENCH), exist_ok=True)
-        subprocess.run(["nvcc", *NVCC_FLAGS, "-o", MICROBENCH, mb], check=True, cwd=CSRC)
+    host = os.path.join(CSRC, "host")
+    if force or _stale(FRONTEND, srcs + [os.path.join(host, "frontend.map")]):
+        subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-Wno-subobject-linkage", "-Wl,--version-script=frontend.map",
+                        "-o", FRONTEND, "frontend_host.cpp"], check=True, cwd=host)
+    for name in ("microbench", "microbench2"):
+        mb, out = os.path.join(CSRC, name + ".cu"), os.path.join(os.path.dirname(MICROBENCH), name)
+        if os.path.exists(mb) and (force or _stale(out, srcs)):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run(["nvcc", *NVCC_FLAGS, "-o", out, mb], check=True, cwd=CSRC)
     return LIB
 
 

@@ -74,6 +74,10 @@ struct bp_cs {
     DevBuf scols;              // plan: per term, the word check_small works from
     DevBuf fat_rows;           // plan: rows handled by check_fat_rows (+ one u32 counter at the end)
     DevBuf gen_rows;           // plan: rows of kind Generic when the instance also has plain rows (+ counter)
+    DevBuf lct_lc, lct_slice_off, lct_cols, lct_vals, lct_tmp;  // plan: LC tiles of the streaming full-width kernel (check_lct)
+    bool lct_ok = false;       // plan: the LC-tile layout exists and covers every non-fat row
+    bool lct_enabled = true;   // bp_cs_set_option("stream_kernel", 0) keeps the thread-per-row kernel
+    uint64_t lct_groups = 0;   // 32-term groups in the layout (padding included)
     DevBuf deferred;           // per check: plain rows check_small handed to check_rows
     DevBuf fat_undecided;      // per check: fat rows check_fat_int handed to check_fat_rows
     uint64_t n_fat_rows = 0, n_gen_rows = 0, n_plain_rows = 0;  // plan statistics (host copies)
@@ -359,6 +363,52 @@ int select_rows(bp_cs* h, DevBuf& list, uint32_t kind, uint64_t expect) {
     return BP_OK;
 }
 
+// LC tiles for the streaming full-width kernel (kernels.cuh: check_lct): only for product-heavy instances without plain rows
+// (synthetic-style: every non-fat row would go to the thread-per-row kernel), every column in range.  A second copy of the
+// coefficients in tile order (+ ~4 % padding); when it does not fit in memory the thread-per-row kernel simply stays in use.
+int build_lct(bp_cs* h) {
+    h->lct_ok = false;
+    const uint64_t ft = eff_fat_terms(h);
+    if (!h->lct_enabled || !(2 * h->n_gen > h->nnz) || h->n_plain_rows != 0 || !h->cols_in_range || ft > 65535 || !h->n_rows) return BP_OK;
+    const uint32_t n = (uint32_t)h->n_rows;
+    const uint32_t n_tiles = (n + kLctRows - 1) / kLctRows;
+    int rc;
+    if ((rc = ensure(h, h->lct_lc, (size_t)n_tiles * kLctLcs * 4, 0)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->lct_slice_off, (size_t)n_tiles * kLctSlices * 4, 0)) != BP_OK) return rc;
+    if ((rc = ensure(h, h->lct_tmp, (size_t)n_tiles * 8 + 16, 0)) != BP_OK) return rc;
+    uint32_t* groups = (uint32_t*)h->lct_tmp.p;       // per tile
+    uint32_t* base = groups + n_tiles + 1;            // exclusive scan of it (+ total)
+    lct_plan<<<std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count * 8), 256, 0, h->stream>>>((const uint32_t*)h->row_ptr.p, n, (uint32_t)ft, n_tiles,
+                                                                                         (uint32_t*)h->lct_lc.p, (uint32_t*)h->lct_slice_off.p, groups);
+    h->launches++;
+    CU(h, cudaMemsetAsync(groups + n_tiles, 0, 4, h->stream));
+    size_t tmp_bytes = 0;
+    CU(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, groups, base, (int)(n_tiles + 1), h->stream));
+    if ((rc = ensure(h, h->scan_tmp, tmp_bytes, 0)) != BP_OK) return rc;
+    CU(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, tmp_bytes, groups, base, (int)(n_tiles + 1), h->stream));
+    uint32_t total = 0;
+    CU(h, cudaMemcpyAsync(h->h_pinned_small, base + n_tiles, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(&total, h->h_pinned_small, 4);
+    if ((uint64_t)total * 32 > 2 * h->nnz + 4096) return BP_OK;  // pathological length mix: the padding would double the stream
+    // the big arrays: give up quietly when they do not fit
+    if (ensure(h, h->lct_cols, std::max<size_t>((size_t)total * 32 * 4, 256), 0) != BP_OK ||
+        ensure(h, h->lct_vals, std::max<size_t>((size_t)total * 32 * 32, 256), 0) != BP_OK) {
+        for (DevBuf* b : {&h->lct_cols, &h->lct_vals})
+            if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+        h->err.clear();
+        return BP_OK;
+    }
+    lct_fill<<<std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count * 8), 256, 0, h->stream>>>(
+        (const uint32_t*)h->row_ptr.p, (const uint32_t*)h->cols.p, (const uint4*)h->vals.p, n_tiles, (const uint32_t*)h->lct_lc.p, base,
+        (uint32_t*)h->lct_slice_off.p, (uint32_t*)h->lct_cols.p, (uint4*)h->lct_vals.p);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    h->lct_groups = total;
+    h->lct_ok = true;
+    return BP_OK;
+}
+
 // (Re)build the plan when rows or the threshold changed: row_meta, the per-kind counts, the fat / generic row lists and the
 // deferred-row buffer.
 int ensure_plan(bp_cs* h) {
@@ -406,6 +456,7 @@ int ensure_plan(bp_cs* h) {
         if ((rc = select_rows(h, h->gen_rows, kRowGeneric, h->n_plain_rows ? h->n_gen_rows : 0)) != BP_OK) return rc;
         if ((rc = ensure(h, h->deferred, std::max<size_t>((size_t)h->n_plain_rows * 4, 4), 0)) != BP_OK) return rc;
         if ((rc = ensure(h, h->fat_undecided, std::max<size_t>((size_t)h->n_fat_rows * 4, 4), 0)) != BP_OK) return rc;
+        if ((rc = build_lct(h)) != BP_OK) return rc;
     }
     h->plan_valid = true;
     h->plan_gen++;
@@ -509,6 +560,21 @@ int ensure_chunk_plan(bp_cs* h, int max_pieces = 16) {
     return BP_OK;
 }
 
+bool lct_usable(const bp_cs* h) { return h->lct_ok && h->lct_enabled && h->wide_valid && (h->kernels_mask & 1); }
+LctView lct_view(const bp_cs* h) {
+    LctView v;
+    v.lc = (const uint32_t*)h->lct_lc.p;
+    v.slice_off = (const uint32_t*)h->lct_slice_off.p;
+    v.cols = (const uint32_t*)h->lct_cols.p;
+    v.vals = (const uint4*)h->lct_vals.p;
+    v.n_tiles = (uint32_t)((h->n_rows + kLctRows - 1) / kLctRows);
+    return v;
+}
+int lct_grid(const bp_cs* h) {
+    const uint64_t n_tiles = (h->n_rows + kLctRows - 1) / kLctRows;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)h->sm_count * 2));
+}
+
 // Launch K1/K2 on the handle's stream.  Emit mode (any of az/bz/cz set): the full-width kernels over every row.
 // Check mode: result init; check_small over the plain rows (integer arithmetic on the shadows); check_rows over the generic
 // rows and whatever check_small deferred; check_fat_rows (warp per row) over the fat rows.
@@ -573,6 +639,14 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
                               m, o, h->fc, (const uint32_t*)h->gen_rows.p, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
         h->launches += 2;
         if (h->n_fat_rows) CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    } else if (emit && h->variant < 0 && lct_usable(h)) {
+        const LctView lv = lct_view(h);
+        DISPATCH_FIELD(h, (check_lct<F, true><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc)));
+        h->launches++;
+        if ((h->kernels_mask & 2) && h->n_fat_rows) {
+            DISPATCH_FIELD(h, (check_fat_rows<F, true, 0, 4><<<fat_grid, block, 0, h->stream>>>(m, o, h->fc, fat, n_fat)));
+            h->launches++;
+        }
     } else if (emit) {
         BP_LAUNCH(true, 0, 4, 0, 4);
     } else if (h->variant >= 100) {
@@ -641,6 +715,10 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
                     DISPATCH_FIELD(h, (check_rows<F, false, kVDefault, 6, true><<<lgrid, block, 0, h->stream>>>(
                                           m, o, h->fc, gl, (uint32_t)h->n_gen_rows, (const uint32_t*)h->deferred.p, h->d_ndef)));
                 }
+                h->launches++;
+            } else if (h->variant < 0 && lct_usable(h)) {
+                const LctView lv = lct_view(h);
+                DISPATCH_FIELD(h, (check_lct<F, false><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc)));
                 h->launches++;
             } else {
                 if (park) { DISPATCH_FIELD(h, (check_rows<F, false, kVDefault | kVPark, 6><<<grid, block, 0, h->stream>>>(m, o, h->fc))); }
@@ -883,7 +961,8 @@ void bp_cs_free(bp_cs* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_graph(h);
     for (DevBuf* b : {&h->row_ptr, &h->cols, &h->vals, &h->kexp, &h->inputs, &h->aux, &h->shadow, &h->scan_tmp, &h->scratch, &h->u8_stage,
-                      &h->row_meta, &h->scols, &h->fat_rows, &h->gen_rows, &h->deferred, &h->fat_undecided})
+                      &h->row_meta, &h->scols, &h->fat_rows, &h->gen_rows, &h->deferred, &h->fat_undecided, &h->lct_lc, &h->lct_slice_off,
+                      &h->lct_cols, &h->lct_vals, &h->lct_tmp})
         if (b->p) cudaFree(b->p);
     if (h->d_result) cudaFree(h->d_result);
     if (h->h_pinned_small) cudaFreeHost(h->h_pinned_small);
@@ -1117,6 +1196,11 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
         h->sparse_upload = v != 0;
         return BP_OK;
     }
+    if (!std::strcmp(key, "stream_kernel")) {
+        h->lct_enabled = v != 0;
+        h->plan_valid = false;
+        return BP_OK;
+    }
     if (!std::strcmp(key, "graph")) {
         h->use_graph = v != 0;
         if (!h->use_graph) drop_graph(h);
@@ -1143,6 +1227,13 @@ int bp_cs_get_option(bp_cs* h, const char* key, int64_t* v) {
     if (!std::strcmp(key, "gen_terms")) { *v = (int64_t)h->n_gen; return BP_OK; }
     if (!std::strcmp(key, "sm_count")) { *v = h->sm_count; return BP_OK; }
     if (!std::strcmp(key, "graph")) { *v = h->use_graph ? 1 : 0; return BP_OK; }
+    if (!std::strcmp(key, "stream_kernel") || !std::strcmp(key, "stream_groups")) {  // 1 when the LC-tile layout is in use; its size
+        CU(h, cudaSetDevice(h->device));
+        int rc = ensure_plan(h);
+        if (rc != BP_OK) return rc;
+        *v = key[7] == 'k' ? (lct_usable(h) ? 1 : 0) : (int64_t)(h->lct_ok ? h->lct_groups : 0);
+        return BP_OK;
+    }
     if (!std::strcmp(key, "graph_replays")) { *v = h->graph_replays; return BP_OK; }
     if (!std::strcmp(key, "graph_captures")) { *v = h->graph_captures; return BP_OK; }
     // plan statistics (build the plan if needed): rows per kernel
@@ -1810,9 +1901,20 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
     uint8_t* bits_in = (uint8_t*)h->h_pack;
     uint8_t* bits_aux = bits_in + aux_off;
     std::vector<std::vector<Exc>> exc((size_t)nt * 2);
-    auto pack = [&](const uint64_t* src, uint64_t n, uint8_t* dst, unsigned t, std::vector<Exc>& out) {
-        // thread t takes the bytes [b0, b1) of the bit string, i.e. the elements [8*b0, min(8*b1, n))
-        const uint64_t nbytes = (n + 7) / 8, b0 = nbytes * t / nt, b1 = nbytes * (t + 1) / nt;
+    // With "sparse_upload" (row shards) only the pieces of the aux witness that this handle's rows read are packed and sent.
+    std::vector<std::pair<uint64_t, uint64_t>> aux_bytes_ranges;  // [first byte, end byte) of the aux bit string
+    const bool sparse = h->sparse_upload && h->n_rows && n_aux;
+    if (sparse) {
+        if ((rc = ensure_plan(h)) != BP_OK || (rc = ensure_chunk_plan(h, 16)) != BP_OK) return rc;
+        for (int i = 0; i < h->chunk_plan.n_pieces; ++i)  // (piece offsets are multiples of 256 elements)
+            aux_bytes_ranges.push_back({h->chunk_plan.off[i] / 8, (h->chunk_plan.off[i] + h->chunk_plan.len[i] + 7) / 8});
+    } else if (n_aux) {
+        aux_bytes_ranges.push_back({0, aux_bytes});
+    }
+    uint64_t aux_range_bytes = 0;
+    for (auto& r : aux_bytes_ranges) aux_range_bytes += r.second - r.first;
+    // bytes [b0, b1) of the bit string of `src` (elements [8*b0, min(8*b1, n)))
+    auto pack_bytes = [&](const uint64_t* src, uint64_t n, uint8_t* dst, uint64_t b0, uint64_t b1, std::vector<Exc>& out) {
         for (uint64_t b = b0; b < b1; ++b) {
             uint8_t acc = 0;
             const uint64_t e0 = 8 * b, e1 = std::min<uint64_t>(e0 + 8, n);
@@ -1827,15 +1929,20 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
             dst[b] = acc;
         }
     };
+    auto work = [&](unsigned t) {
+        if (n_in) pack_bytes(inputs_le, n_in, bits_in, in_bytes * t / nt, in_bytes * (t + 1) / nt, exc[2 * t]);
+        // thread t takes the slice [s0, s1) of the concatenated aux byte ranges
+        uint64_t s0 = aux_range_bytes * t / nt, s1 = aux_range_bytes * (t + 1) / nt, base = 0;
+        for (auto& r : aux_bytes_ranges) {
+            const uint64_t len = r.second - r.first, lo = std::max(s0, base), hi = std::min(s1, base + len);
+            if (lo < hi) pack_bytes(aux_le, n_aux, bits_aux, r.first + (lo - base), r.first + (hi - base), exc[2 * t + 1]);
+            base += len;
+        }
+    };
     {
         std::vector<std::thread> th;
-        for (unsigned t = 1; t < nt; ++t)
-            th.emplace_back([&, t] {
-                if (n_in) pack(inputs_le, n_in, bits_in, t, exc[2 * t]);
-                pack(aux_le, n_aux, bits_aux, t, exc[2 * t + 1]);
-            });
-        if (n_in) pack(inputs_le, n_in, bits_in, 0, exc[0]);
-        pack(aux_le, n_aux, bits_aux, 0, exc[1]);
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
         for (auto& x : th) x.join();
     }
     size_t n_exc[2] = {0, 0};
@@ -1843,7 +1950,7 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
         n_exc[0] += exc[2 * t].size();
         n_exc[1] += exc[2 * t + 1].size();
     }
-    if (n_exc[0] + n_exc[1] > (n_in + n_aux) / 16 + 1024) {  // not a bit witness: send it as it is
+    if (n_exc[0] + n_exc[1] > (n_in + (sparse ? 8 * aux_range_bytes : n_aux)) / 16 + 1024) {  // not a bit witness: send it as it is
         if (n_in && (rc = bp_cs_set_range(h, 0, 0, n_in, inputs_le)) != BP_OK) return rc;
         if (n_aux && (rc = bp_cs_set_range(h, 1, 0, n_aux, aux_le)) != BP_OK) return rc;
         return check_graphed(h, (long long*)dev_result, nullptr);
@@ -1855,7 +1962,18 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
                     return fail(h, BP_E_RANGE, "bp_cs_recheck_scalars: %s element %llu is not canonical (>= p)", k ? "aux" : "input",
                                 (unsigned long long)e.idx);
     if (n_in && (rc = set_range_packed(h, 0, 0, n_in, bits_in, true, false)) != BP_OK) return rc;
-    if (n_aux && (rc = set_range_packed(h, 1, 0, n_aux, bits_aux, true, false)) != BP_OK) return rc;
+    if (sparse) {
+        if ((rc = ensure(h, h->u8_stage, aux_bytes, 0)) != BP_OK) return rc;
+        h->wide_valid = false;
+        for (int i = 0; i < h->chunk_plan.n_pieces; ++i) {
+            const uint64_t off = h->chunk_plan.off[i], len = h->chunk_plan.len[i];
+            CU(h, cudaMemcpyAsync((char*)h->u8_stage.p + off / 8, bits_aux + off / 8, (size_t)((len + 7) / 8), cudaMemcpyHostToDevice, h->stream));
+            launch_widen(h, true, off, len, shadow_ptr(h, 1) + off);
+        }
+        CU(h, cudaGetLastError());
+    } else if (n_aux && (rc = set_range_packed(h, 1, 0, n_aux, bits_aux, true, false)) != BP_OK) {
+        return rc;
+    }
     for (int k = 0; k < 2; ++k) {
         const size_t n = n_exc[k];
         if (!n) continue;

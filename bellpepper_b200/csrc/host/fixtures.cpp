@@ -80,35 +80,69 @@ void bits_to_bytes_be(const std::vector<Boolean>& bits, uint8_t* out) {
     }
 }
 
-// sha256() with row filtering per compression block; same circuit as gadgets.hpp `sha256`.
+// sha256() with row filtering per compression block; same circuit as gadgets.hpp `sha256`.  Rows of the blocks inside any of the
+// n_ranges half-open block ranges [ranges[2i], ranges[2i+1]) (ascending, disjoint) are kept, all others dropped; for each range
+// global_before[i] = rows that precede its first row in the WHOLE circuit, local_before[i] = kept rows that precede it.
 template <class CS>
-void sha256_sharded(CS& cs, FilterSink& fs, const uint8_t* msg, uint64_t len, uint64_t bb, uint64_t be, uint8_t digest[32], uint64_t* rows_before) {
-    // the input-bit rows belong to "block -1": kept by the shard that holds block 0
+void sha256_ranges(CS& cs, FilterSink& fs, const uint8_t* msg, uint64_t len, const uint64_t* ranges, uint64_t n_ranges, uint8_t digest[32],
+                   uint64_t* global_before, uint64_t* local_before) {
+    auto keep_block = [&](uint64_t blk, uint64_t* which) {
+        for (uint64_t i = 0; i < n_ranges; ++i)
+            if (blk >= ranges[2 * i] && blk < ranges[2 * i + 1]) {
+                *which = i;
+                return true;
+            }
+        return false;
+    };
+    // the input-bit rows belong to "block -1": kept by whoever holds block 0
     cs.flush();
-    fs.rows_enabled = bb == 0;
+    uint64_t which = 0;
+    fs.rows_enabled = keep_block(0, &which);
+    const uint64_t dropped0 = fs.rows_dropped;
+    uint64_t kept = 0, seen = 0;  // rows kept / rows produced so far by THIS call
+    auto account = [&](uint64_t produced, bool was_kept) {
+        seen += produced;
+        if (was_kept) kept += produced;
+    };
+    uint64_t rows_at = cs.num_constraints();
     std::vector<Boolean> input;
     alloc_message_bits(cs, msg, len, input);
+    cs.flush();
+    account(cs.num_constraints() - rows_at, fs.rows_enabled);
+    rows_at = cs.num_constraints();
     std::vector<Boolean> padded = input;
     const uint64_t plen = padded.size();
     padded.push_back(Boolean::constant(true));
     while ((padded.size() + 64) % 512 != 0) padded.push_back(Boolean::constant(false));
     for (int i = 63; i >= 0; --i) padded.push_back(Boolean::constant((plen >> i) & 1));
     std::vector<UInt32> cur = sha256_iv();
-    uint64_t before = 0;
     for (uint64_t blk = 0; blk < padded.size() / 512; ++blk) {
-        cs.flush();
-        const bool keep = blk >= bb && blk < be;
-        if (keep && !fs.rows_enabled && blk == bb) before = fs.rows_dropped;
+        const bool keep = keep_block(blk, &which);
+        if (keep && blk == ranges[2 * which]) {  // first block of a range: what precedes it
+            // (a range that starts at block 0 also owns the input-bit rows)
+            if (global_before) global_before[which] = blk == 0 ? 0 : seen;
+            if (local_before) local_before[which] = blk == 0 ? 0 : kept;
+        }
         fs.rows_enabled = keep;
         auto ns = cs.ns([&] { return "block " + std::to_string(blk); });
         cur = sha256_compression_function(ns, padded.data() + 512 * blk, cur);
+        cs.flush();
+        account(cs.num_constraints() - rows_at, keep);
+        rows_at = cs.num_constraints();
     }
-    cs.flush();
+    (void)dropped0;
     fs.rows_enabled = true;
     std::vector<Boolean> out;
     for (auto& wd : cur) wd.into_bits_be(out);
     bits_to_bytes_be(out, digest);
-    if (rows_before) *rows_before = before;
+}
+
+template <class CS>
+void sha256_sharded(CS& cs, FilterSink& fs, const uint8_t* msg, uint64_t len, uint64_t bb, uint64_t be, uint8_t digest[32], uint64_t* rows_before) {
+    const uint64_t r[2] = {bb, be};
+    uint64_t g = 0, l = 0;
+    sha256_ranges(cs, fs, msg, len, r, 1, digest, &g, &l);
+    if (rows_before) *rows_before = g;
 }
 
 }  // namespace
@@ -179,6 +213,17 @@ int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t bb, uint
     return guarded(t, [&] {
         if (t->named) sha256_sharded(*t->named_cs, *t->filter, msg, len, bb, be, digest, rows_before);
         else sha256_sharded(*t->bulk_cs, *t->filter, msg, len, bb, be, digest, rows_before);
+    });
+}
+
+int bp_tcs_sha256_ranges(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint64_t* ranges, uint64_t n_ranges, uint8_t digest[32],
+                         uint64_t* global_before, uint64_t* local_before) {
+    if (!t || (!msg && len) || !digest || !ranges || !n_ranges) return BP_E_ARG;
+    for (uint64_t i = 0; i < n_ranges; ++i)
+        if (ranges[2 * i] >= ranges[2 * i + 1] || (i && ranges[2 * i] < ranges[2 * i - 1])) return BP_E_ARG;
+    return guarded(t, [&] {
+        if (t->named) sha256_ranges(*t->named_cs, *t->filter, msg, len, ranges, n_ranges, digest, global_before, local_before);
+        else sha256_ranges(*t->bulk_cs, *t->filter, msg, len, ranges, n_ranges, digest, global_before, local_before);
     });
 }
 

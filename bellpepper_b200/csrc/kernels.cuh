@@ -1281,6 +1281,259 @@ __global__ void __launch_bounds__(128, MB) check_fat_rows(CsrView m, CheckOut o,
     publish_first_bad(my_bad, m, o, my_err);
 }
 
+// ---- K1 / K2, product-heavy instances: the streaming full-width kernel over LC TILES ------------------------------------------
+// A thread per row reading CSR makes every lane of a warp walk its own stream (32 distinct lines per load instruction, the L1
+// tag stage is the bottleneck: measured 8 cycles per term and SM even with an L2-resident witness) and makes a warp wait for its
+// longest row.  The plan therefore re-lays the rows out once, in tiles of 256 rows = 768 LCs:
+//   * the tile's LCs are SORTED by length (descending) and cut into 24 slices of 32 -- one lane per LC, all lanes of a slice
+//     (almost) equally long: no divergence, ~4 % padding;
+//   * a slice stores its terms term-major: group j holds the j-th term of its 32 LCs, so a warp reads 32 x 32 B of coefficients
+//     and 32 x 4 B of column words with ONE fully coalesced load each, streamed once (L1 no-allocate, L2 evict-first), while
+//     each lane gathers its witness element (256-bit load, L2 evict-last) one term ahead of the arithmetic;
+//   * an LC ends in shared memory (A.w, B.w reduced; the C sum unreduced, 17 limbs); after a block barrier a thread per row does
+//     the Hadamard product, the one lazy reduction and the zero test exactly like check_rows.
+// lct_lc[tile*768 + p] = (len << 16) | lc-in-tile (3*row_in_tile + type) for sorted position p; lct_slice_off[tile*24 + q] =
+// first 32-slot group of slice q; lct_cols / lct_vals are indexed by slot = 32*group + lane.  Rows longer than fat_terms (done
+// by check_fat_rows) and rows past the end have length-0 LCs.
+constexpr uint32_t kLctRows = 256, kLctLcs = 768, kLctSlices = 24, kLctThreads = 256;
+constexpr uint32_t kLctNullCol = kClsZero << kColClsShift;
+
+__device__ __forceinline__ void ld256_stream(uint32_t* x, const uint4* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ld256_keep(uint32_t* x, const uint4* p) {
+    asm volatile("ld.global.nc.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ uint32_t ld32_stream(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// Plan, pass 1: sort a tile's LCs by length, record (len, lc) per sorted position, the slice lengths (groups) and their sum.
+__global__ void __launch_bounds__(256) lct_plan(const uint32_t* __restrict__ row_ptr, uint32_t n_rows, uint32_t fat_terms, uint32_t n_tiles,
+                                               uint32_t* __restrict__ lct_lc, uint32_t* __restrict__ slice_rel /*n_tiles*24*/,
+                                               uint32_t* __restrict__ tile_groups /*n_tiles*/) {
+    __shared__ uint32_t key[1024];
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < 1024u; i += 256u) {
+            uint32_t k = 0;
+            if (i < kLctLcs) {
+                const uint64_t lc = (uint64_t)tile * kLctLcs + i;
+                const uint32_t row = (uint32_t)(lc / 3u);
+                uint32_t len = 0;
+                if (row < n_rows && row_ptr[3 * (size_t)row + 3] - row_ptr[3 * (size_t)row] <= fat_terms) len = row_ptr[lc + 1] - row_ptr[lc];
+                k = (len << 10) | (1023u - i);
+            }
+            key[i] = k;
+        }
+        __syncthreads();
+        for (uint32_t size = 2; size <= 1024u; size <<= 1) {  // bitonic sort, DESCENDING
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = threadIdx.x; t < 512u; t += 256u) {
+                    const uint32_t lo = 2 * t - (t & (stride - 1));  // index with the `stride` bit clear
+                    const uint32_t hi = lo + stride;
+                    const bool desc = (lo & size) == 0;
+                    const uint32_t a = key[lo], b = key[hi];
+                    if ((a < b) == desc) { key[lo] = b; key[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t p = threadIdx.x; p < kLctLcs; p += 256u) {
+            const uint32_t k = key[p];
+            lct_lc[(size_t)tile * kLctLcs + p] = ((k >> 10) << 16) | (1023u - (k & 1023u));
+        }
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (uint32_t q = 0; q < kLctSlices; ++q) {
+                slice_rel[(size_t)tile * kLctSlices + q] = acc;
+                acc += key[32u * q] >> 10;  // the slice's longest LC (sorted: its first)
+            }
+            tile_groups[tile] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Plan, pass 2: copy the terms into their slots (term-major within a slice); slice_off = tile_base + slice_rel, in place.
+__global__ void __launch_bounds__(256) lct_fill(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, const uint4* __restrict__ vals,
+                                               uint32_t n_tiles, const uint32_t* __restrict__ lct_lc, const uint32_t* __restrict__ tile_base,
+                                               uint32_t* __restrict__ slice_off /*in: rel, out: absolute*/, uint32_t* __restrict__ lct_cols,
+                                               uint4* __restrict__ lct_vals) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t q = warp; q < kLctSlices; q += 8u) {
+            const uint32_t w = lct_lc[(size_t)tile * kLctLcs + 32u * q + lane];
+            const uint32_t len = w >> 16, L = __shfl_sync(0xffffffffu, len, 0);
+            const uint32_t g0 = tile_base[tile] + slice_off[(size_t)tile * kLctSlices + q];
+            const uint32_t k0 = row_ptr[(size_t)tile * kLctLcs + (w & 0xffffu)];  // (only read when len > 0: then the LC exists)
+            for (uint32_t j = 0; j < L; ++j) {
+                const size_t slot = ((size_t)g0 + j) * 32u + lane;
+                if (j < len) {
+                    lct_cols[slot] = cols[k0 + j];
+                    lct_vals[2 * slot] = vals[2 * (size_t)(k0 + j)];
+                    lct_vals[2 * slot + 1] = vals[2 * (size_t)(k0 + j) + 1];
+                } else {
+                    lct_cols[slot] = kLctNullCol;
+                    lct_vals[2 * slot] = make_uint4(0, 0, 0, 0);
+                    lct_vals[2 * slot + 1] = make_uint4(0, 0, 0, 0);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) slice_off[(size_t)tile * kLctSlices + q] = g0;
+        }
+    }
+}
+
+struct LctView {
+    const uint32_t* __restrict__ lc;         // [n_tiles * 768]
+    const uint32_t* __restrict__ slice_off;  // [n_tiles * 24]
+    const uint32_t* __restrict__ cols;       // [32 * n_groups]
+    const uint4* __restrict__ vals;          // [2 * 32 * n_groups]
+    uint32_t n_tiles;
+};
+
+// One term of a lane: column word -> class, witness element (gathered), coefficient (streamed).
+struct LctTerm {
+    uint32_t cls;
+    uint32_t w[8], c[8];
+};
+__device__ __forceinline__ void lct_load(LctTerm& t, const LctView& v, const CsrView& m, size_t slot, uint64_t pol) {
+    const uint32_t col = ld32_stream(v.cols + slot, pol);
+    t.cls = (col >> kColClsShift) & 7u;
+    if (t.cls == kClsZero) return;  // zero coefficient, or padding
+    const bool is_aux = (col & kColAux) != 0;
+    ld256_keep(t.w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)(col & kColIdxMask));
+    if (is_product_class(t.cls)) ld256_stream(t.c, v.vals + 2 * slot);
+}
+template <int F, int RIPPLE> __device__ __forceinline__ void lct_apply(uint32_t* acc, LctTerm& t, uint32_t& gen, uint32_t& mag) {
+    const uint32_t cls = t.cls;
+    if (cls == kClsZero) return;
+    if (is_product_class(cls)) {
+        mac_wide(acc, t.c, t.w);
+        gen = 1;
+        return;
+    }
+    if (cls == kClsM1 || cls == kClsM2) {
+        uint32_t n[8];
+        neg_mod<F>(n, t.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t.w[i] = n[i];
+    }
+    acc_add8<RIPPLE>(acc, t.w);
+    mag += 1;
+    if (cls == kClsP2 || cls == kClsM2) {
+        acc_add8<RIPPLE>(acc, t.w);
+        mag += 1;
+    }
+}
+
+template <int F, bool EMIT>
+__global__ void __launch_bounds__(kLctThreads, 2) check_lct(CsrView m, LctView v, CheckOut o, FieldConsts fc) {
+    __shared__ uint32_t s_ab[2][8][kLctRows];   // A.w / B.w of the tile's rows (8 limbs, < 2^256), limb-major
+    __shared__ uint32_t s_c[17][kLctRows];      // unreduced sum of the (negated) C terms
+    __shared__ uint8_t s_flag[kLctRows];        // bit 0: C had a full product; bits 1..: plain magnitude of C (saturating at 8)
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    uint32_t my_bad = 0xffffffffu;
+    for (uint32_t tile = blockIdx.x; tile < v.n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (uint32_t s3 = 0; s3 < 3u; ++s3) {
+            // slices sorted by length: warp w takes q = w, 15 - w, 16 + w, so that every warp gets about the same number of terms
+            const uint32_t q = s3 == 0 ? warp : (s3 == 1 ? 15u - warp : 16u + warp);
+            const uint32_t word = __ldg(v.lc + (size_t)tile * kLctLcs + 32u * q + lane);
+            const uint32_t len = word >> 16, id = word & 0xffffu;
+            const uint32_t L = __shfl_sync(0xffffffffu, len, 0);
+            if (L == 0) continue;  // (uniform) nothing but empty / skipped LCs: their shared-memory entries are written below
+            const size_t slot0 = (size_t)__ldg(v.slice_off + (size_t)tile * kLctSlices + q) * 32u + lane;
+            uint32_t acc[17];
+            zeron<17>(acc);
+            uint32_t gen = 0, mag = 0;
+            const bool is_c = (id % 3u) == 2u;
+            LctTerm cur;
+            lct_load(cur, v, m, slot0, pol);
+#pragma unroll 1
+            for (uint32_t j = 0; j < L; ++j) {
+                LctTerm nxt;
+                nxt.cls = kClsZero;
+                if (j + 1u < L) lct_load(nxt, v, m, slot0 + 32u * (size_t)(j + 1u), pol);
+                if (is_c) lct_apply<F, 17>(acc, cur, gen, mag);
+                else lct_apply<F, 9>(acc, cur, gen, mag);
+                cur = nxt;
+            }
+            const uint32_t r = id / 3u;
+            if (len) {
+                if (is_c) {
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) s_c[i][r] = acc[i];
+                    s_flag[r] = (uint8_t)((gen ? 1u : 0u) | ((mag > 8u ? 8u : mag) << 1));
+                } else {
+                    uint32_t val[8];
+                    finish_ab<F, true>(val, acc, gen, mag);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s_ab[id % 3u][i][r] = val[i];
+                }
+            }
+        }
+        // LCs of length 0 were never visited by a lane with len > 0: their entries are zero
+        // (three passes over the tile's LC words would cost more than writing the zeros first, so: a second, cheap sweep)
+        __syncthreads();
+        {
+            const uint32_t r = threadIdx.x;
+            const uint32_t row = tile * kLctRows + r;
+            if (row < m.n_rows) {
+                const uint32_t p0 = __ldg(m.row_ptr + 3 * (size_t)row), p1 = __ldg(m.row_ptr + 3 * (size_t)row + 1),
+                               p2 = __ldg(m.row_ptr + 3 * (size_t)row + 2), p3 = __ldg(m.row_ptr + 3 * (size_t)row + 3);
+                if (p3 - p0 <= m.fat_terms) {
+                    uint32_t acc[17], az[8], bz[8];
+                    uint32_t gen = 0, mag = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        az[i] = p1 > p0 ? s_ab[0][i][r] : 0u;
+                        bz[i] = p2 > p1 ? s_ab[1][i][r] : 0u;
+                    }
+                    if (p3 > p2) {
+#pragma unroll
+                        for (int i = 0; i < 17; ++i) acc[i] = s_c[i][r];
+                        gen = s_flag[r] & 1u;
+                        mag = s_flag[r] >> 1;
+                    } else {
+                        zeron<17>(acc);
+                    }
+                    if (EMIT) {
+                        uint32_t x[8];
+                        if (o.cz) {
+                            finish_c_canonical<F>(x, acc, fc);
+                            st8(o.cz + 2 * (size_t)row, x);
+                        }
+                        if (o.az) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) x[i] = az[i];
+                            canon_ab<F>(x);
+                            st8(o.az + 2 * (size_t)row, x);
+                        }
+                        if (o.bz) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) x[i] = bz[i];
+                            canon_ab<F>(x);
+                            st8(o.bz + 2 * (size_t)row, x);
+                        }
+                    }
+                    if (!row_satisfied<F, true>(acc, az, bz, gen, mag) && row < my_bad) my_bad = row;
+                }
+            }
+        }
+        __syncthreads();  // the tile's shared-memory results are free again
+    }
+    publish_first_bad(my_bad, m, o, 0u);
+}
+
 __global__ void init_result(long long* first_bad, unsigned int* err, uint32_t* n_deferred) {
     *first_bad = 0x7fffffffffffffffLL;
     *err = 0;

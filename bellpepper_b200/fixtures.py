@@ -4,6 +4,7 @@ gadget circuits).  Used by tests and bench.py; production C++ users include csrc
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -20,6 +21,7 @@ _SIGS = {
     "bp_tcs_flush": (ctypes.c_int, [vp]),
     "bp_tcs_sha256_block": (ctypes.c_int, [vp, vp, vp]),
     "bp_tcs_sha256": (ctypes.c_int, [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, u64p]),
+    "bp_tcs_sha256_ranges": (ctypes.c_int, [vp, vp, ctypes.c_uint64, u64p, ctypes.c_uint64, vp, u64p, u64p]),
     "bp_tcs_blake2s": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, vp]),
     "bp_wcs_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "bp_tcs_which_is_unsatisfied": (ctypes.c_int64, [vp, vp, ctypes.c_uint64]),
@@ -33,7 +35,9 @@ _SIGS = {
                                               ctypes.POINTER(vp), u64p, ctypes.POINTER(vp), u64p]),
 }
 _bound = False
+_host = None
 U64_MAX = (1 << 64) - 1
+FRONTEND_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbp_frontend.so")
 
 
 def _lib():
@@ -45,6 +49,21 @@ def _lib():
             fn.restype, fn.argtypes = res, args
         _bound = True
     return L
+
+
+def _host_lib():
+    """libbp_frontend.so: the same front-end built on its own (g++, no CUDA) for HOST RECORDING -- what the CPU legs use
+    (bench.py --impl reference, cpu_baseline samples, CPU tests), so that they never map the CUDA library."""
+    global _host
+    if _host is None:
+        if not os.path.exists(FRONTEND_PATH):
+            raise ffi.NativeLibraryMissing(f"{FRONTEND_PATH} not found -- run __graft_entry__.build()")
+        L = ctypes.CDLL(FRONTEND_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _host = L
+    return _host
 
 
 def available() -> bool:
@@ -71,7 +90,7 @@ class Tcs:
     """One C++ TestConstraintSystem (+ its device handle or host recorder)."""
 
     def __init__(self, field: int, device: int = 0, named: bool = True, reserve=(0, 0, 0)):
-        self.L = _lib()
+        self.L = _lib() if device >= 0 else _host_lib()  # host recording never touches the CUDA library
         self.t = vp()
         rc = self.L.bp_tcs_new(field, device, int(named), *reserve, ctypes.byref(self.t))
         if rc != 0:
@@ -108,6 +127,16 @@ class Tcs:
         before = ctypes.c_uint64()
         self._ck(self.L.bp_tcs_sha256(self.t, msg, len(msg), block_begin, block_end, out, ctypes.byref(before)))
         return out.raw, before.value
+
+    def sha256_ranges(self, msg: bytes, ranges):
+        """Rows of the compression blocks in `ranges` (list of (begin, end), ascending, disjoint) only; returns (digest,
+        [(global_rows_before, local_rows_before) per range])."""
+        flat = (ctypes.c_uint64 * (2 * len(ranges)))(*[x for r in ranges for x in r])
+        gb = (ctypes.c_uint64 * len(ranges))()
+        lb = (ctypes.c_uint64 * len(ranges))()
+        out = ctypes.create_string_buffer(32)
+        self._ck(self.L.bp_tcs_sha256_ranges(self.t, msg, len(msg), flat, len(ranges), out, gb, lb))
+        return out.raw, [(int(g), int(l)) for g, l in zip(gb, lb)]
 
     def blake2s(self, msg: bytes, personalization: bytes = b"12345678") -> bytes:
         assert len(personalization) == 8

@@ -38,6 +38,13 @@ int bp_tcs_sha256_block(bp_tcs* t, const uint8_t block[64], uint8_t out32[32]);
 int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t block_begin, uint64_t block_end, uint8_t digest[32],
                   uint64_t* rows_before);
 
+/* Same circuit, rows kept for several block ranges at once: ranges = n_ranges pairs [begin, end), ascending and disjoint.
+ * global_before[i] = rows of the WHOLE circuit that precede range i's first row (a range starting at block 0 also owns the
+ * rows of the input bits and gets 0), local_before[i] = kept rows that precede it.  For sampled parity checks of a long
+ * chain: one host recording gives the oracle the rows of a few blocks anywhere in the chain, under their global numbers. */
+int bp_tcs_sha256_ranges(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint64_t* ranges, uint64_t n_ranges, uint8_t digest[32],
+                         uint64_t* global_before, uint64_t* local_before);
+
 /* blake2s() gadget over `len` message bytes, each bit allocated as "input bit <byte> <bit>" least significant first,
  * with an 8-byte personalization (crates/bellpepper/src/gadgets/blake2s.rs:344-406, tests :498-555).  digest = the 32
  * output bytes (the gadget's output bits are little-endian per byte). */

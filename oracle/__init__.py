@@ -65,6 +65,7 @@ def lib() -> ctypes.CDLL:
     L.bpo_synth_fill.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
                                  ctypes.c_uint64, ctypes.c_uint64, u32p, u64p]
     L.bpo_synth_witness.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u64p]
+    L.bpo_synth_witness_at.argtypes = [ctypes.c_int, ctypes.c_uint64, u64p, ctypes.c_uint64, u64p]
     _lib = L
     return L
 

@@ -365,3 +365,16 @@ int bpo_synth_witness(int field, uint64_t seed, uint64_t i0, uint64_t n, uint64_
     }
     return 0;
 }
+
+/* Witness elements at arbitrary unified indices idx[0..n): canonical.  (Sampled parity checks of instances whose whole
+ * witness would not be worth materialising on the host: only the elements some sampled row reads are generated.) */
+int bpo_synth_witness_at(int field, uint64_t seed, const uint64_t *idx, uint64_t n, uint64_t *out) {
+    if (field < 0 || field > 2) return -1;
+    const bpo_field *f = &FIELDS[field];
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        if (idx[i] == 0) { out[4 * i] = 1; out[4 * i + 1] = out[4 * i + 2] = out[4 * i + 3] = 0; continue; }
+        sample(f, gkey(seed, 4, idx[i], 0), out + 4 * i);
+    }
+    return 0;
+}

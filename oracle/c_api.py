@@ -126,3 +126,22 @@ def synth_instance(field: int, seed: int, t: int, n_vars: int, n_inputs: int, n_
     lens, cols, coeffs = synth_rows(field, seed, t, n_vars, n_inputs, row0, n_rows)
     w = synth_witness(field, seed, 0, n_vars)
     return lens, cols, coeffs, w[:n_inputs].copy(), w[n_inputs:].copy()
+
+
+def synth_witness_at(field: int, seed: int, idx: np.ndarray) -> np.ndarray:
+    idx = np.ascontiguousarray(idx, np.uint64)
+    out = np.zeros((idx.size, 4), np.uint64)
+    assert lib().bpo_synth_witness_at(field, seed, _p64(idx), idx.size, _p64(out)) == 0
+    return out
+
+
+def synth_sparse_instance(field: int, seed: int, t: int, n_vars: int, n_inputs: int, row0: int, n_rows: int) -> Instance:
+    """Rows [row0, row0+n_rows) of the synthetic recipe as an oracle instance WITHOUT the whole witness: the columns the rows
+    read are renumbered into a compact aux space and only those witness elements are generated (same values, same sums).  For
+    sampled parity checks of instances whose witness is GiBs (BASELINE configs[4]: 2^27 variables)."""
+    lens, cols, coeffs = synth_rows(field, seed, t, n_vars, n_inputs, row0, n_rows)
+    unified = np.where(cols >> 31, (cols & np.uint32(0x7FFFFFFF)).astype(np.uint64) + np.uint64(n_inputs), cols.astype(np.uint64))
+    uniq, inv = np.unique(unified, return_inverse=True)
+    w = synth_witness_at(field, seed, uniq)
+    one = np.asarray([[1, 0, 0, 0]], np.uint64)
+    return Instance(field, lens, inv.astype(np.uint32) | np.uint32(0x80000000), coeffs, one, w)

@@ -7,6 +7,13 @@ pub struct bp_cs {
     _private: [u8; 0],
 }
 
+/// A group of row shards on several GPUs of one node (one process per GPU).
+#[repr(C)]
+pub struct bp_group {
+    _private: [u8; 0],
+}
+pub const BP_GROUP_ID_BYTES: usize = 128;
+
 pub const BP_OK: c_int = 0;
 pub const BP_E_CUDA: c_int = -1;
 pub const BP_E_OOM: c_int = -2;
@@ -39,6 +46,9 @@ extern "C" {
     pub fn bp_cs_set_range_bits(cs: *mut bp_cs, is_aux: c_int, first: u64, n: u64, bits: *const u8) -> c_int;
     pub fn bp_cs_recheck_bits(cs: *mut bp_cs, inputs_bits: *const u8, aux_bits: *const u8, row: *mut i64) -> c_int;
     pub fn bp_cs_recheck_bits_async(cs: *mut bp_cs, inputs_bits: *const u8, aux_bits: *const u8, dev_result: *mut i64) -> c_int;
+    pub fn bp_cs_set_many(cs: *mut bp_cs, is_aux: c_int, n: u64, idx: *const u64, vals_le: *const u64) -> c_int;
+    pub fn bp_cs_recheck_scalars(cs: *mut bp_cs, inputs_le: *const u64, aux_le: *const u64, row: *mut i64) -> c_int;
+    pub fn bp_cs_recheck_scalars_async(cs: *mut bp_cs, inputs_le: *const u64, aux_le: *const u64, dev_result: *mut i64) -> c_int;
     pub fn bp_cs_check_async(cs: *mut bp_cs, dev_result: *mut i64) -> c_int;
     pub fn bp_cs_eval(cs: *mut bp_cs, az: *mut u64, bz: *mut u64, cz: *mut u64) -> c_int;
     pub fn bp_cs_eval_async(cs: *mut bp_cs, dev_az: *mut u64, dev_bz: *mut u64, dev_cz: *mut u64) -> c_int;
@@ -50,6 +60,16 @@ extern "C" {
     pub fn bp_cs_sync(cs: *mut bp_cs) -> c_int;
     pub fn bp_cs_set_option(cs: *mut bp_cs, key: *const c_char, value: i64) -> c_int;
     pub fn bp_cs_get_option(cs: *mut bp_cs, key: *const c_char, value: *mut i64) -> c_int;
+    pub fn bp_group_unique_id(id: *mut u8) -> c_int;
+    pub fn bp_group_init(cs: *mut bp_cs, id: *const u8, rank: c_int, world: c_int, out: *mut *mut bp_group) -> c_int;
+    pub fn bp_group_free(g: *mut bp_group);
+    pub fn bp_group_info(g: *mut bp_group, rank: *mut c_int, world: *mut c_int, transport: *mut c_int) -> c_int;
+    pub fn bp_group_check(g: *mut bp_group, row: *mut i64) -> c_int;
+    pub fn bp_group_check_async(g: *mut bp_group, dev_result: *mut i64) -> c_int;
+    pub fn bp_group_reduce_async(g: *mut bp_group, dev_result: *mut i64) -> c_int;
+    pub fn bp_group_broadcast_witness(g: *mut bp_group, root: c_int) -> c_int;
+    pub fn bp_group_set_witness_sharded(g: *mut bp_group, is_aux: c_int, slice_le: *const u64) -> c_int;
+    pub fn bp_split_rows_by_nnz(lens: *const u32, n_rows: u64, world: c_int, bounds: *mut u64) -> c_int;
     pub fn bp_cs_synth_rows(cs: *mut bp_cs, seed: u64, t: u32, n_vars: u64, n_inputs: u64, row0: u64, n_rows: u64) -> c_int;
     pub fn bp_cs_synth_witness(cs: *mut bp_cs, seed: u64, n_vars: u64, n_inputs: u64) -> c_int;
 }

@@ -483,7 +483,7 @@ def test_save_and_load_round_trip(tmp_path):
     open(bad, "wb").write(raw[:-8])
     assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -4 and not h3.value
     # a header of another layout version / byte order / impossible counts is not one of ours
-    for off, val in ((7, b"\x01"), (20, b"\x04\x03\x02\x01"), (16, b"\x10\x00\x00\x00")):
+    for off, val in ((7, b"\x01"), (20, b"\x01\x02\x03\x04"), (16, b"\x10\x00\x00\x00")):
         open(bad, "wb").write(raw[:off] + val + raw[off + len(val):])
         assert L.bp_cs_load(bad, 0, ctypes.byref(h3)) == -5 and not h3.value
 

@@ -38,26 +38,31 @@ def test_set_many_matches_oracle_and_rejects_bad_batches():
             new = [rng.randrange(p) for _ in idx]
             old = c_api.limbs_to_ints(aux[idx])
             ia = np.asarray(idx, np.uint64)
-            h.ok(h.L.bp_cs_set_many(h.h, 1, n, ia.ctypes.data, c_api.ints_to_limbs(new).ctypes.data))
+            va = c_api.ints_to_limbs(new)  # (kept alive across the call: `x.ctypes.data` of a temporary dangles)
+            h.ok(h.L.bp_cs_set_many(h.h, 1, n, ia.ctypes.data, va.ctypes.data))
             for i, v in zip(idx, new):
                 inst.set(True, i, v)
             assert h.first_unsatisfied() == inst.check(2, False) >= 0
             got = np.zeros((aux.shape[0], 4), np.uint64)
             h.ok(h.L.bp_cs_witness(h.h, 1, 0, aux.shape[0], got.ctypes.data))
             assert c_api.limbs_to_ints(got[idx]) == new
-            h.ok(h.L.bp_cs_set_many(h.h, 1, n, ia.ctypes.data, c_api.ints_to_limbs(old).ctypes.data))
+            va = c_api.ints_to_limbs(old)
+            h.ok(h.L.bp_cs_set_many(h.h, 1, n, ia.ctypes.data, va.ctypes.data))
             for i, v in zip(idx, old):
                 inst.set(True, i, v)
             assert h.first_unsatisfied() == -1
         # a batch with one bad entry changes nothing
         ia = np.asarray([3, aux.shape[0]], np.uint64)
-        assert h.L.bp_cs_set_many(h.h, 1, 2, ia.ctypes.data, c_api.ints_to_limbs([1, 2]).ctypes.data) == -3
+        va = c_api.ints_to_limbs([1, 2])
+        assert h.L.bp_cs_set_many(h.h, 1, 2, ia.ctypes.data, va.ctypes.data) == -3
         ia = np.asarray([3, 4], np.uint64)
-        assert h.L.bp_cs_set_many(h.h, 1, 2, ia.ctypes.data, c_api.ints_to_limbs([1, p]).ctypes.data) == -3
+        va = c_api.ints_to_limbs([1, p])
+        assert h.L.bp_cs_set_many(h.h, 1, 2, ia.ctypes.data, va.ctypes.data) == -3
         assert h.first_unsatisfied() == -1
         # inputs too (ONE is an ordinary slot: test_cs.rs:160-169)
         ia = np.asarray([0], np.uint64)
-        h.ok(h.L.bp_cs_set_many(h.h, 0, 1, ia.ctypes.data, c_api.ints_to_limbs([2]).ctypes.data))
+        va = c_api.ints_to_limbs([2])
+        h.ok(h.L.bp_cs_set_many(h.h, 0, 1, ia.ctypes.data, va.ctypes.data))
         inst.set(False, 0, 2)
         assert h.first_unsatisfied() == inst.check(2, False)
 
