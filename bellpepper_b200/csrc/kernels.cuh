@@ -1403,12 +1403,23 @@ struct LctTerm {
     uint32_t cls;
     uint32_t w[8], c[8];
 };
-__device__ __forceinline__ void lct_load(LctTerm& t, const LctView& v, const CsrView& m, size_t slot, uint64_t pol) {
-    const uint32_t col = ld32_stream(v.cols + slot, pol);
+// The three stages of a term's memory pipeline: its column word (coalesced stream, fetched three terms ahead), an L2 prefetch
+// of its witness element and coefficient (two terms ahead: no registers held while DRAM answers), the loads proper (one term
+// ahead: L2 hits by then).
+__device__ __forceinline__ const uint4* lct_witness_addr(uint32_t col, const CsrView& m) {
+    return ((col & kColAux) ? m.aux : m.inputs) + 2 * (size_t)(col & kColIdxMask);
+}
+template <int PF> __device__ __forceinline__ void lct_prefetch(uint32_t col, const LctView& v, const CsrView& m, size_t slot) {
+    if (PF == 0) return;
+    const uint32_t cls = (col >> kColClsShift) & 7u;
+    if (cls == kClsZero) return;
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(lct_witness_addr(col, m)));
+    if (PF >= 2 && is_product_class(cls)) asm volatile("prefetch.global.L2 [%0];" ::"l"(v.vals + 2 * slot));
+}
+__device__ __forceinline__ void lct_fetch(LctTerm& t, uint32_t col, const LctView& v, const CsrView& m, size_t slot) {
     t.cls = (col >> kColClsShift) & 7u;
     if (t.cls == kClsZero) return;  // zero coefficient, or padding
-    const bool is_aux = (col & kColAux) != 0;
-    ld256_keep(t.w, (is_aux ? m.aux : m.inputs) + 2 * (size_t)(col & kColIdxMask));
+    ld256_keep(t.w, lct_witness_addr(col, m));
     if (is_product_class(t.cls)) ld256_stream(t.c, v.vals + 2 * slot);
 }
 template <int F, int RIPPLE> __device__ __forceinline__ void lct_apply(uint32_t* acc, LctTerm& t, uint32_t& gen, uint32_t& mag) {
@@ -1433,7 +1444,9 @@ template <int F, int RIPPLE> __device__ __forceinline__ void lct_apply(uint32_t*
     }
 }
 
-template <int F, bool EMIT>
+// PF: 0 = no L2 prefetch (column words three terms ahead, operands one term ahead in registers), 1 = L2 prefetch of the witness
+// element two terms ahead, 2 = of the witness element and the coefficient.
+template <int F, bool EMIT, int PF>
 __global__ void __launch_bounds__(kLctThreads, 2) check_lct(CsrView m, LctView v, CheckOut o, FieldConsts fc) {
     __shared__ uint32_t s_ab[2][8][kLctRows];   // A.w / B.w of the tile's rows (8 limbs, < 2^256), limb-major
     __shared__ uint32_t s_c[17][kLctRows];      // unreduced sum of the (negated) C terms
@@ -1456,16 +1469,22 @@ __global__ void __launch_bounds__(kLctThreads, 2) check_lct(CsrView m, LctView v
             zeron<17>(acc);
             uint32_t gen = 0, mag = 0;
             const bool is_c = (id % 3u) == 2u;
+            // software pipeline over the slice's L groups (padding groups carry the null column word)
+            auto col_at = [&](uint32_t j) { return j < L ? ld32_stream(v.cols + slot0 + 32u * (size_t)j, pol) : kLctNullCol; };
+            uint32_t c0 = col_at(0), c1 = col_at(1), c2 = col_at(2);
+            lct_prefetch<PF>(c1, v, m, slot0 + 32u);
             LctTerm cur;
-            lct_load(cur, v, m, slot0, pol);
+            lct_fetch(cur, c0, v, m, slot0);
 #pragma unroll 1
             for (uint32_t j = 0; j < L; ++j) {
+                const uint32_t c3 = col_at(j + 3u);
+                lct_prefetch<PF>(c2, v, m, slot0 + 32u * (size_t)(j + 2u));
                 LctTerm nxt;
-                nxt.cls = kClsZero;
-                if (j + 1u < L) lct_load(nxt, v, m, slot0 + 32u * (size_t)(j + 1u), pol);
-                if (is_c) lct_apply<F, 17>(acc, cur, gen, mag);
-                else lct_apply<F, 9>(acc, cur, gen, mag);
+                lct_fetch(nxt, c1, v, m, slot0 + 32u * (size_t)(j + 1u));
+                lct_apply<F, 17>(acc, cur, gen, mag);  // (one code path for A, B and C lanes: a slice mixes them)
                 cur = nxt;
+                c1 = c2;
+                c2 = c3;
             }
             const uint32_t r = id / 3u;
             if (len) {

@@ -496,7 +496,7 @@ def test_load_rejects_inconsistent_row_offsets(tmp_path):
     from bellpepper_b200 import ffi
 
     fid = 0
-    lens, cols, coeffs, inputs, aux, _ = _gadget_like_instance(fid, 5, 200, 300, 3)
+    lens, cols, coeffs, inputs, aux, _ = _gadget_like_instance(fid, 5, 200, 1500, 3)
     n_rows = lens.size // 3
     path = str(tmp_path / "s.bpr1cs").encode()
     L = ffi.load()

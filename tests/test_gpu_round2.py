@@ -323,3 +323,38 @@ def test_group_of_two_ranks_matches_oracle(tmp_path, mailbox):
         for got, want in o["checks"]:
             assert got == want, (rk, o)
         assert o["witness_equal"]
+
+
+@pytest.mark.parametrize("fid,log_rows,t", [(0, 22, 6), (1, 20, 32)])
+def test_full_width_kernels_at_size_match_oracle(fid, log_rows, t):
+    """Parity at a size where 32-bit offsets, tile boundaries and the LC-tile layout matter: a
+    device-generated synthetic instance of 2^22 rows (t = 6) / 2^20 rows (t = 32); canonical A.w, B.w, C.w of row blocks at the
+    start, at odd offsets in the middle and at the very end bit for bit against the oracle (which generates only the witness
+    elements those rows read), with the streaming LC-tile kernel and with the thread-per-row kernel, and the two kernels agree
+    on EVERY row."""
+    import torch
+
+    n = 1 << log_rows
+    n_vars = n
+    with Handle(fid, reserve=(n, int(n * 3 * t * 1.02) + 4096, n_vars)) as h:
+        h.ok(h.L.bp_cs_synth_witness(h.h, synth.SEED, n_vars, synth.N_INPUTS))
+        for s in range(0, n, 1 << 20):
+            h.ok(h.L.bp_cs_synth_rows(h.h, synth.SEED, t, n_vars, synth.N_INPUTS, s, min(1 << 20, n - s)))
+        outs = {}
+        for sk in (1, 0):
+            h.opt("stream_kernel", sk)
+            assert h.opt("stream_kernel") == sk
+            dev = [torch.empty((n, 4), dtype=torch.int64, device="cuda:0") for _ in range(3)]
+            h.ok(h.L.bp_cs_eval_async(h.h, *[ctypes.c_void_p(x.data_ptr()) for x in dev]))
+            h.ok(h.L.bp_cs_sync(h.h))
+            outs[sk] = dev
+            assert h.first_unsatisfied() == 0  # random rows: the first one already fails
+        for a, b in zip(outs[1], outs[0]):
+            assert bool((a == b).all())
+        blk = 3000
+        for r0 in (0, 255, n // 2 - 1234, n - blk):
+            inst = c_api.synth_sparse_instance(fid, synth.SEED, t, n_vars, synth.N_INPUTS, r0, blk)
+            bad, az, bz, cz = inst.eval(2)
+            for dev_t, ref in zip(outs[1], (az, bz, cz)):
+                assert (dev_t[r0:r0 + blk].cpu().numpy().view(np.uint64) == ref).all()
+            inst.close()
