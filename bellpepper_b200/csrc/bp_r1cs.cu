@@ -113,6 +113,8 @@ struct bp_cs {
     bool use_graph = true;      // bp_cs_set_option("graph", 0) turns it off
     uint64_t plan_gen = 0;      // bumped whenever the plan is rebuilt
     int64_t graph_replays = 0, graph_captures = 0;
+    DevBuf wprog, wprog_in;       // witness program (kernels.cuh: wprog_run) and its per-run inputs (message bytes, chaining states)
+    uint32_t wprog_hdr[16] = {};  // host copy of the program header (0 = none installed)
     void* h_pack = nullptr;       // pinned: bit-packed witness produced by bp_cs_recheck_scalars (inputs, then aux 64-byte aligned)
     size_t h_pack_cap = 0;
     void* h_patch = nullptr;      // pinned: exception list of the same call / batch of bp_cs_set_many (indices, then values)
@@ -980,6 +982,8 @@ void bp_cs_free(bp_cs* h) {
     if (h->h_pack) cudaFreeHost(h->h_pack);
     if (h->h_patch) cudaFreeHost(h->h_patch);
     if (h->patch_stage.p) cudaFree(h->patch_stage.p);
+    if (h->wprog.p) cudaFree(h->wprog.p);
+    if (h->wprog_in.p) cudaFree(h->wprog_in.p);
     for (int s = 0; s < kNumStage; ++s) {
         if (h->h_stage[s]) cudaFreeHost(h->h_stage[s]);
         if (h->stage_ev[s]) cudaEventDestroy(h->stage_ev[s]);
@@ -1830,6 +1834,128 @@ int bp_cs_synth_witness(bp_cs* h, uint64_t seed, uint64_t n_vars, uint64_t n_inp
 
 
 }  // extern "C"
+
+// ---- witness program: generate the next witness on the device ---------------------------------------------------
+namespace {
+// Everything the kernel indexes with is checked here, once: a malformed program is refused, never run.
+const char* wprog_validate(const uint32_t* w, uint64_t n_words, uint64_t n_aux) {
+    if (n_words < kWpHeaderWords || w[0] != kWpMagic || w[1] != 1) return "not a witness program (magic / version)";
+    const uint64_t n_units = w[2], n_tapes = w[3], msg_base = w[4], n_msg = w[5], total = w[7], unit_off = w[10], tape_off = w[11];
+    if (w[12] != n_words || total != n_aux) return "program size or variable count does not match the system";
+    if (unit_off != kWpHeaderWords || tape_off != unit_off + 4 * n_units || tape_off + 8 * n_tapes > n_words || !n_units || !n_tapes)
+        return "bad section offsets";
+    if (msg_base + n_msg > n_aux) return "message bits exceed the aux space";
+    std::vector<uint32_t> tape_vars(n_tapes);
+    for (uint64_t t = 0; t < n_tapes; ++t) {
+        const uint32_t* tr = w + tape_off + 8 * t;
+        const uint64_t n_vars = tr[0], lev = tr[1], n_lev = tr[2], ent = tr[3], n_ent = tr[4], sum = tr[5], n_sum = tr[6], sop = tr[7];
+        tape_vars[t] = tr[0];
+        if (lev % 4 || ent % 4 || lev + 4 * n_lev > n_words || ent + 4 * n_ent > n_words || sum + 4 * n_sum > n_words || sop > n_words ||
+            n_vars >= (1u << 24) || n_ent != n_vars || n_sum > w[9] || n_vars > w[8])
+            return "bad tape record";
+        uint64_t e_prev = 0, s_prev = 0;
+        for (uint64_t l = 0; l < n_lev; ++l) {
+            const uint32_t* lr = w + lev + 4 * l;
+            if (lr[0] != e_prev || lr[1] < lr[0] || lr[1] > n_ent || lr[2] != s_prev || lr[3] < lr[2] || lr[3] > n_sum) return "bad level record";
+            e_prev = lr[1];
+            s_prev = lr[3];
+        }
+        if (e_prev != n_ent || s_prev != n_sum) return "levels do not cover the tape";
+        uint64_t max_sop = 0;
+        auto operand_ok = [&](uint32_t op, uint32_t mask) {
+            const uint32_t kind = op >> 29, p = op & mask;
+            if (kind < 2) return true;
+            if (kind < 4) return p < n_vars;
+            if (kind < 6) return true;  // message offsets depend on the unit: checked below per unit through max_msg
+            return p < 256u;
+        };
+        for (uint64_t k = 0; k < n_sum; ++k) {
+            const uint32_t* sr = w + sum + 4 * k;
+            if ((uint64_t)sop + sr[0] + sr[1] > n_words) return "sum operands out of range";
+            max_sop = std::max<uint64_t>(max_sop, (uint64_t)sr[0] + sr[1]);
+            for (uint32_t i = 0; i < sr[1]; ++i)
+                if (!operand_ok(w[sop + sr[0] + i], 0x00ffffffu)) return "bad sum operand";
+        }
+        std::vector<uint8_t> written(n_vars, 0);
+        for (uint64_t e = 0; e < n_ent; ++e) {
+            const uint32_t* er = w + ent + 4 * e;
+            const uint32_t op = er[0] >> 28, res = er[0] & 0x0fffffffu;
+            if (res >= n_vars || written[res] || op == kWpFree || op > kWpSumBit) return "bad tape entry";
+            written[res] = 1;
+            if (op == kWpSumBit) {
+                if (er[1] >= n_sum || er[2] >= 64) return "bad sum bit";
+            } else if (!operand_ok(er[1], 0x1fffffffu) || !operand_ok(er[2], 0x1fffffffu) ||
+                       ((op == kWpCh || op == kWpMaj) && !operand_ok(er[3], 0x1fffffffu))) {
+                return "bad operand";
+            }
+        }
+    }
+    // units: tapes exist, variables inside the aux space and disjoint from the message bits, message windows inside the message
+    for (uint64_t u = 0; u < n_units; ++u) {
+        const uint32_t* ur = w + unit_off + 4 * u;
+        if (ur[0] >= n_tapes || (uint64_t)ur[1] + tape_vars[ur[0]] > n_aux || ur[3] >= n_units || ur[2] > n_msg) return "bad unit record";
+    }
+    // message operand offsets: at most 2^24 past the unit's base by construction; bound them by the message length here
+    for (uint64_t u = 0; u < n_units; ++u) {
+        const uint32_t* ur = w + unit_off + 4 * u;
+        const uint32_t* tr = w + tape_off + 8 * ur[0];
+        const uint64_t room = n_msg - ur[2];
+        auto msg_ok = [&](uint32_t op, uint32_t mask) { const uint32_t k = op >> 29; return k < 4 || k >= 6 || (op & mask) < room; };
+        for (uint64_t e = 0; e < tr[4]; ++e) {
+            const uint32_t* er = w + tr[3] + 4 * e;
+            if ((er[0] >> 28) != kWpSumBit && !(msg_ok(er[1], 0x1fffffffu) && msg_ok(er[2], 0x1fffffffu) && msg_ok(er[3], 0x1fffffffu)))
+                return "message operand past the end of the message";
+        }
+        for (uint64_t k = 0; k < tr[6]; ++k) {
+            const uint32_t* sr = w + tr[5] + 4 * k;
+            for (uint32_t i = 0; i < sr[1]; ++i)
+                if (!msg_ok(w[tr[7] + sr[0] + i], 0x00ffffffu)) return "message operand past the end of the message";
+        }
+    }
+    return nullptr;
+}
+}  // namespace
+
+extern "C" int bp_cs_set_witness_program(bp_cs* h, const uint32_t* words, uint64_t n_words) {
+    if (!h || !words) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (const char* why = wprog_validate(words, n_words, h->n_aux)) return fail(h, BP_E_ARG, "bp_cs_set_witness_program: %s", why);
+    int rc = ensure(h, h->wprog, (size_t)n_words * 4, 0);
+    if (rc != BP_OK) return rc;
+    CU(h, cudaMemcpyAsync(h->wprog.p, words, (size_t)n_words * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(h->wprog_hdr, words, sizeof h->wprog_hdr);
+    return BP_OK;
+}
+
+extern "C" int bp_cs_generate_witness_async(bp_cs* h, const uint8_t* msg, uint64_t msg_len, const uint32_t* states, uint64_t n_state_words) {
+    if (!h || !msg || !states) return BP_E_ARG;
+    if (h->wprog_hdr[0] != kWpMagic) return fail(h, BP_E_STATE, "no witness program installed (bp_cs_set_witness_program)");
+    const uint32_t n_units = h->wprog_hdr[2], n_msg_bits = h->wprog_hdr[5];
+    if (msg_len * 8 != n_msg_bits || n_state_words != 8ull * n_units || h->wprog_hdr[7] != h->n_aux)
+        return fail(h, BP_E_ARG, "bp_cs_generate_witness: message of %llu bits / %llu state words, program wants %u / %llu",
+                    (unsigned long long)(msg_len * 8), (unsigned long long)n_state_words, n_msg_bits, (unsigned long long)(8ull * n_units));
+    CU(h, cudaSetDevice(h->device));
+    const size_t state_off = ((size_t)msg_len + 15) & ~size_t(15);
+    int rc = ensure(h, h->wprog_in, state_off + (size_t)n_state_words * 4, 0);
+    if (rc != BP_OK) return rc;
+    if ((rc = upload(h, h->wprog_in.p, msg, (size_t)msg_len)) != BP_OK) return rc;
+    if ((rc = upload(h, (char*)h->wprog_in.p + state_off, states, (size_t)n_state_words * 4)) != BP_OK) return rc;
+    uint32_t* aux_shadow = shadow_ptr(h, 1);
+    h->wide_valid = false;  // only the shadows are written (kernels.cuh: ld_witness)
+    wprog_expand_msg<<<grid_for(h, n_msg_bits, 256, 8), 256, 0, h->stream>>>((const uint8_t*)h->wprog_in.p, n_msg_bits, h->wprog_hdr[6],
+                                                                            aux_shadow + h->wprog_hdr[4]);
+    const uint32_t bit_words = (h->wprog_hdr[8] + 31) / 32 + 1, sum_slots = h->wprog_hdr[9] + 1;
+    const size_t smem = (size_t)kWpWarps * ((size_t)sum_slots * 8 + (size_t)bit_words * 4);
+    if (smem > 200 * 1024) return fail(h, BP_E_RANGE, "witness program unit too large for shared memory");
+    if (smem > 48 * 1024) CU(h, cudaFuncSetAttribute(wprog_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_units + kWpWarps - 1) / kWpWarps, (uint64_t)h->sm_count * 16));
+    wprog_run<<<grid, 32 * kWpWarps, smem, h->stream>>>((const uint32_t*)h->wprog.p, (const uint8_t*)h->wprog_in.p,
+                                                        (const uint32_t*)((char*)h->wprog_in.p + state_off), aux_shadow, n_units, bit_words, sum_slots);
+    h->launches += 2;
+    CU(h, cudaGetLastError());
+    return settle(h);
+}
 
 // ---- K4: batched set (test_cs.rs:270-282) ----------------------------------------------------------------------------------
 namespace {

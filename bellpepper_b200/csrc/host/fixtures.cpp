@@ -39,6 +39,8 @@ struct bp_tcs {
     std::unique_ptr<TestConstraintSystem> named_cs;
     std::unique_ptr<BulkConstraintSystem> bulk_cs;
     std::string err;
+    bool record_tape = false;        // bp_tcs_record_witness_program: the next sha256 synthesis also records its witness tape
+    std::vector<uint32_t> wprog;     // the program built from it (wtape.hpp)
 };
 
 namespace {
@@ -85,7 +87,15 @@ void bits_to_bytes_be(const std::vector<Boolean>& bits, uint8_t* out) {
 // global_before[i] = rows that precede its first row in the WHOLE circuit, local_before[i] = kept rows that precede it.
 template <class CS>
 void sha256_ranges(CS& cs, FilterSink& fs, const uint8_t* msg, uint64_t len, const uint64_t* ranges, uint64_t n_ranges, uint8_t digest[32],
-                   uint64_t* global_before, uint64_t* local_before) {
+                   uint64_t* global_before, uint64_t* local_before, WitnessTape* tape = nullptr) {
+    struct TapeScope {  // recording is on exactly while this synthesis runs
+        explicit TapeScope(WitnessTape* t) { g_tape = t; }
+        ~TapeScope() { g_tape = nullptr; }
+    } tape_scope(tape);
+    if (tape) {
+        tape->aux_base = cs.num_aux();
+        tape->n_msg_bits = 8 * len;
+    }
     auto keep_block = [&](uint64_t blk, uint64_t* which) {
         for (uint64_t i = 0; i < n_ranges; ++i)
             if (blk >= ranges[2 * i] && blk < ranges[2 * i + 1]) {
@@ -124,6 +134,14 @@ void sha256_ranges(CS& cs, FilterSink& fs, const uint8_t* msg, uint64_t len, con
             if (local_before) local_before[which] = blk == 0 ? 0 : kept;
         }
         fs.rows_enabled = keep;
+        if (tape) {  // a unit of the witness program: its message window and which variables carry the chaining state
+            tape->begin_unit(512 * blk);
+            for (uint32_t j = 0; j < 8; ++j)
+                for (uint32_t i = 0; i < 32; ++i) {
+                    const Boolean& b = cur[j].bits[i];
+                    if (!b.is_constant()) tape->units.back().state[b.bit.variable.index()] = (32 * j + i) | (b.kind == Boolean::Not ? 0x80000000u : 0u);
+                }
+        }
         auto ns = cs.ns([&] { return "block " + std::to_string(blk); });
         cur = sha256_compression_function(ns, padded.data() + 512 * blk, cur);
         cs.flush();
@@ -210,10 +228,11 @@ int bp_tcs_sha256_block(bp_tcs* t, const uint8_t block[64], uint8_t out32[32]) {
 
 int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t bb, uint64_t be, uint8_t digest[32], uint64_t* rows_before) {
     if (!t || (!msg && len) || !digest) return BP_E_ARG;
-    return guarded(t, [&] {
-        if (t->named) sha256_sharded(*t->named_cs, *t->filter, msg, len, bb, be, digest, rows_before);
-        else sha256_sharded(*t->bulk_cs, *t->filter, msg, len, bb, be, digest, rows_before);
-    });
+    const uint64_t r[2] = {bb, be};
+    uint64_t g = 0, l = 0;
+    const int rc = bb < be ? bp_tcs_sha256_ranges(t, msg, len, r, 1, digest, &g, &l) : BP_E_ARG;
+    if (rc == BP_OK && rows_before) *rows_before = g;
+    return rc;
 }
 
 int bp_tcs_sha256_ranges(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint64_t* ranges, uint64_t n_ranges, uint8_t digest[32],
@@ -222,9 +241,73 @@ int bp_tcs_sha256_ranges(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint
     for (uint64_t i = 0; i < n_ranges; ++i)
         if (ranges[2 * i] >= ranges[2 * i + 1] || (i && ranges[2 * i] < ranges[2 * i - 1])) return BP_E_ARG;
     return guarded(t, [&] {
-        if (t->named) sha256_ranges(*t->named_cs, *t->filter, msg, len, ranges, n_ranges, digest, global_before, local_before);
-        else sha256_ranges(*t->bulk_cs, *t->filter, msg, len, ranges, n_ranges, digest, global_before, local_before);
+        WitnessTape tape;
+        WitnessTape* tp = t->record_tape ? &tape : nullptr;
+        if (t->named) sha256_ranges(*t->named_cs, *t->filter, msg, len, ranges, n_ranges, digest, global_before, local_before, tp);
+        else sha256_ranges(*t->bulk_cs, *t->filter, msg, len, ranges, n_ranges, digest, global_before, local_before, tp);
+        if (tp) {
+            t->wprog = tape.build_program(t->named ? t->named_cs->num_aux() : t->bulk_cs->num_aux(), /*msb_first=*/true);
+            if (!tape.ok) throw std::runtime_error("witness tape: " + tape.why);
+        }
     });
+}
+
+int bp_tcs_record_witness_program(bp_tcs* t, int on) {
+    if (!t) return BP_E_ARG;
+    t->record_tape = on != 0;
+    return BP_OK;
+}
+
+int bp_tcs_witness_program(bp_tcs* t, const uint32_t** words, uint64_t* n_words) {
+    if (!t || !words || !n_words) return BP_E_ARG;
+    if (t->wprog.empty()) {
+        t->err = "no witness program recorded (bp_tcs_record_witness_program before the synthesis)";
+        return BP_E_STATE;
+    }
+    *words = t->wprog.data();
+    *n_words = t->wprog.size();
+    return BP_OK;
+}
+
+// Chaining states of sha256 over `len` message bytes: 8 words BEFORE each compression block (block 0: the IV), blocks as the
+// gadget pads them (sha256.rs:50-77).  Plain SHA-256 on the host: what bp_cs_generate_witness_async wants per unit.
+int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, uint64_t max_blocks, uint64_t* n_blocks) {
+    if ((!msg && len) || !n_blocks) return BP_E_ARG;
+    using sha256_detail::IV;
+    using sha256_detail::K;
+    const uint64_t blocks = (len + 9 + 63) / 64;
+    *n_blocks = blocks;
+    if (!states) return BP_OK;
+    if (max_blocks < blocks) return BP_E_RANGE;
+    uint32_t h[8];
+    std::memcpy(h, IV, sizeof h);
+    auto rotr = [](uint32_t x, unsigned r) { return (x >> r) | (x << (32 - r)); };
+    for (uint64_t b = 0; b < blocks; ++b) {
+        std::memcpy(states + 8 * b, h, sizeof h);
+        uint8_t blk[64];
+        for (unsigned i = 0; i < 64; ++i) {
+            const uint64_t p = 64 * b + i;
+            uint8_t v = 0;
+            if (p < len) v = msg[p];
+            else if (p == len) v = 0x80;
+            else if (p >= 64 * blocks - 8) v = (uint8_t)((8 * len) >> (8 * (64 * blocks - 1 - p)));
+            blk[i] = v;
+        }
+        uint32_t w[64];
+        for (unsigned i = 0; i < 16; ++i) w[i] = (uint32_t)blk[4 * i] << 24 | (uint32_t)blk[4 * i + 1] << 16 | (uint32_t)blk[4 * i + 2] << 8 | blk[4 * i + 3];
+        for (unsigned i = 16; i < 64; ++i) {
+            const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = h[0], bb = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (unsigned i = 0; i < 64; ++i) {
+            const uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & bb) ^ (a & c) ^ (bb & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = bb; bb = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += bb; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    return BP_OK;
 }
 
 int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint8_t digest[32]) {

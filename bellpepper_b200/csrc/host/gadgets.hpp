@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "cs.hpp"
+#include "wtape.hpp"
 
 namespace bph {
 
@@ -33,6 +34,7 @@ struct AllocatedBit {
 
     template <class CS> static AllocatedBit alloc(CS&& cs, OptBool value) {  // boolean.rs:68-97
         const Variable var = cs.alloc([] { return std::string("boolean"); }, [&] { return bit_value(value); });
+        if (g_tape) g_tape->on_alloc(var);  // a free bit, or the next bit of the addmany sum being recorded
         cs.enforce([] { return std::string("boolean constraint"); },
                    [&](LinearCombination lc) { return std::move(lc) + one_var() - var; },
                    [&](LinearCombination lc) { return std::move(lc) + var; },
@@ -47,6 +49,7 @@ struct AllocatedBit {
             rv = a.value ^ b.value;
             return rv ? Fr::one() : Fr::zero();
         });
+        if (g_tape) g_tape->on_op(kTapeXor, r, WitnessTape::operand(a.variable, false), WitnessTape::operand(b.variable, false));
         cs.enforce([] { return std::string("xor constraint"); },
                    [&](LinearCombination lc) { return std::move(lc) + a.variable + a.variable; },
                    [&](LinearCombination lc) { return std::move(lc) + b.variable; },
@@ -61,6 +64,7 @@ struct AllocatedBit {
             rv = a.value & b.value;
             return rv ? Fr::one() : Fr::zero();
         });
+        if (g_tape) g_tape->on_op(kTapeAnd, r, WitnessTape::operand(a.variable, false), WitnessTape::operand(b.variable, false));
         cs.enforce([] { return std::string("and constraint"); },
                    [&](LinearCombination lc) { return std::move(lc) + a.variable; },
                    [&](LinearCombination lc) { return std::move(lc) + b.variable; },
@@ -75,6 +79,7 @@ struct AllocatedBit {
             rv = a.value & (b.value ^ 1);
             return rv ? Fr::one() : Fr::zero();
         });
+        if (g_tape) g_tape->on_op(kTapeAndNot, r, WitnessTape::operand(a.variable, false), WitnessTape::operand(b.variable, false));
         cs.enforce([] { return std::string("and not constraint"); },
                    [&](LinearCombination lc) { return std::move(lc) + a.variable; },
                    [&](LinearCombination lc) { return std::move(lc) + one_var() - b.variable; },
@@ -89,6 +94,7 @@ struct AllocatedBit {
             rv = (a.value ^ 1) & (b.value ^ 1);
             return rv ? Fr::one() : Fr::zero();
         });
+        if (g_tape) g_tape->on_op(kTapeNor, r, WitnessTape::operand(a.variable, false), WitnessTape::operand(b.variable, false));
         cs.enforce([] { return std::string("nor constraint"); },
                    [&](LinearCombination lc) { return std::move(lc) + one_var() - a.variable; },
                    [&](LinearCombination lc) { return std::move(lc) + one_var() - b.variable; },
@@ -139,6 +145,11 @@ struct Boolean {  // boolean.rs:368-376
         }
     }
 
+    uint32_t tape_operand() const {  // witness tape (wtape.hpp): constant / variable / negated variable
+        if (kind == Constant) return c ? kOpConst1 : kOpConst0;
+        return WitnessTape::operand(bit.variable, kind == Not);
+    }
+
     template <class CS> static Boolean xor_(CS&& cs, const Boolean& a, const Boolean& b) {  // boolean.rs:472-491
         if (a.kind == Constant && !a.c) return b;
         if (b.kind == Constant && !b.c) return a;
@@ -173,6 +184,7 @@ struct Boolean {  // boolean.rs:368-376
         if (b.kind == Constant && b.c) return and_(cs, a.not_(), c.not_()).not_();
         const Field* f = cs.field();
         const Variable ch = cs.alloc([] { return std::string("ch"); }, [&] { return bit_value(chv); });
+        if (g_tape) g_tape->on_op(kTapeCh, ch, a.tape_operand(), b.tape_operand(), c.tape_operand());
         cs.enforce([] { return std::string("ch computation"); },
                    [&](LinearCombination) { return b.lc(f, one_var(), Fr::one()) - c.lc(f, one_var(), Fr::one()); },
                    [&](LinearCombination) { return a.lc(f, one_var(), Fr::one()); },
@@ -192,6 +204,7 @@ struct Boolean {  // boolean.rs:368-376
         if (a.kind == Constant && a.c) return and_(cs, b.not_(), c.not_()).not_();
         const Field* f = cs.field();
         const Variable maj = cs.alloc([] { return std::string("maj"); }, [&] { return bit_value(mv); });
+        if (g_tape) g_tape->on_op(kTapeMaj, maj, a.tape_operand(), b.tape_operand(), c.tape_operand());
         Boolean bc = constant(false);
         {
             auto ns = cs.ns([] { return std::string("b and c"); });
@@ -371,6 +384,11 @@ struct UInt32 {
         LinearCombination result_lc(f);
         Fr coeff = Fr::one();
         unsigned i = 0;
+        if (g_tape) {  // the result bits allocated below are the bits of this integer sum
+            g_tape->begin_sum();
+            for (size_t k = 0; k < n_ops; ++k)
+                for (unsigned bi = 0; bi < 32; ++bi) g_tape->sum_operand(operands[k].bits[bi].tape_operand(), bi);
+        }
         while (max_value != 0) {
             AllocatedBit b{Variable{0}, kNone};
             {
@@ -383,6 +401,7 @@ struct UInt32 {
             ++i;
             coeff = f->dbl(coeff);
         }
+        if (g_tape) g_tape->end_sum();
         cs.get_root().enforce_equal(i, lc, result_lc);
         return out;
     }

@@ -1601,6 +1601,111 @@ __global__ void group_exchange(long long* word, GroupSlot* const* __restrict__ b
     }
 }
 
+// ---- witness program: the witness of a bit-logic gadget circuit generated on the device ----------------------
+// Replaces, for the NEXT witness of an already synthesized circuit, the host closures of the gadgets (boolean.rs:68-272,
+// 536-759; uint32.rs:306-406; sha256.rs:83-272) and the upload of their results.  The program (csrc/host/wtape.hpp builds it
+// while the circuit is synthesized; layout in include/bp_r1cs.h) holds, per unit (e.g. one sha256 compression block), a tape:
+// one entry per aux variable of the unit -- XOR / AND / AND_NOT / NOR / CH / MAJ of earlier values, or bit j of an integer sum
+// of weighted bits (addmany) -- sorted into dependency levels.  One WARP evaluates one unit: the unit's values live in shared
+// memory as a bit set (lanes OR their result bits in), a level's sums are reduced cooperatively (lanes stride the operands,
+// shuffle-add), its entries are one per lane; operands outside the unit are bits of the message bytes or of the unit's
+// chaining state (host-supplied: 8 words per unit).  At the end the warp writes the unit's values into the witness shadows.
+constexpr uint32_t kWpMagic = 0x50575042u, kWpHeaderWords = 16;
+constexpr uint32_t kWpFree = 0, kWpXor = 1, kWpAnd = 2, kWpAndNot = 3, kWpNor = 4, kWpCh = 5, kWpMaj = 6, kWpSumBit = 7;
+constexpr int kWpWarps = 4;  // warps (= units) per CTA
+
+__global__ void wprog_expand_msg(const uint8_t* __restrict__ msg, uint64_t n_bits, uint32_t msb_first, uint32_t* __restrict__ shadow) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_bits; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = msg[i >> 3];
+        shadow[i] = msb_first ? (b >> (7u - (uint32_t)(i & 7u))) & 1u : (b >> (uint32_t)(i & 7u)) & 1u;
+    }
+}
+
+struct WpUnit {
+    const uint32_t* bits;     // shared: the unit's values
+    const uint8_t* msg;
+    const uint32_t* state;    // 8 words
+    uint32_t msg_bit_base, msb_first;
+};
+__device__ __forceinline__ uint32_t wp_value(uint32_t op, uint32_t payload_mask, const WpUnit& u) {
+    const uint32_t kind = op >> 29, p = op & payload_mask;
+    uint32_t v;
+    if (kind < 2u) {
+        v = kind;
+    } else if (kind < 4u) {
+        v = (u.bits[p >> 5] >> (p & 31u)) & 1u;
+    } else if (kind < 6u) {
+        const uint32_t g = u.msg_bit_base + p, b = u.msg[g >> 3];
+        v = u.msb_first ? (b >> (7u - (g & 7u))) & 1u : (b >> (g & 7u)) & 1u;
+    } else {
+        v = (u.state[p >> 5] >> (p & 31u)) & 1u;
+    }
+    return (kind >= 2u && (kind & 1u)) ? v ^ 1u : v;
+}
+
+__global__ void __launch_bounds__(32 * kWpWarps) wprog_run(const uint32_t* __restrict__ prog, const uint8_t* __restrict__ msg,
+                                                           const uint32_t* __restrict__ states, uint32_t* __restrict__ aux_shadow, uint32_t n_units,
+                                                           uint32_t bit_words /*per warp*/, uint32_t sum_slots /*per warp*/) {
+    extern __shared__ __align__(16) unsigned char wp_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long* sumv = reinterpret_cast<unsigned long long*>(wp_smem) + (size_t)warp * sum_slots;
+    uint32_t* bits = reinterpret_cast<uint32_t*>(wp_smem + (size_t)kWpWarps * sum_slots * 8u) + (size_t)warp * bit_words;
+    const uint32_t unit_off = prog[10], tape_off = prog[11], msb_first = prog[6];
+    for (uint32_t unit = blockIdx.x * kWpWarps + warp; unit < n_units; unit += gridDim.x * kWpWarps) {
+        const uint32_t* ur = prog + unit_off + 4u * unit;
+        const uint32_t* tr = prog + tape_off + 8u * ur[0];
+        const uint32_t n_vars = tr[0], n_levels = tr[2];
+        const uint32_t* levels = prog + tr[1];
+        const uint32_t* ents = prog + tr[3];
+        const uint32_t* sums = prog + tr[5];
+        const uint32_t* sumops = prog + tr[7];
+        WpUnit u{bits, msg, states + 8u * ur[3], ur[2], msb_first};
+        for (uint32_t i = lane; i < (n_vars + 31u) / 32u; i += 32u) bits[i] = 0u;
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t l = 0; l < n_levels; ++l) {
+            const uint32_t e0 = __ldg(levels + 4u * l), e1 = __ldg(levels + 4u * l + 1), s0 = __ldg(levels + 4u * l + 2),
+                           s1 = __ldg(levels + 4u * l + 3);
+#pragma unroll 1
+            for (uint32_t s = s0; s < s1; ++s) {  // integer sums of this level: lanes stride the weighted bits
+                const uint32_t first = __ldg(sums + 4u * s), n_ops = __ldg(sums + 4u * s + 1);
+                unsigned long long acc = 0;
+                for (uint32_t k = lane; k < n_ops; k += 32u) {
+                    const uint32_t op = __ldg(sumops + first + k);
+                    acc += (unsigned long long)wp_value(op, 0x00ffffffu, u) << ((op >> 24) & 31u);
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                if (lane == 0) sumv[s] = acc + (((unsigned long long)__ldg(sums + 4u * s + 3) << 32) | __ldg(sums + 4u * s + 2));
+            }
+            __syncwarp();
+            for (uint32_t e = e0 + lane; e < e1; e += 32u) {
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(ents) + e);
+                const uint32_t op = r.x >> 28, res = r.x & 0x0fffffffu;
+                uint32_t v;
+                if (op == kWpSumBit) {
+                    v = (uint32_t)(sumv[r.y] >> r.z) & 1u;
+                } else {
+                    const uint32_t a = wp_value(r.y, 0x1fffffffu, u), b = wp_value(r.z, 0x1fffffffu, u);
+                    if (op == kWpXor) v = a ^ b;
+                    else if (op == kWpAnd) v = a & b;
+                    else if (op == kWpAndNot) v = a & (b ^ 1u);
+                    else if (op == kWpNor) v = (a ^ 1u) & (b ^ 1u);
+                    else {
+                        const uint32_t c = wp_value(r.w, 0x1fffffffu, u);
+                        v = op == kWpCh ? ((a & b) ^ ((a ^ 1u) & c)) : ((a & b) ^ (a & c) ^ (b & c));
+                    }
+                }
+                if (v) atomicOr(bits + (res >> 5), 1u << (res & 31u));
+            }
+            __syncwarp();
+        }
+        uint32_t* out = aux_shadow + ur[1];
+        for (uint32_t i = lane; i < n_vars; i += 32u) out[i] = (bits[i >> 5] >> (i & 31u)) & 1u;
+        __syncwarp();
+    }
+}
+
 // ---- K3: ingest conversion ------------------------------------------------------------------------------------------------
 // Pass 1, one thread per LC of the chunk: an A/B LC is "plain" when every coefficient is a small signed integer and the
 // magnitudes sum to <= 7 (so its value stays below 8p); C LCs are classed per term.  kind: 0 = general, 1 = plain.

@@ -53,6 +53,8 @@ SIGNATURES = {
     "bp_cs_set_many": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, vp, vp]),
     "bp_cs_recheck_scalars": (ctypes.c_int, [vp, vp, vp, i64p]),
     "bp_cs_recheck_scalars_async": (ctypes.c_int, [vp, vp, vp, vp]),
+    "bp_cs_set_witness_program": (ctypes.c_int, [vp, vp, ctypes.c_uint64]),
+    "bp_cs_generate_witness_async": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, ctypes.c_uint64]),
     "bp_group_unique_id": (ctypes.c_int, [vp]),
     "bp_group_init": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
     "bp_group_free": (None, [vp]),

@@ -23,6 +23,9 @@ _SIGS = {
     "bp_tcs_sha256": (ctypes.c_int, [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, u64p]),
     "bp_tcs_sha256_ranges": (ctypes.c_int, [vp, vp, ctypes.c_uint64, u64p, ctypes.c_uint64, vp, u64p, u64p]),
     "bp_tcs_blake2s": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, vp]),
+    "bp_tcs_record_witness_program": (ctypes.c_int, [vp, ctypes.c_int]),
+    "bp_tcs_witness_program": (ctypes.c_int, [vp, ctypes.POINTER(vp), u64p]),
+    "bp_sha256_chain_states": (ctypes.c_int, [vp, ctypes.c_uint64, vp, ctypes.c_uint64, u64p]),
     "bp_wcs_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "bp_tcs_which_is_unsatisfied": (ctypes.c_int64, [vp, vp, ctypes.c_uint64]),
     "bp_tcs_set": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
@@ -138,6 +141,15 @@ class Tcs:
         self._ck(self.L.bp_tcs_sha256_ranges(self.t, msg, len(msg), flat, len(ranges), out, gb, lb))
         return out.raw, [(int(g), int(l)) for g, l in zip(gb, lb)]
 
+    def record_witness_program(self, on: bool = True):
+        self._ck(self.L.bp_tcs_record_witness_program(self.t, int(on)))
+
+    def witness_program(self) -> np.ndarray:
+        """The device witness program recorded by the last sha256 synthesis (uint32 words; include/bp_r1cs.h)."""
+        p, n = vp(), ctypes.c_uint64()
+        self._ck(self.L.bp_tcs_witness_program(self.t, ctypes.byref(p), ctypes.byref(n)))
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)), shape=(n.value,)).copy()
+
     def blake2s(self, msg: bytes, personalization: bytes = b"12345678") -> bytes:
         assert len(personalization) == 8
         out = ctypes.create_string_buffer(32)
@@ -234,7 +246,7 @@ def sha256_chain_host_csr(field: int, blocks: int):
         return t.host_csr()
 
 
-def sha256_chain_into_new_handle(field: int, device: int, blocks: int, rank: int = 0, world: int = 1):
+def sha256_chain_into_new_handle(field: int, device: int, blocks: int, rank: int = 0, world: int = 1, record_witness_program: bool = False):
     """BASELINE configs[1]: sha256 gadget over `blocks` chained compression blocks, rows of this rank's block range
     streamed into a fresh device handle.  Returns (bp_cs handle as c_void_p, info); the caller frees via `info['tcs']`."""
     # rows are what is balanced: the shard holding block 0 also holds the 8 * len(msg) boolean rows of the input bits
@@ -244,9 +256,23 @@ def sha256_chain_into_new_handle(field: int, device: int, blocks: int, rank: int
     per_block_rows, per_block_terms, per_block_vars = 26400, 170000, 26500
     t = Tcs(field, device, named=False,
             reserve=((b1 - b0) * per_block_rows + 4096, (b1 - b0) * per_block_terms + 65536, blocks * per_block_vars + 4096))
+    if record_witness_program:
+        t.record_witness_program()
     digest, before = t.sha256(chain_message(blocks), b0, b1)
     L = ffi.load()
     h = vp(t.handle)
     assert L.bp_cs_set_row_base(h, before) == 0
     info = {"rows_total": t.num_constraints(), "row0": before, "blocks": blocks, "digest": digest.hex(), "tcs": t}
+    if record_witness_program:
+        info["witness_program"] = t.witness_program()
     return h, info
+
+
+def sha256_chain_states(msg: bytes) -> np.ndarray:
+    """uint32[blocks, 8]: the hash state before each compression block (plain SHA-256 on the host)."""
+    L = _host_lib()
+    n = ctypes.c_uint64()
+    assert L.bp_sha256_chain_states(msg, len(msg), None, 0, ctypes.byref(n)) == 0
+    out = np.zeros((n.value, 8), np.uint32)
+    assert L.bp_sha256_chain_states(msg, len(msg), out.ctypes.data, n.value, ctypes.byref(n)) == 0
+    return out

@@ -246,7 +246,7 @@ def build_workload(ctx, name):
     elif kind == "sha256":
         from bellpepper_b200 import fixtures
 
-        h, finfo = fixtures.sha256_chain_into_new_handle(field, device, prm["blocks"], rank, world)
+        h, finfo = fixtures.sha256_chain_into_new_handle(field, device, prm["blocks"], rank, world, record_witness_program=True)
         info.update(finfo)
     elif kind == "blake2s":
         from bellpepper_b200 import fixtures
@@ -394,7 +394,7 @@ def measure(ctx, name, a, headline):
                    "what": ("32-byte canonical scalars, bp_cs_set_range -> check -> result" if world == 1 else
                             "32-byte canonical scalars: every rank uploads 1/N of the aux witness over its own PCIe link, NVLink "
                             "all-gather (bp_group_set_witness_sharded), validation, check + exchange; bytes are one rank's")}
-        e2e_main, e2e_bits = e2e_raw, None
+        e2e_main, e2e_bits, e2e_generated = e2e_raw, None, None
         if kind != "synthetic":
             # (2) same scalars through the library's host-side packer (bits + exception list); row shards pack only what they read
             if world > 1:
@@ -439,6 +439,33 @@ def measure(ctx, name, a, headline):
                                     "bp_cs_recheck_bits: H2D, widened into the shadows, check"}
             if world > 1:
                 assert L.bp_cs_set_option(h, b"sparse_upload", 0) == 0
+            # (4) no witness upload at all: the device generates it from the MESSAGE (64 bytes per block) with the program the
+            # front-end recorded at synthesis; the host computes the 8-word chaining state per block (plain SHA-256)
+            if info.get("witness_program") is not None:
+                from bellpepper_b200 import fixtures
+
+                prog = info["witness_program"]
+                assert L.bp_cs_set_witness_program(h, ctypes.c_void_p(prog.ctypes.data), prog.size) == 0, L.bp_cs_last_error(h)
+                msg = fixtures.chain_message(prm["blocks"])
+
+                def step_generated():
+                    st = fixtures.sha256_chain_states(msg)
+                    assert L.bp_cs_generate_witness_async(h, msg, len(msg), ctypes.c_void_p(st.ctypes.data), st.size) == 0, L.bp_cs_last_error(h)
+                    if world == 1:
+                        assert L.bp_cs_first_unsatisfied(h, ctypes.byref(row)) == 0, L.bp_cs_last_error(h)
+                        return row.value
+                    return group_row()
+
+                gen_s = time_e2e(step_generated)
+                assert step_generated() == -1, "the device-generated witness does not satisfy the circuit"
+                gen = torch.empty((n_aux, 4), dtype=torch.int64)
+                assert L.bp_cs_witness(h, 1, 0, n_aux, ctypes.c_void_p(gen.data_ptr())) == 0
+                e2e_generated = {"value": n_rows_total / gen_s, "ms_per_step": gen_s * 1e3, "h2d_bytes_per_step": len(msg) + 32 * prm["blocks"],
+                                 "equals_front_end_witness": bool((gen == w_aux).all()), "program_bytes": int(prog.size) * 4,
+                                 "what": "witness GENERATED ON THE DEVICE from the message bytes (bp_cs_generate_witness_async: the program "
+                                         "the front-end recorded at synthesis, one warp per compression block), chaining states by plain "
+                                         "SHA-256 on the host, then the check; no witness crosses PCIe"}
+                del gen
             # leave the device witness in its full form again for what follows
             assert L.bp_cs_set_range(h, 0, 0, info["n_inputs"], p_in) == 0
             assert L.bp_cs_set_range(h, 1, 0, n_aux, p_aux) == 0
@@ -525,7 +552,8 @@ def measure(ctx, name, a, headline):
                               "inside the timed region",
                     "what": e2e_main["what"],
                     **({"other_reference_format_path": e2e_main["other_reference_format_path"]} if "other_reference_format_path" in e2e_main else {}),
-                    **({"prepacked_bits": e2e_bits} if e2e_bits else {})},
+                    **({"prepacked_bits": e2e_bits} if e2e_bits else {}),
+                    **({"generated_on_device": e2e_generated} if e2e_generated else {})},
             "gpu_launches": n_launch,
             "launch_mechanism": f"{plan['graph_replays']} graph replays / {plan['graph_captures']} captures so far; transport "
                                 + {0: "single rank", 1: "NCCL all-reduce", 2: "peer-memory mailboxes (no NCCL launch per step)"}[transport.value],

@@ -45,6 +45,15 @@ int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t block_be
 int bp_tcs_sha256_ranges(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint64_t* ranges, uint64_t n_ranges, uint8_t digest[32],
                          uint64_t* global_before, uint64_t* local_before);
 
+/* Witness program (include/bp_r1cs.h: bp_cs_set_witness_program).  With recording on, the next bp_tcs_sha256[_ranges] also
+ * records how every aux variable of the circuit follows from the message bits (csrc/host/wtape.hpp) and builds the device
+ * program, one unit per compression block; bp_tcs_witness_program lends it out (valid until the next synthesis on `t`).
+ * bp_sha256_chain_states: the 8-word hash state BEFORE each of the (len + 9 + 63) / 64 blocks, block 0 = the IV -- the
+ * per-unit chaining states bp_cs_generate_witness_async takes (states == NULL: just the block count). */
+int bp_tcs_record_witness_program(bp_tcs* t, int on);
+int bp_tcs_witness_program(bp_tcs* t, const uint32_t** words, uint64_t* n_words);
+int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, uint64_t max_blocks, uint64_t* n_blocks);
+
 /* blake2s() gadget over `len` message bytes, each bit allocated as "input bit <byte> <bit>" least significant first,
  * with an 8-byte personalization (crates/bellpepper/src/gadgets/blake2s.rs:344-406, tests :498-555).  digest = the 32
  * output bytes (the gadget's output bits are little-endian per byte). */

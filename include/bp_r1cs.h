@@ -140,6 +140,27 @@ int bp_cs_set_many(bp_cs* cs, int is_aux, uint64_t n, const uint64_t* idx, const
 int bp_cs_recheck_scalars(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row);
 int bp_cs_recheck_scalars_async(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result);
 
+/* ---- witness generation on the device (the "witness evaluation" half: SizedWitness::generate_witness_into, witness_cs.rs:7-41)
+ * For a bit-logic gadget circuit (boolean / uint32 / sha256: every aux value is a bit that follows from earlier bits) the NEXT
+ * witness of an already synthesized circuit need not be produced by re-running the gadgets' host closures
+ * (sha256.rs:83-272 through boolean.rs:68-272, 536-759 and uint32.rs:306-406) and uploading n_aux values: the front-end
+ * records, once, HOW each aux variable follows from earlier ones (csrc/host/wtape.hpp; bp_tcs_witness_program in
+ * bp_fixtures.h) and the device replays that program from the message bytes.
+ *
+ * Program = uint32 words: a 16-word header {magic "BPWP", version 1, n_units, n_tapes, aux index of message bit 0,
+ * n_msg_bits, bit order (1 = most significant bit of a byte first), n_aux, max variables / max sums of a tape, offsets},
+ * a unit table {tape, first aux index, first message bit, chaining-state index} -- a unit is e.g. one compression block --
+ * a tape table, and per tape its dependency levels, entries {result | op << 28, a, b, c} (XOR, AND, AND_NOT, NOR, CH, MAJ of
+ * operands that are constants, variables of the unit, message bits or chaining-state bits, possibly negated; or bit j of an
+ * integer sum of weighted bits, uint32.rs:306-406) and sums.  bp_cs_set_witness_program validates every index (BP_E_ARG).
+ *
+ * bp_cs_generate_witness_async: msg = the message bytes (msg_len * 8 must equal the program's n_msg_bits), states = 8 words of
+ * chaining state per unit (for a sha256 chain: the hash state BEFORE each block; bp_sha256_chain_states computes them on the
+ * host in microseconds).  Writes every aux value (inputs are untouched); follow with bp_cs_first_unsatisfied / check_async.
+ * 64 bytes of H2D per block instead of 26 000 witness values. */
+int bp_cs_set_witness_program(bp_cs* cs, const uint32_t* words, uint64_t n_words);
+int bp_cs_generate_witness_async(bp_cs* cs, const uint8_t* msg, uint64_t msg_len, const uint32_t* states, uint64_t n_state_words);
+
 /* Same check, asynchronous: enqueue on the handle's stream and leave the result in DEVICE memory as one
  * int64 (first failing GLOBAL row = row_base + local row; INT64_MAX when satisfied) so that a row-sharded
  * multi-GPU caller can min-all-reduce it without a host round trip.  No host synchronisation. */

@@ -60,6 +60,8 @@ extern "C" {
     pub fn bp_cs_sync(cs: *mut bp_cs) -> c_int;
     pub fn bp_cs_set_option(cs: *mut bp_cs, key: *const c_char, value: i64) -> c_int;
     pub fn bp_cs_get_option(cs: *mut bp_cs, key: *const c_char, value: *mut i64) -> c_int;
+    pub fn bp_cs_set_witness_program(cs: *mut bp_cs, words: *const u32, n_words: u64) -> c_int;
+    pub fn bp_cs_generate_witness_async(cs: *mut bp_cs, msg: *const u8, msg_len: u64, states: *const u32, n_state_words: u64) -> c_int;
     pub fn bp_group_unique_id(id: *mut u8) -> c_int;
     pub fn bp_group_init(cs: *mut bp_cs, id: *const u8, rank: c_int, world: c_int, out: *mut *mut bp_group) -> c_int;
     pub fn bp_group_free(g: *mut bp_group);

@@ -235,7 +235,7 @@ GROUP_WORKER = textwrap.dedent(
     b = np.zeros(world + 1, np.uint64)
     assert L.bp_split_rows_by_nnz(lens.ctypes.data, n_rows, world, b.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) == 0
     r0, r1 = int(b[rank]), int(b[rank + 1])
-    ptr = np.concatenate([[0], np.cumsum(lens.reshape(-1, 3).sum(1))])
+    ptr = np.concatenate([[0], np.cumsum(lens.reshape(-1, 3).sum(1).astype(np.int64))])
     h = Handle(fid, device=rank)
     first = ctypes.c_uint64()
     h.ok(L.bp_cs_alloc(h.h, 0, inputs[1:].ctypes.data, inputs.shape[0] - 1, ctypes.byref(first)))
@@ -311,7 +311,9 @@ def test_group_of_two_ranks_matches_oracle(tmp_path, mailbox):
         env["BP_GROUP_NO_MAILBOX"] = "1"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611" if mailbox else "29612", str(script)], capture_output=True, text=True, timeout=600, env=env)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    if r.returncode != 0:
+        tb = [ln for ln in r.stderr.splitlines() if "Error" in ln or "error" in ln or "File" in ln][-12:]
+        raise AssertionError("worker failed:\n" + "\n".join(tb) + "\n" + r.stdout[-1500:])
     res = {}
     for ln in r.stdout.splitlines():
         if ln.startswith("RESULT "):
@@ -358,3 +360,53 @@ def test_full_width_kernels_at_size_match_oracle(fid, log_rows, t):
             for dev_t, ref in zip(outs[1], (az, bz, cz)):
                 assert (dev_t[r0:r0 + blk].cpu().numpy().view(np.uint64) == ref).all()
             inst.close()
+
+
+@pytest.mark.parametrize("fid,blocks", [(1, 3), (0, 7)])
+def test_witness_generated_on_device_equals_the_front_end(fid, blocks):
+    """the sha256-chain witness generated on the device from the message bytes (the program the front-end
+    recorded while it synthesized the circuit) equals, bit for bit, what the gadgets' host closures produce -- for the recorded
+    message and for another one -- and the circuit holds with it."""
+    from bellpepper_b200 import ffi, fixtures
+
+    L = ffi.load()
+    msg = fixtures.chain_message(blocks)
+    with fixtures.Tcs(fid, device=0, named=False) as t:
+        t.record_witness_program()
+        t.sha256(msg)
+        prog = t.witness_program()
+        h = ffi.vp(t.handle)
+        n_aux = t.num_aux()
+        want = np.zeros((n_aux, 4), np.uint64)
+        assert L.bp_cs_witness(h, 1, 0, n_aux, want.ctypes.data) == 0
+        assert t.first_unsatisfied_row() == -1
+        assert L.bp_cs_set_witness_program(h, prog.ctypes.data, prog.size) == 0, L.bp_cs_last_error(h)
+        for m in (msg, bytes((b * 5 + 3) & 0xFF for b in msg)):
+            # wreck the witness first: the generator must rewrite every aux value
+            junk = np.ones(n_aux, np.uint8)
+            assert L.bp_cs_set_range_u8(h, 1, 0, n_aux, junk.ctypes.data) == 0
+            assert t.first_unsatisfied_row() >= 0
+            st = fixtures.sha256_chain_states(m)
+            assert L.bp_cs_generate_witness_async(h, m, len(m), st.ctypes.data, st.size) == 0, L.bp_cs_last_error(h)
+            assert t.first_unsatisfied_row() == -1
+            got = np.zeros((n_aux, 4), np.uint64)
+            assert L.bp_cs_witness(h, 1, 0, n_aux, got.ctypes.data) == 0
+            if m is msg:
+                assert (got == want).all()
+            else:
+                with fixtures.Tcs(fid, device=-1, named=False) as rec:
+                    rec.sha256(m)
+                    assert (got == rec.host_csr()[4]).all()
+        # a wrong chaining state is caught by the circuit itself
+        st = fixtures.sha256_chain_states(msg).copy()
+        st[1][3] ^= 4
+        assert L.bp_cs_generate_witness_async(h, msg, len(msg), st.ctypes.data, st.size) == 0
+        assert t.first_unsatisfied_row() >= 0
+        # malformed programs and mismatched inputs are refused
+        bad = prog.copy()
+        bad[int(prog[10]) + 1] = n_aux  # unit 0's variables past the end of the aux space
+        assert L.bp_cs_set_witness_program(h, bad.ctypes.data, bad.size) == -5
+        bad = prog.copy()
+        bad[0] ^= 1
+        assert L.bp_cs_set_witness_program(h, bad.ctypes.data, bad.size) == -5
+        assert L.bp_cs_generate_witness_async(h, msg[:-1], len(msg) - 1, st.ctypes.data, st.size) == -5
