@@ -635,6 +635,47 @@ class TestConstraintSystem(_ConstraintSystemBase):
     def pretty_print(self) -> str:
         return "\n".join(self.pretty_print_list())
 
+    def pretty_print_equations(self) -> str:
+        """`MetricCS::pretty_print` (crates/bellpepper/src/util_cs/metric_cs.rs:130-195): the inputs, then one line per constraint
+        `path: (A) * (B) = (C)` with every LC normalised by `proc_lc` (merged, zero coefficients dropped, inputs before aux).
+        Coefficients: -1 prints as " - ", 1 as nothing, a power of two as "2^i . " FOLLOWED by the scalar's Debug form (the
+        reference breaks out of its search loop and then prints the scalar as well), anything else as the Debug form alone:
+        `Scalar(0x...)` for BLS12-381 (blstrs), `0x...` for the pasta fields, 64 hex digits big-endian."""
+        p = self.p
+        pow2 = {pow(2, i, p): i for i in range(255)}
+        dbg = (lambda c: f"Scalar(0x{c:064x})") if self.dev.field == 0 else (lambda c: f"0x{c:064x}")
+        out = [f"INPUT {n}\n" for n in self.input_names]
+        buf, pos = bytes(self.dev._structure), 0
+
+        def pp() -> str:
+            nonlocal pos
+            n = int.from_bytes(buf[pos:pos + 8], "big")
+            pos += 8
+            parts, first = ["("], True
+            for _ in range(n):
+                kind, idx, co = buf[pos:pos + 1], int.from_bytes(buf[pos + 1:pos + 9], "big"), int.from_bytes(buf[pos + 9:pos + 41], "big")
+                pos += 41
+                if co == p - 1:
+                    parts.append(" - ")
+                elif not first:
+                    parts.append(" + ")
+                first = False
+                if co != 1 and co != p - 1:
+                    if co in pow2:
+                        parts.append(f"2^{pow2[co]} . ")
+                    parts.append(f"{dbg(co)} . ")
+                parts.append(f"`I{self.input_names[idx]}`" if kind == b"I" else f"`A{self.aux_names[idx]}`")
+            if first:
+                parts.append("0")
+            parts.append(")")
+            return "".join(parts)
+
+        for path in self.constraint_paths:
+            a, b, c = pp(), pp(), pp()
+            out.append(f"\n{path}: {a} * {b} = {c}")
+        out.append("\n")
+        return "".join(out)
+
 
 class SizedWitness:
     """`SizedWitness` (witness_cs.rs:7-41): a bulk witness producer of known size.  Subclasses give the three counts and

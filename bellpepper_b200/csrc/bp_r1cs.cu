@@ -1835,6 +1835,121 @@ int bp_cs_synth_witness(bp_cs* h, uint64_t seed, uint64_t n_vars, uint64_t n_inp
 
 }  // extern "C"
 
+// ---- prover hand-off: the system in a documented, implementation-independent layout ----------------------------------------
+// Not a reference interface (LinearCombination is not serialisable there, lc.rs:34; the reference has no on-disk R1CS).  What
+// a downstream prover (a Nova / Spartan style R1CSShape + witness) needs after the check: A, B, C with CANONICAL coefficients
+// (no class bits, no internal scaling), the witness, and optionally A.w, B.w, C.w -- exactly the arrays bp_cs_enforce /
+// bp_cs_alloc take, so another handle (or the oracle) can ingest the file as it is.  Little-endian:
+//   char magic[8] = "BPR1CSX\1"; u32 version = 1; u32 field; u64 n_rows, n_inputs, n_aux, nnz, row_base; u32 flags (bit 0: A.w,
+//   B.w, C.w follow the witness); u32 reserved;
+//   u32 lens[3 n_rows] (|A_i|, |B_i|, |C_i|); u32 cols[nnz] (bit 31 = aux); u64 coeffs[nnz][4]; u64 inputs[n_inputs][4];
+//   u64 aux[n_aux][4]; (flags & 1) u64 az[n_rows][4], bz[n_rows][4], cz[n_rows][4]; u64 checksum (as in bp_cs_save).
+extern "C" int bp_cs_export(bp_cs* h, const char* path, int with_products) {
+    if (!h || !path) return BP_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (!h->wide_valid) {
+        for (int k = 0; k < 2; ++k) {
+            const uint64_t n = k ? h->n_aux : h->n_inputs;
+            if (!n) continue;
+            materialize_wide<<<grid_for(h, 2 * n, 256, 8), 256, 0, h->stream>>>(shadow_ptr(h, k), n, (uint4*)(k ? h->aux.p : h->inputs.p));
+            h->launches++;
+        }
+        CU(h, cudaGetLastError());
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(h, BP_E_STATE, "cannot open %s for writing", path);
+    struct {
+        char magic[8];
+        uint32_t version, field;
+        uint64_t n_rows, n_inputs, n_aux, nnz, row_base;
+        uint32_t flags, reserved;
+    } hd;
+    std::memset(&hd, 0, sizeof hd);
+    std::memcpy(hd.magic, "BPR1CSX\1", 8);
+    hd.version = 1;
+    hd.field = (uint32_t)h->field;
+    hd.n_rows = h->n_rows; hd.n_inputs = h->n_inputs; hd.n_aux = h->n_aux; hd.nnz = h->nnz; hd.row_base = h->row_base;
+    hd.flags = with_products ? 1u : 0u;
+    Checksum ck;
+    auto put = [&](const void* p, size_t n) {
+        ck.add(p, n);
+        return fwrite(p, 1, n, f) == n;
+    };
+    int rc = fwrite(&hd, sizeof hd, 1, f) == 1 ? BP_OK : fail(h, BP_E_STATE, "short write");
+    const size_t n_lc = 3 * (size_t)h->n_rows;
+    // lens: differences of the row offsets, chunk by chunk through the pinned staging buffer
+    {
+        uint32_t* st = (uint32_t*)h->h_stage[0];
+        const size_t per = kStageBytes / 4 - 1;
+        for (size_t i = 0; i < n_lc && rc == BP_OK; i += per) {
+            const size_t n = std::min(per, n_lc - i);
+            cudaError_t e = cudaMemcpyAsync(st, (const uint32_t*)h->row_ptr.p + i, (n + 1) * 4, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { rc = fail(h, BP_E_CUDA, "export: %s", cudaGetErrorString(e)); break; }
+            for (size_t j = 0; j < n; ++j) st[j] = st[j + 1] - st[j];
+            if (!put(st, n * 4)) rc = fail(h, BP_E_STATE, "short write");
+        }
+    }
+    // columns without the class bits
+    {
+        uint32_t* st = (uint32_t*)h->h_stage[0];
+        const size_t per = kStageBytes / 4;
+        for (size_t i = 0; i < h->nnz && rc == BP_OK; i += per) {
+            const size_t n = std::min(per, (size_t)h->nnz - i);
+            cudaError_t e = cudaMemcpyAsync(st, (const uint32_t*)h->cols.p + i, n * 4, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { rc = fail(h, BP_E_CUDA, "export: %s", cudaGetErrorString(e)); break; }
+            for (size_t j = 0; j < n; ++j) st[j] &= (kColAux | kColIdxMask);
+            if (!put(st, n * 4)) rc = fail(h, BP_E_STATE, "short write");
+        }
+    }
+    // canonical coefficients
+    if (rc == BP_OK && h->nnz) {
+        const size_t per = kStageBytes / 32;
+        rc = ensure(h, h->scratch, per * 32, 0);
+        for (size_t i = 0; i < h->nnz && rc == BP_OK; i += per) {
+            const size_t n = std::min(per, (size_t)h->nnz - i);
+            DISPATCH_FIELD(h, (export_terms<F><<<grid_for(h, n, 128, 16), 128, 0, h->stream>>>((const uint4*)h->vals.p, (const uint32_t*)h->cols.p,
+                                                                                              (const uint32_t*)h->row_ptr.p, (uint32_t)n_lc + 1u,
+                                                                                              (uint32_t)i, (uint32_t)n, (uint4*)h->scratch.p)));
+            h->launches++;
+            cudaError_t e = cudaMemcpyAsync(h->h_stage[0], h->scratch.p, n * 32, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { rc = fail(h, BP_E_CUDA, "export: %s", cudaGetErrorString(e)); break; }
+            if (!put(h->h_stage[0], n * 32)) rc = fail(h, BP_E_STATE, "short write");
+        }
+    }
+    auto put_dev = [&](const void* dev, size_t bytes) {
+        for (size_t off = 0; off < bytes && rc == BP_OK; off += kStageBytes) {
+            const size_t n = std::min(kStageBytes, bytes - off);
+            cudaError_t e = cudaMemcpyAsync(h->h_stage[0], (const char*)dev + off, n, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { rc = fail(h, BP_E_CUDA, "export: %s", cudaGetErrorString(e)); break; }
+            if (!put(h->h_stage[0], n)) rc = fail(h, BP_E_STATE, "short write");
+        }
+    };
+    put_dev(h->inputs.p, (size_t)h->n_inputs * 32);
+    put_dev(h->aux.p, (size_t)h->n_aux * 32);
+    if (rc == BP_OK && with_products && h->n_rows) {
+        const size_t bytes = (size_t)h->n_rows * 32;
+        DevBuf out;  // (not h->scratch: launch_check's kernels use it through the plan)
+        rc = ensure(h, out, 3 * bytes, 0);
+        if (rc == BP_OK) {
+            uint4* d = (uint4*)out.p;
+            rc = launch_check(h, h->d_result, d, (uint4*)((char*)out.p + bytes), (uint4*)((char*)out.p + 2 * bytes));
+            if (rc == BP_OK) put_dev(out.p, 3 * bytes);
+        }
+        if (out.p) {
+            cudaStreamSynchronize(h->stream);
+            cudaFree(out.p);
+        }
+    }
+    const uint64_t sum = ck.value();
+    if (rc == BP_OK && fwrite(&sum, 8, 1, f) != 1) rc = fail(h, BP_E_STATE, "short write");
+    if (fclose(f) != 0 && rc == BP_OK) rc = fail(h, BP_E_STATE, "close failed");
+    return rc;
+}
+
 // ---- witness program: generate the next witness on the device ---------------------------------------------------
 namespace {
 // Everything the kernel indexes with is checked here, once: a malformed program is refused, never run.

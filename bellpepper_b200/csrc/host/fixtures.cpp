@@ -310,6 +310,100 @@ int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, u
     return BP_OK;
 }
 
+// ---- num gadgets (crates/bellpepper-core/src/gadgets/num.rs) -----------------------------------------------------------------
+int bp_tcs_num_unpack(bp_tcs* t, const uint64_t value[4], int strict, uint8_t* bits_out) {
+    if (!t || !value) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            Fr v;
+            std::memcpy(v.l, value, 32);
+            if (!cs.field()->is_canonical(v)) throw std::out_of_range("value >= p");
+            const AllocatedNum n = AllocatedNum::alloc(cs, [&] { return v; });
+            const std::vector<Boolean> bits = strict ? n.to_bits_le_strict(cs) : n.to_bits_le(cs);
+            if (bits_out)
+                for (size_t i = 0; i < bits.size(); ++i) bits_out[i] = (uint8_t)bits[i].get_value();
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
+int bp_tcs_num_arith(bp_tcs* t, const uint64_t a4[4], const uint64_t b4[4]) {
+    if (!t || !a4 || !b4) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            Fr av, bv;
+            std::memcpy(av.l, a4, 32);
+            std::memcpy(bv.l, b4, 32);
+            AllocatedNum a{std::nullopt, Variable{0}}, b{std::nullopt, Variable{0}};
+            {
+                auto ns = cs.ns([] { return std::string("a"); });
+                a = AllocatedNum::alloc(ns, [&] { return av; });
+            }
+            {
+                auto ns = cs.ns([] { return std::string("b"); });
+                b = AllocatedNum::alloc(ns, [&] { return bv; });
+            }
+            const AllocatedNum prod = a.mul(cs, b);     // "product num", "multiplication constraint"
+            const AllocatedNum sq = a.square(cs);       // "squared num", "squaring constraint"
+            const AllocatedNum sum = prod.add(cs, sq);  // "sum num", "addition constraint"
+            (void)sum;
+            {
+                auto ns = cs.ns([] { return std::string("nonzero"); });
+                b.assert_nonzero(ns);                   // "nonzero/ephemeral inverse", "nonzero/nonzero assertion constraint"
+            }
+            {
+                auto ns = cs.ns([] { return std::string("swap"); });
+                const AllocatedBit c = AllocatedBit::alloc(ns.ns([] { return std::string("condition"); }), (OptBool)1);
+                AllocatedNum::conditionally_reverse(ns, a, b, Boolean::from(c));
+            }
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
+// A product-heavy GADGET circuit for the full-width kernels: x <- x^2 * y + x, n times, x unpacked into bits every
+// `unpack_every` steps (0 = never): multiplication / squaring / addition rows over full-width values and 256-term rows.
+int bp_tcs_num_chain(bp_tcs* t, uint64_t n_steps, uint64_t unpack_every, const uint64_t x0[4], const uint64_t y0[4]) {
+    if (!t || !x0 || !y0) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            Fr xv, yv;
+            std::memcpy(xv.l, x0, 32);
+            std::memcpy(yv.l, y0, 32);
+            AllocatedNum x{std::nullopt, Variable{0}}, y{std::nullopt, Variable{0}};
+            {
+                auto ns = cs.ns([] { return std::string("x0"); });
+                x = AllocatedNum::alloc(ns, [&] { return xv; });
+            }
+            {
+                auto ns = cs.ns([] { return std::string("y"); });
+                y = AllocatedNum::alloc(ns, [&] { return yv; });
+            }
+            for (uint64_t i = 0; i < n_steps; ++i) {
+                auto ns = cs.ns([&] { return "step " + std::to_string(i); });
+                const AllocatedNum s = x.square(ns);
+                AllocatedNum m{std::nullopt, Variable{0}};
+                {
+                    auto n2 = ns.ns([] { return std::string("times y"); });
+                    m = s.mul(n2, y);
+                }
+                {
+                    auto n2 = ns.ns([] { return std::string("plus x"); });
+                    x = m.add(n2, x);
+                }
+                if (unpack_every && (i + 1) % unpack_every == 0) {
+                    auto n2 = ns.ns([] { return std::string("unpack"); });
+                    x.to_bits_le(n2);
+                }
+            }
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
 int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint8_t digest[32]) {
     if (!t || (!msg && len) || !personalization || !digest) return BP_E_ARG;
     return guarded(t, [&] {

@@ -149,6 +149,21 @@ struct Field {
         return mul(a, pow2(k));
     }
     bool is_canonical(const Fr& a) const { return !geq(a.l, fp->p); }
+    Fr square(const Fr& a) const { return mul(a, a); }
+    // a^(p-2): the inverse of a non-zero element (`invert()` in num.rs:378-389; witness values of the num gadgets only)
+    Fr invert(const Fr& a) const {
+        uint64_t e[4];
+        const uint64_t two[4] = {2, 0, 0, 0};
+        sub_raw(e, fp->p, two);
+        Fr r = Fr::one(), b = a;
+        for (int i = 0; i < 256; ++i) {
+            if ((e[i / 64] >> (i % 64)) & 1) r = mul(r, b);
+            b = mul(b, b);
+        }
+        return r;
+    }
+    // bit i of the canonical representation (to_le_bits)
+    static bool bit(const Fr& a, unsigned i) { return (a.l[i / 64] >> (i % 64)) & 1; }
 };
 
 }  // namespace bph

@@ -42,6 +42,17 @@ struct AllocatedBit {
         return AllocatedBit{var, value};
     }
 
+    // boolean.rs:27-64: a bit that must be false whenever `must_be_false` is true:  (1 - must_be_false - a) * a = 0
+    template <class CS> static AllocatedBit alloc_conditionally(CS&& cs, OptBool value, const AllocatedBit& must_be_false) {
+        const Variable var = cs.alloc([] { return std::string("boolean"); }, [&] { return bit_value(value); });
+        if (g_tape) g_tape->fail("alloc_conditionally is not a recorded gadget");
+        cs.enforce([] { return std::string("boolean constraint"); },
+                   [&](LinearCombination lc) { return std::move(lc) + one_var() - must_be_false.variable - var; },
+                   [&](LinearCombination lc) { return std::move(lc) + var; },
+                   [&](LinearCombination lc) { return lc; });
+        return AllocatedBit{var, value};
+    }
+
     template <class CS> static AllocatedBit xor_(CS&& cs, const AllocatedBit& a, const AllocatedBit& b) {  // boolean.rs:101-151
         OptBool rv = kNone;
         const Variable r = cs.alloc([] { return std::string("xor result"); }, [&] {
@@ -218,6 +229,212 @@ struct Boolean {  // boolean.rs:368-376
                    [&](LinearCombination) { return a.lc(f, one_var(), Fr::one()); },
                    [&](LinearCombination) { return bc.lc(f, one_var(), Fr::one()) - maj; });
         return from(AllocatedBit{maj, mv});
+    }
+};
+
+// ---- field element -> bits (boolean.rs:320-366) and AllocatedNum (gadgets/num.rs:10-460) ---------------------------------
+constexpr unsigned kNumBits = 255;  // ff::PrimeField::NUM_BITS (all three fields)
+
+// boolean.rs:320-366: NUM_BITS freshly allocated bits "bit i", little-endian, of `value` (nullptr = no assignment).
+template <class CS> std::vector<AllocatedBit> field_into_allocated_bits_le(CS&& cs, const Fr* value) {
+    std::vector<AllocatedBit> bits;
+    bits.reserve(kNumBits);
+    for (unsigned i = 0; i < kNumBits; ++i) {
+        auto ns = cs.ns([&] { return "bit " + std::to_string(i); });
+        bits.push_back(AllocatedBit::alloc(ns, value ? (OptBool)Field::bit(*value, i) : kNone));
+    }
+    return bits;
+}
+
+struct AllocatedNum {
+    std::optional<Fr> value;
+    Variable variable;
+
+    template <class CS, class V> static AllocatedNum alloc(CS&& cs, V&& value_fn) {  // num.rs:27-47
+        std::optional<Fr> nv;
+        const Variable var = cs.alloc([] { return std::string("num"); }, [&] {
+            const Fr t = value_fn();
+            nv = t;
+            return t;
+        });
+        if (g_tape) g_tape->fail("AllocatedNum is not a recorded gadget");
+        return AllocatedNum{nv, var};
+    }
+    template <class CS, class V> static AllocatedNum alloc_input(CS&& cs, V&& value_fn) {  // num.rs:61-81
+        std::optional<Fr> nv;
+        const Variable var = cs.alloc_input([] { return std::string("input num"); }, [&] {
+            const Fr t = value_fn();
+            nv = t;
+            return t;
+        });
+        return AllocatedNum{nv, var};
+    }
+    const Fr& need() const {
+        if (!value) throw SynthesisError::assignment_missing();
+        return *value;
+    }
+    template <class CS> void inputize(CS&& cs) const {  // num.rs:104-121
+        const Variable input = cs.alloc_input([] { return std::string("input variable"); }, [&] { return need(); });
+        cs.enforce([] { return std::string("enforce input is correct"); },
+                   [&](LinearCombination lc) { return std::move(lc) + input; },
+                   [&](LinearCombination lc) { return std::move(lc) + one_var(); },
+                   [&](LinearCombination lc) { return std::move(lc) + variable; });
+    }
+
+    // num.rs:263-274: NUM_BITS bits and ONE 256-term row  0 * 0 = sum 2^i bit_i - self  (the repo's fattest LCs)
+    template <class CS> std::vector<Boolean> to_bits_le(CS&& cs) const {
+        const std::vector<AllocatedBit> bits = field_into_allocated_bits_le(cs, value ? &*value : nullptr);
+        unpacking_constraint(cs, bits, /*reversed=*/false);
+        std::vector<Boolean> out;
+        for (auto& b : bits) out.push_back(Boolean::from(b));
+        return out;
+    }
+
+    // num.rs:128-247: the same with the representation forced below the modulus.  Walks the bits of p - 1 from the top: a bit
+    // in a run of ones is a plain allocated bit; at a zero bit of p - 1 the bit must be false when every bit of all the runs
+    // of ones so far was set (k-ary AND chained through `last_run`).
+    template <class CS> std::vector<Boolean> to_bits_le_strict(CS&& cs) const {
+        const Field* f = cs.field();
+        const Fr b = f->neg(Fr::one());  // p - 1
+        std::vector<AllocatedBit> result;  // big-endian
+        std::optional<AllocatedBit> last_run;
+        std::vector<AllocatedBit> current_run;
+        bool found_one = false;
+        unsigned i = 0;
+        for (int pos = 255; pos >= 0; --pos) {
+            const bool bbit = Field::bit(b, (unsigned)pos);
+            const OptBool abit = value ? (OptBool)Field::bit(*value, (unsigned)pos) : kNone;
+            found_one |= bbit;
+            if (!found_one) {
+                if (abit > 0) throw std::logic_error("to_bits_le_strict: value has a bit above the modulus");
+                continue;
+            }
+            if (bbit) {
+                auto ns = cs.ns([&] { return "bit " + std::to_string(i); });
+                const AllocatedBit a = AllocatedBit::alloc(ns, abit);
+                current_run.push_back(a);
+                result.push_back(a);
+            } else {
+                if (!current_run.empty()) {
+                    if (last_run) current_run.push_back(*last_run);
+                    auto ns = cs.ns([&] { return "run ending at " + std::to_string(i); });
+                    AllocatedBit cur = current_run[0];  // kary_and (num.rs:133-160)
+                    for (size_t k = 1; k < current_run.size(); ++k) {
+                        auto n2 = ns.ns([&] { return "and " + std::to_string(k); });
+                        cur = AllocatedBit::and_(n2, cur, current_run[k]);
+                    }
+                    last_run = cur;
+                    current_run.clear();
+                }
+                auto ns = cs.ns([&] { return "bit " + std::to_string(i); });
+                result.push_back(AllocatedBit::alloc_conditionally(ns, abit, *last_run));
+            }
+            ++i;
+        }
+        if (!current_run.empty()) throw std::logic_error("to_bits_le_strict: the modulus is odd, so p - 1 ends in a zero bit");
+        unpacking_constraint(cs, result, /*reversed=*/true);
+        std::vector<Boolean> out;
+        for (auto it = result.rbegin(); it != result.rend(); ++it) out.push_back(Boolean::from(*it));
+        return out;
+    }
+
+    template <class CS> AllocatedNum add(CS&& cs, const AllocatedNum& o) const {  // num.rs:276-306
+        const Field* f = cs.field();
+        std::optional<Fr> v;
+        const Variable var = cs.alloc([] { return std::string("sum num"); }, [&] {
+            v = f->add(need(), o.need());
+            return *v;
+        });
+        cs.enforce([] { return std::string("addition constraint"); },
+                   [&](LinearCombination lc) { return std::move(lc) + variable + o.variable; },
+                   [&](LinearCombination lc) { return std::move(lc) + one_var(); },
+                   [&](LinearCombination lc) { return std::move(lc) + var; });
+        return AllocatedNum{v, var};
+    }
+    template <class CS> AllocatedNum mul(CS&& cs, const AllocatedNum& o) const {  // num.rs:308-338
+        const Field* f = cs.field();
+        std::optional<Fr> v;
+        const Variable var = cs.alloc([] { return std::string("product num"); }, [&] {
+            v = f->mul(need(), o.need());
+            return *v;
+        });
+        cs.enforce([] { return std::string("multiplication constraint"); },
+                   [&](LinearCombination lc) { return std::move(lc) + variable; },
+                   [&](LinearCombination lc) { return std::move(lc) + o.variable; },
+                   [&](LinearCombination lc) { return std::move(lc) + var; });
+        return AllocatedNum{v, var};
+    }
+    template <class CS> AllocatedNum square(CS&& cs) const {  // num.rs:340-370
+        const Field* f = cs.field();
+        std::optional<Fr> v;
+        const Variable var = cs.alloc([] { return std::string("squared num"); }, [&] {
+            v = f->square(need());
+            return *v;
+        });
+        cs.enforce([] { return std::string("squaring constraint"); },
+                   [&](LinearCombination lc) { return std::move(lc) + variable; },
+                   [&](LinearCombination lc) { return std::move(lc) + variable; },
+                   [&](LinearCombination lc) { return std::move(lc) + var; });
+        return AllocatedNum{v, var};
+    }
+    template <class CS> void assert_nonzero(CS&& cs) const {  // num.rs:372-401
+        const Field* f = cs.field();
+        const Variable inv = cs.alloc([] { return std::string("ephemeral inverse"); }, [&] {
+            const Fr& t = need();
+            if (t.is_zero()) throw SynthesisError::division_by_zero();
+            return f->invert(t);
+        });
+        cs.enforce([] { return std::string("nonzero assertion constraint"); },
+                   [&](LinearCombination lc) { return std::move(lc) + variable; },
+                   [&](LinearCombination lc) { return std::move(lc) + inv; },
+                   [&](LinearCombination lc) { return std::move(lc) + one_var(); });
+    }
+    // num.rs:403-455: (b, a) when the condition holds, else (a, b)
+    template <class CS> static std::pair<AllocatedNum, AllocatedNum> conditionally_reverse(CS&& cs, const AllocatedNum& a, const AllocatedNum& b,
+                                                                                         const Boolean& condition) {
+        const Field* f = cs.field();
+        auto pick = [&](bool swap_first) {
+            const OptBool cv = condition.get_value();
+            if (cv < 0) throw SynthesisError::assignment_missing();
+            return (cv != 0) == swap_first ? b.need() : a.need();
+        };
+        AllocatedNum c{std::nullopt, Variable{0}}, d{std::nullopt, Variable{0}};
+        {
+            auto ns = cs.ns([] { return std::string("conditional reversal result 1"); });
+            c = alloc(ns, [&] { return pick(true); });
+        }
+        cs.enforce([] { return std::string("first conditional reversal"); },
+                   [&](LinearCombination lc) { return std::move(lc) + a.variable - b.variable; },
+                   [&](LinearCombination) { return condition.lc(f, one_var(), Fr::one()); },
+                   [&](LinearCombination lc) { return std::move(lc) + a.variable - c.variable; });
+        {
+            auto ns = cs.ns([] { return std::string("conditional reversal result 2"); });
+            d = alloc(ns, [&] { return pick(false); });
+        }
+        cs.enforce([] { return std::string("second conditional reversal"); },
+                   [&](LinearCombination lc) { return std::move(lc) + b.variable - a.variable; },
+                   [&](LinearCombination) { return condition.lc(f, one_var(), Fr::one()); },
+                   [&](LinearCombination lc) { return std::move(lc) + b.variable - d.variable; });
+        return {c, d};
+    }
+
+  private:
+    // 0 * 0 = sum_i 2^i bit_i - self   (num.rs:236-247, 263-274); `bits` little-endian, or big-endian when reversed
+    template <class CS> void unpacking_constraint(CS&& cs, const std::vector<AllocatedBit>& bits, bool reversed) const {
+        const Field* f = cs.field();
+        cs.enforce([] { return std::string("unpacking constraint"); },
+                   [&](LinearCombination lc) { return lc; },
+                   [&](LinearCombination lc) { return lc; },
+                   [&](LinearCombination) {
+                       LinearCombination lc(f);
+                       Fr coeff = Fr::one();
+                       for (size_t k = 0; k < bits.size(); ++k) {
+                           const AllocatedBit& bt = reversed ? bits[bits.size() - 1 - k] : bits[k];
+                           lc.add_term(bt.variable, coeff);
+                           coeff = f->dbl(coeff);
+                       }
+                       return std::move(lc) - variable;
+                   });
     }
 };
 

@@ -1786,6 +1786,49 @@ __global__ void convert_terms(uint4* vals, uint32_t* cols, uint16_t* __restrict_
     }
 }
 
+// bp_cs_export: terms [k0, k0+n) back from the internal form to CANONICAL coefficients (the inverse of convert_terms).
+//   A/B terms: classes P1/M1/P2/M2 are +-1, +-2 of a plain LC (nothing stored); GEN / POW2* are stored as c * 2^288: one lazy
+//   reduction undoes the scaling.   C terms: the class and the stored value describe the NEGATED coefficient.
+template <int F>
+__global__ void export_terms(const uint4* __restrict__ vals, const uint32_t* __restrict__ cols, const uint32_t* __restrict__ row_ptr, uint32_t n_lc,
+                             uint32_t k0, uint32_t n, uint4* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t k = k0 + i;
+        uint32_t lo = 0, hi = n_lc;  // largest lc with row_ptr[lc] <= k
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (__ldg(row_ptr + mid) <= k) lo = mid; else hi = mid;
+        }
+        const bool is_c = lo % 3u == 2u;
+        const uint32_t cls = (__ldg(cols + k) >> kColClsShift) & 7u;
+        uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cls == kClsP1 || cls == kClsM1) c[0] = 1u;
+        else if (cls == kClsP2 || cls == kClsM2) c[0] = 2u;
+        else if (cls != kClsZero) {
+            ld8(c, vals + 2 * (size_t)k);
+            if (!is_c) {
+                uint32_t t[17];
+#pragma unroll
+                for (int j = 0; j < 17; ++j) t[j] = j < 8 ? c[j] : 0u;
+                redc_acc<F>(c, t);  // stored * 2^-288, in [0, 2p)
+                reduce_once<F>(c);
+            }
+        }
+        // the sign: M classes are negative; for C everything describes -coefficient
+        const bool stored_negative = cls == kClsM1 || cls == kClsM2;
+        const bool flip = cls != kClsZero && (stored_negative != is_c);
+        uint32_t nz = 0, ng[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nz |= c[j];
+        neg_mod<F>(ng, c);
+        if (flip && nz) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = ng[j];
+        }
+        st8(out + 2 * (size_t)i, c);
+    }
+}
+
 // Witness upload: value < p check, and the 4-byte shadow of every element.
 template <int F> __global__ void validate_canonical(const uint4* __restrict__ v, uint64_t n, unsigned int* err, uint32_t* __restrict__ shadow) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {

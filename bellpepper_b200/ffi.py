@@ -45,6 +45,7 @@ SIGNATURES = {
     "bp_cs_eval_lc": (ctypes.c_int, [vp, vp, vp, ctypes.c_uint32, vp]),
     "bp_cs_save": (ctypes.c_int, [vp, ctypes.c_char_p]),
     "bp_cs_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]),
+    "bp_cs_export": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_int]),
     "bp_cs_set_stream": (ctypes.c_int, [vp, vp]),
     "bp_cs_set_row_base": (ctypes.c_int, [vp, ctypes.c_uint64]),
     "bp_cs_sync": (ctypes.c_int, [vp]),

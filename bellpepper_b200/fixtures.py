@@ -23,6 +23,9 @@ _SIGS = {
     "bp_tcs_sha256": (ctypes.c_int, [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, u64p]),
     "bp_tcs_sha256_ranges": (ctypes.c_int, [vp, vp, ctypes.c_uint64, u64p, ctypes.c_uint64, vp, u64p, u64p]),
     "bp_tcs_blake2s": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, vp]),
+    "bp_tcs_num_unpack": (ctypes.c_int, [vp, vp, ctypes.c_int, vp]),
+    "bp_tcs_num_arith": (ctypes.c_int, [vp, vp, vp]),
+    "bp_tcs_num_chain": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp]),
     "bp_tcs_record_witness_program": (ctypes.c_int, [vp, ctypes.c_int]),
     "bp_tcs_witness_program": (ctypes.c_int, [vp, ctypes.POINTER(vp), u64p]),
     "bp_sha256_chain_states": (ctypes.c_int, [vp, ctypes.c_uint64, vp, ctypes.c_uint64, u64p]),
@@ -140,6 +143,24 @@ class Tcs:
         out = ctypes.create_string_buffer(32)
         self._ck(self.L.bp_tcs_sha256_ranges(self.t, msg, len(msg), flat, len(ranges), out, gb, lb))
         return out.raw, [(int(g), int(l)) for g, l in zip(gb, lb)]
+
+    @staticmethod
+    def _limbs(value: int) -> np.ndarray:
+        return np.frombuffer(int(value).to_bytes(32, "little"), dtype="<u8").copy()
+
+    def num_unpack(self, value: int, strict: bool = False):
+        """AllocatedNum::alloc + to_bits_le[_strict] (num.rs:128-274); returns the 255 bits, little-endian."""
+        v, bits = self._limbs(value), np.zeros(255, np.uint8)
+        self._ck(self.L.bp_tcs_num_unpack(self.t, v.ctypes.data, int(strict), bits.ctypes.data))
+        return bits
+
+    def num_arith(self, a: int, b: int):
+        va, vb = self._limbs(a), self._limbs(b)
+        self._ck(self.L.bp_tcs_num_arith(self.t, va.ctypes.data, vb.ctypes.data))
+
+    def num_chain(self, n_steps: int, unpack_every: int, x0: int, y0: int):
+        vx, vy = self._limbs(x0), self._limbs(y0)
+        self._ck(self.L.bp_tcs_num_chain(self.t, n_steps, unpack_every, vx.ctypes.data, vy.ctypes.data))
 
     def record_witness_program(self, on: bool = True):
         self._ck(self.L.bp_tcs_record_witness_program(self.t, int(on)))

@@ -152,7 +152,7 @@ class CpuSample:
             self.n_vars = 1 << prm["log_rows"]
             n = min(1 << max_rows_log2, 1 << prm["log_rows"])
             if self.n_vars > (1 << 25):  # a witness of GiBs: keep only what the sampled rows read (same values, same sums)
-                n = min(n, 1 << 20)
+                n = min(n, 1 << 18)
                 self.inst = c_api.synth_sparse_instance(field, SEED, prm["t"], self.n_vars, N_INPUTS, 0, n)
                 self.what = f"first 2^{n.bit_length() - 1} rows of {name} (the witness elements they read)"
             else:

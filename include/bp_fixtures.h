@@ -54,6 +54,18 @@ int bp_tcs_record_witness_program(bp_tcs* t, int on);
 int bp_tcs_witness_program(bp_tcs* t, const uint32_t** words, uint64_t* n_words);
 int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, uint64_t max_blocks, uint64_t* n_blocks);
 
+/* num gadgets (crates/bellpepper-core/src/gadgets/num.rs), driven the way the reference's tests drive them:
+ *  bp_tcs_num_unpack: AllocatedNum::alloc ("num") then to_bits_le (num.rs:263-274) or to_bits_le_strict (:128-247) at the
+ *    root -- "bit i/boolean", "unpacking constraint" (one 256-term row over full-width values); bits_out (nullable)
+ *    receives the NUM_BITS = 255 bits, little-endian.  KATs: num.rs:696-764.
+ *  bp_tcs_num_arith: "a/num", "b/num", mul / square / add (num.rs:276-370: "product num", "squared num", "sum num"),
+ *    "nonzero/..." assert_nonzero (:372-401) and "swap/..." conditionally_reverse (:403-455).  KATs: num.rs:591-693.
+ *  bp_tcs_num_chain: a product-heavy gadget circuit, x <- x^2 * y + x n times with x unpacked every `unpack_every`
+ *    steps: rows whose witness values are full-width field elements (the full-width kernels' case). */
+int bp_tcs_num_unpack(bp_tcs* t, const uint64_t value[4], int strict, uint8_t* bits_out);
+int bp_tcs_num_arith(bp_tcs* t, const uint64_t a[4], const uint64_t b[4]);
+int bp_tcs_num_chain(bp_tcs* t, uint64_t n_steps, uint64_t unpack_every, const uint64_t x0[4], const uint64_t y0[4]);
+
 /* blake2s() gadget over `len` message bytes, each bit allocated as "input bit <byte> <bit>" least significant first,
  * with an 8-byte personalization (crates/bellpepper/src/gadgets/blake2s.rs:344-406, tests :498-555).  digest = the 32
  * output bytes (the gadget's output bits are little-endian per byte). */

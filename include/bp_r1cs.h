@@ -186,6 +186,17 @@ int bp_cs_eval_lc(bp_cs* cs, const uint32_t* cols, const uint64_t* coeffs_le, ui
 int bp_cs_save(bp_cs* cs, const char* path);
 int bp_cs_load(const char* path, int device, bp_cs** out);
 
+/* ---- prover hand-off ------------------------------------------------------------------------------------
+ * Not a reference interface either (the reference has no on-disk R1CS).  What the step AFTER the check needs -- a Nova /
+ * Spartan style shape (A, B, C) + witness, optionally with A.w, B.w, C.w -- in a documented, implementation-independent
+ * layout: canonical little-endian coefficients, no class bits, no internal scaling; exactly the arrays bp_cs_enforce /
+ * bp_cs_alloc take, so another handle (or the CPU oracle) ingests the file as it is.
+ *   char magic[8] = "BPR1CSX\1"; u32 version = 1; u32 field; u64 n_rows, n_inputs, n_aux, nnz, row_base;
+ *   u32 flags (bit 0: products follow); u32 reserved;
+ *   u32 lens[3 n_rows]  (|A_i|, |B_i|, |C_i|);  u32 cols[nnz]  (bit 31 = aux);  u64 coeffs[nnz][4];
+ *   u64 inputs[n_inputs][4];  u64 aux[n_aux][4];  [u64 az[n_rows][4], bz[..], cz[..]];  u64 checksum (as bp_cs_save). */
+int bp_cs_export(bp_cs* cs, const char* path, int with_products);
+
 /* ---- execution control -----------------------------------------------------------------------------*/
 /* Use an existing CUDA stream (cudaStream_t as void*) for all work.  NULL = the handle's own non-blocking
  * stream; the legacy default stream is cudaStreamLegacy, i.e. (void*)0x1. */

@@ -55,6 +55,7 @@ extern "C" {
     pub fn bp_cs_eval_lc(cs: *mut bp_cs, cols: *const u32, coeffs_le: *const u64, n_terms: u32, out: *mut u64) -> c_int;
     pub fn bp_cs_save(cs: *mut bp_cs, path: *const c_char) -> c_int;
     pub fn bp_cs_load(path: *const c_char, device: c_int, out: *mut *mut bp_cs) -> c_int;
+    pub fn bp_cs_export(cs: *mut bp_cs, path: *const c_char, with_products: c_int) -> c_int;
     pub fn bp_cs_set_stream(cs: *mut bp_cs, cuda_stream: *mut c_void) -> c_int;
     pub fn bp_cs_set_row_base(cs: *mut bp_cs, row_base: u64) -> c_int;
     pub fn bp_cs_sync(cs: *mut bp_cs) -> c_int;

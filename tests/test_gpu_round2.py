@@ -410,3 +410,82 @@ def test_witness_generated_on_device_equals_the_front_end(fid, blocks):
         bad[0] ^= 1
         assert L.bp_cs_set_witness_program(h, bad.ctypes.data, bad.size) == -5
         assert L.bp_cs_generate_witness_async(h, msg[:-1], len(msg) - 1, st.ctypes.data, st.size) == -5
+
+
+def _read_export(path):
+    import struct
+
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"BPR1CSX\x01"
+    version, field, n_rows, n_inputs, n_aux, nnz, row_base, flags, _ = struct.unpack_from("<IIQQQQQII", raw, 8)
+    assert version == 1
+    off = 8 + struct.calcsize("<IIQQQQQII")
+    out = {"field": field, "n_rows": n_rows, "row_base": row_base, "flags": flags}
+
+    def take(count, dtype, shape=None):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dtype, count=count, offset=off)
+        off += a.nbytes
+        return a.reshape(shape) if shape else a
+
+    out["lens"] = take(3 * n_rows, "<u4")
+    out["cols"] = take(nnz, "<u4")
+    out["coeffs"] = take(4 * nnz, "<u8", (-1, 4))
+    out["inputs"] = take(4 * n_inputs, "<u8", (-1, 4))
+    out["aux"] = take(4 * n_aux, "<u8", (-1, 4))
+    if flags & 1:
+        for k in ("az", "bz", "cz"):
+            out[k] = take(4 * n_rows, "<u8", (-1, 4))
+    assert off + 8 == len(raw)
+    return out
+
+
+@pytest.mark.parametrize("fid", sorted(FIELDS))
+def test_export_round_trips_to_the_oracle_csr(tmp_path, fid):
+    """Prover hand-off: bp_cs_export writes A, B, C with CANONICAL coefficients (internal scaling, negated C and
+    coefficient classes undone), the witness and A.w / B.w / C.w; the file equals the arrays that were ingested, bit for bit, on
+    a gadget-shaped instance (every coefficient class, plain and general LCs) and on a synthetic one; another handle fed with
+    the file's arrays gives the same verdict."""
+    for make in ("gadget", "synthetic"):
+        if make == "gadget":
+            lens, cols, coeffs, inputs, aux, _ = _gadget_like_instance(fid, 41, 1200, 2000, 7)
+        else:
+            lens, cols, coeffs, inputs, aux = c_api.synth_instance(fid, synth.SEED, 5, 3000, synth.N_INPUTS, 900)
+        inst = c_api.Instance(fid, lens, cols, coeffs, inputs, aux)
+        bad, az, bz, cz = inst.eval(2)
+        path = str(tmp_path / f"{make}.bpx").encode()
+        with Handle(fid) as h:
+            h.load_instance(lens, cols, coeffs, inputs, aux)
+            h.ok(h.L.bp_cs_set_row_base(h.h, 77))
+            h.ok(h.L.bp_cs_export(h.h, path, 1))
+            want_row = h.first_unsatisfied()
+        x = _read_export(path.decode())
+        assert x["field"] == fid and x["row_base"] == 77 and x["flags"] == 1
+        assert (x["lens"] == lens).all() and (x["cols"] == cols).all()
+        assert (x["coeffs"] == coeffs).all()
+        assert (x["inputs"] == inputs).all() and (x["aux"] == aux).all()
+        assert (x["az"] == az).all() and (x["bz"] == bz).all() and (x["cz"] == cz).all()
+        with Handle(fid) as h2:  # the file's arrays are exactly what bp_cs_alloc / bp_cs_enforce take
+            h2.load_instance(np.array(x["lens"]), np.array(x["cols"]), np.array(x["coeffs"]), np.array(x["inputs"]), np.array(x["aux"]))
+            assert h2.first_unsatisfied() == want_row == bad
+
+
+def test_metric_cs_pretty_print():
+    """MetricCS::pretty_print (crates/bellpepper/src/util_cs/metric_cs.rs:130-195) from the host mirror."""
+    from bellpepper_b200 import ONE, TestConstraintSystem
+
+    cs = TestConstraintSystem(0)
+    p = cs.p
+    a = cs.alloc("a", lambda: 3)
+    with cs.namespace("ns"):
+        b = cs.alloc("b", lambda: 5)
+    x = cs.alloc_input("x", lambda: 15)
+    cs.enforce("mult", lambda lc: lc + a, lambda lc: lc + b, lambda lc: lc + x)
+    cs.enforce("odd", lambda lc: lc + (32, a) - b + (7, ONE), lambda lc: lc + ONE - ONE, lambda lc: lc)
+    s = cs.pretty_print_equations()
+    d = lambda c: f"Scalar(0x{c:064x})"
+    assert s == ("INPUT ONE\nINPUT x\n"
+                 "\nmult: (`Aa`) * (`Ans/b`) = (`Ix`)"
+                 f"\nodd: ({d(7)} . `IONE` + 2^5 . {d(32)} . `Aa` - `Ans/b`) * (0) = (0)"
+                 "\n")
+    cs.close()
