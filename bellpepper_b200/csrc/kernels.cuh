@@ -1563,32 +1563,32 @@ __global__ void init_result(long long* first_bad, unsigned int* err, uint32_t* n
 // Every rank owns a mailbox of 2 x world slots in its own HBM; `boxes[r]` is rank r's mailbox as mapped into this process
 // (CUDA IPC over NVLink; boxes[rank] is the local one).  Exchange number e (a device-side counter, the same on every rank
 // because the call is collective) uses the slots of parity e & 1: lane j stores this rank's word into slot [e&1][rank] of
-// rank j's mailbox -- the value, a system-scope fence, then the epoch as the release flag -- and waits until slot [e&1][j] of
-// its OWN mailbox carries epoch e, i.e. until rank j's word has arrived.  Parity is enough: a rank cannot start exchange e+2
-// before every other rank has finished reading exchange e (its e+1 needs their e+1, which they only start after their e).
+// rank j's mailbox and waits until slot [e&1][j] of its OWN mailbox carries exchange e, i.e. until rank j's word has arrived.
+// A slot is two 8-byte packets {32 bits of the value, the 32-bit exchange number}: an aligned 8-byte store is one transaction,
+// so a packet whose flag is current carries current data -- no fence, no second round trip (the flag-in-the-data idea of
+// NCCL's LL protocol).  Parity is enough: a rank cannot start exchange e+2 before every other rank has finished reading
+// exchange e (its e+1 needs their e+1, which they only start after their e).
 struct GroupSlot {
-    long long value;
-    unsigned long long epoch;
+    unsigned long long lo, hi;  // (exchange number << 32) | value bits 31..0 / 63..32
 };
 __global__ void group_exchange(long long* word, GroupSlot* const* __restrict__ boxes, GroupSlot* my_box, unsigned long long* epoch_ctr, int rank,
                                int world) {
     const int j = threadIdx.x;
     const unsigned long long e = *epoch_ctr + 1ull;
+    const unsigned long long tag = (e & 0xffffffffull) << 32;
     const int par = (int)(e & 1ull);
-    const long long mine = *word;
+    const unsigned long long mine = (unsigned long long)*word;
     __syncwarp();
     long long got = 0x7fffffffffffffffLL;
     if (j < world) {
         GroupSlot* dst = boxes[j] + par * world + rank;
-        asm volatile("st.volatile.global.s64 [%0], %1;" ::"l"(&dst->value), "l"(mine) : "memory");
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(tag | (mine & 0xffffffffull)), "l"(tag | (mine >> 32)) : "memory");
         const GroupSlot* src = my_box + par * world + j;
-        unsigned long long seen;
+        unsigned long long lo, hi;
         do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&src->epoch) : "memory");
-        } while (seen != e);
-        asm volatile("ld.volatile.global.s64 %0, [%1];" : "=l"(got) : "l"(&src->value) : "memory");
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+        } while ((lo >> 32) != (tag >> 32) || (hi >> 32) != (tag >> 32));
+        got = (long long)((hi << 32) | (lo & 0xffffffffull));
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {

@@ -773,6 +773,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the library's host-side packer (bp_cs_recheck_scalars) uses every hardware thread by default: share them between the ranks
+    os.environ.setdefault("BP_PACK_THREADS", str(max(1, len(os.sched_getaffinity(0)) // max(1, world))))
     from bellpepper_b200.fields import NAME as FIELD_NAME
 
     head_name = HEADLINE if a.workload == "default" else a.workload

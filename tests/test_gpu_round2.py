@@ -309,8 +309,16 @@ def test_group_of_two_ranks_matches_oracle(tmp_path, mailbox):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     if not mailbox:
         env["BP_GROUP_NO_MAILBOX"] = "1"
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29611" if mailbox else "29612", str(script)], capture_output=True, text=True, timeout=600, env=env)
+    import socket
+
+    def launch():
+        with socket.socket() as sk:  # a free rendezvous port (a fixed one can still be in TIME_WAIT from an earlier run)
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                               "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600, env=env)
+
+    r = launch()
     if r.returncode != 0:
         tb = [ln for ln in r.stderr.splitlines() if "Error" in ln or "error" in ln or "File" in ln][-12:]
         raise AssertionError("worker failed:\n" + "\n".join(tb) + "\n" + r.stdout[-1500:])
