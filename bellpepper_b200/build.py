@@ -46,7 +46,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if force or _stale(FRONTEND, srcs + [os.path.join(host, "frontend.map")]):
         subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-Wno-subobject-linkage", "-Wl,--version-script=frontend.map",
                         "-o", FRONTEND, "frontend_host.cpp"], check=True, cwd=host)
-    for name in ("microbench", "microbench2"):
+    for name in ("microbench", "microbench2", "microbench3"):
         mb, out = os.path.join(CSRC, name + ".cu"), os.path.join(os.path.dirname(MICROBENCH), name)
         if os.path.exists(mb) and (force or _stale(out, srcs)):
             os.makedirs(os.path.dirname(out), exist_ok=True)

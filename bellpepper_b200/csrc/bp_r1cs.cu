@@ -730,7 +730,8 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
                 switch (lct_prefetch_depth(h)) {
                     case 0: DISPATCH_FIELD(h, (check_lct<F, false, 0><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
                     case 1: DISPATCH_FIELD(h, (check_lct<F, false, 1><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
-                    default: DISPATCH_FIELD(h, (check_lct<F, false, 2><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
+                    case 2: DISPATCH_FIELD(h, (check_lct<F, false, 2><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
+                    default: DISPATCH_FIELD(h, (check_lct<F, false, 3><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
                 }
                 h->launches++;
             } else {
@@ -1212,7 +1213,7 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
         return BP_OK;
     }
     if (!std::strcmp(key, "stream_prefetch")) {
-        if (v < -1 || v > 2) return fail(h, BP_E_ARG, "stream_prefetch out of range");
+        if (v < -1 || v > 3) return fail(h, BP_E_ARG, "stream_prefetch out of range");
         h->lct_prefetch = (int)v;
         drop_graph(h);
         return BP_OK;
@@ -1965,7 +1966,7 @@ const char* wprog_validate(const uint32_t* w, uint64_t n_words, uint64_t n_aux) 
         const uint32_t* tr = w + tape_off + 8 * t;
         const uint64_t n_vars = tr[0], lev = tr[1], n_lev = tr[2], ent = tr[3], n_ent = tr[4], sum = tr[5], n_sum = tr[6], sop = tr[7];
         tape_vars[t] = tr[0];
-        if (lev % 4 || ent % 4 || lev + 4 * n_lev > n_words || ent + 4 * n_ent > n_words || sum + 4 * n_sum > n_words || sop > n_words ||
+        if (lev % 4 || ent % 4 || sum % 4 || lev + 4 * n_lev > n_words || ent + 4 * n_ent > n_words || sum + 4 * n_sum > n_words || sop > n_words ||
             n_vars >= (1u << 24) || n_ent != n_vars || n_sum > w[9] || n_vars > w[8])
             return "bad tape record";
         uint64_t e_prev = 0, s_prev = 0;

@@ -111,10 +111,12 @@ __device__ __forceinline__ void ld_witness(uint32_t* w, const CsrView& m, bool i
             return;
         }
     }
+    // one 256-bit load; the L2::64B hint keeps an L2 miss of this random gather at 64 bytes of DRAM traffic instead of 128
+    // (microbench3 under ncu)
     const uint4* p = (is_aux ? m.aux : m.inputs) + 2 * (size_t)idx;
-    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
-    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w;
-    w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+    asm volatile("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
 }
 
 __device__ __forceinline__ void ld8(uint32_t* x, const uint4* p) {
@@ -1303,8 +1305,11 @@ __device__ __forceinline__ void ld256_stream(uint32_t* x, const uint4* p) {
                  : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
                  : "l"(p));
 }
+// A random 32-byte gather that misses L2 costs 128 bytes of DRAM traffic by default and 64 with the L2::64B prefetch-size
+// hint (measured with microbench3 under ncu: 107 -> 58 B per gather over a 512 MiB witness, 125 -> 63 B over 4 GiB; the
+// cudaLimitMaxL2FetchGranularity device limit changes nothing): the hint halves the traffic of a kernel that is DRAM-bound.
 __device__ __forceinline__ void ld256_keep(uint32_t* x, const uint4* p) {
-    asm volatile("ld.global.nc.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L2::evict_last.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
                  : "l"(p));
 }
@@ -1413,7 +1418,7 @@ template <int PF> __device__ __forceinline__ void lct_prefetch(uint32_t col, con
     if (PF == 0) return;
     const uint32_t cls = (col >> kColClsShift) & 7u;
     if (cls == kClsZero) return;
-    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(lct_witness_addr(col, m)));
+    if (PF != 3) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(lct_witness_addr(col, m)));
     if (PF >= 2 && is_product_class(cls)) asm volatile("prefetch.global.L2 [%0];" ::"l"(v.vals + 2 * slot));
 }
 __device__ __forceinline__ void lct_fetch(LctTerm& t, uint32_t col, const LctView& v, const CsrView& m, size_t slot) {
@@ -1445,7 +1450,8 @@ template <int F, int RIPPLE> __device__ __forceinline__ void lct_apply(uint32_t*
 }
 
 // PF: 0 = no L2 prefetch (column words three terms ahead, operands one term ahead in registers), 1 = L2 prefetch of the witness
-// element two terms ahead, 2 = of the witness element and the coefficient.
+// element two terms ahead, 2 = of the witness element and the coefficient, 3 = of the coefficient only (a prefetch always
+// brings a whole 128-byte line: for the random witness element that doubles the DRAM bytes of the 64-byte-hinted gather).
 template <int F, bool EMIT, int PF>
 __global__ void __launch_bounds__(kLctThreads, 2) check_lct(CsrView m, LctView v, CheckOut o, FieldConsts fc) {
     __shared__ uint32_t s_ab[2][8][kLctRows];   // A.w / B.w of the tile's rows (8 limbs, < 2^256), limb-major
@@ -1662,43 +1668,72 @@ __global__ void __launch_bounds__(32 * kWpWarps) wprog_run(const uint32_t* __res
         WpUnit u{bits, msg, states + 8u * ur[3], ur[2], msb_first};
         for (uint32_t i = lane; i < (n_vars + 31u) / 32u; i += 32u) bits[i] = 0u;
         __syncwarp();
+        // A unit is a chain of ~10^3 short levels: what matters is the latency of ONE level, so nothing a level needs is
+        // fetched when the level starts.  Level records are read 32 at a time (one per lane, handed round by shuffles); the
+        // first 32 entries and the first sum record of level l+1 are loaded while level l is evaluated.
+        const uint4* ents4 = reinterpret_cast<const uint4*>(ents);
+        const uint4* sums4 = reinterpret_cast<const uint4*>(sums);
+        uint4 ent_n = make_uint4(0, 0, 0, 0), sum_n = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-        for (uint32_t l = 0; l < n_levels; ++l) {
-            const uint32_t e0 = __ldg(levels + 4u * l), e1 = __ldg(levels + 4u * l + 1), s0 = __ldg(levels + 4u * l + 2),
-                           s1 = __ldg(levels + 4u * l + 3);
-#pragma unroll 1
-            for (uint32_t s = s0; s < s1; ++s) {  // integer sums of this level: lanes stride the weighted bits
-                const uint32_t first = __ldg(sums + 4u * s), n_ops = __ldg(sums + 4u * s + 1);
-                unsigned long long acc = 0;
-                for (uint32_t k = lane; k < n_ops; k += 32u) {
-                    const uint32_t op = __ldg(sumops + first + k);
-                    acc += (unsigned long long)wp_value(op, 0x00ffffffu, u) << ((op >> 24) & 31u);
-                }
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                if (lane == 0) sumv[s] = acc + (((unsigned long long)__ldg(sums + 4u * s + 3) << 32) | __ldg(sums + 4u * s + 2));
+        for (uint32_t lb = 0; lb < n_levels; lb += 32u) {
+            const uint4 rec = lb + lane < n_levels ? __ldg(reinterpret_cast<const uint4*>(levels) + lb + lane) : make_uint4(0, 0, 0, 0);
+            const uint32_t in_chunk = min(32u, n_levels - lb);
+            if (lb == 0) {  // prime the pipeline with level 0
+                const uint32_t e0 = __shfl_sync(0xffffffffu, rec.x, 0), e1 = __shfl_sync(0xffffffffu, rec.y, 0);
+                const uint32_t s0 = __shfl_sync(0xffffffffu, rec.z, 0), s1 = __shfl_sync(0xffffffffu, rec.w, 0);
+                if (e0 + lane < e1) ent_n = __ldg(ents4 + e0 + lane);
+                if (s0 < s1) sum_n = __ldg(sums4 + s0);
             }
-            __syncwarp();
-            for (uint32_t e = e0 + lane; e < e1; e += 32u) {
-                const uint4 r = __ldg(reinterpret_cast<const uint4*>(ents) + e);
-                const uint32_t op = r.x >> 28, res = r.x & 0x0fffffffu;
-                uint32_t v;
-                if (op == kWpSumBit) {
-                    v = (uint32_t)(sumv[r.y] >> r.z) & 1u;
-                } else {
-                    const uint32_t a = wp_value(r.y, 0x1fffffffu, u), b = wp_value(r.z, 0x1fffffffu, u);
-                    if (op == kWpXor) v = a ^ b;
-                    else if (op == kWpAnd) v = a & b;
-                    else if (op == kWpAndNot) v = a & (b ^ 1u);
-                    else if (op == kWpNor) v = (a ^ 1u) & (b ^ 1u);
-                    else {
-                        const uint32_t c = wp_value(r.w, 0x1fffffffu, u);
-                        v = op == kWpCh ? ((a & b) ^ ((a ^ 1u) & c)) : ((a & b) ^ (a & c) ^ (b & c));
+#pragma unroll 1
+            for (uint32_t k = 0; k < in_chunk; ++k) {
+                const uint32_t e0 = __shfl_sync(0xffffffffu, rec.x, k), e1 = __shfl_sync(0xffffffffu, rec.y, k);
+                const uint32_t s0 = __shfl_sync(0xffffffffu, rec.z, k), s1 = __shfl_sync(0xffffffffu, rec.w, k);
+                const uint4 ent_c = ent_n, sum_c = sum_n;
+                if (k + 1u < in_chunk) {  // (the first level of the next chunk is fetched when its records are known: see below)
+                    const uint32_t ne0 = __shfl_sync(0xffffffffu, rec.x, k + 1u), ne1 = __shfl_sync(0xffffffffu, rec.y, k + 1u);
+                    const uint32_t ns0 = __shfl_sync(0xffffffffu, rec.z, k + 1u), ns1 = __shfl_sync(0xffffffffu, rec.w, k + 1u);
+                    if (ne0 + lane < ne1) ent_n = __ldg(ents4 + ne0 + lane);
+                    if (ns0 < ns1) sum_n = __ldg(sums4 + ns0);
+                }
+#pragma unroll 1
+                for (uint32_t sidx = s0; sidx < s1; ++sidx) {  // integer sums of this level: lanes stride the weighted bits
+                    const uint4 sr = sidx == s0 ? sum_c : __ldg(sums4 + sidx);
+                    unsigned long long acc = 0;
+                    for (uint32_t q = lane; q < sr.y; q += 32u) {
+                        const uint32_t op = __ldg(sumops + sr.x + q);
+                        acc += (unsigned long long)wp_value(op, 0x00ffffffu, u) << ((op >> 24) & 31u);
                     }
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                    if (lane == 0) sumv[sidx] = acc + (((unsigned long long)sr.w << 32) | sr.z);
                 }
-                if (v) atomicOr(bits + (res >> 5), 1u << (res & 31u));
+                if (s1 > s0) __syncwarp();
+                for (uint32_t e = e0 + lane; e < e1; e += 32u) {
+                    const uint4 r = e < e0 + 32u ? ent_c : __ldg(ents4 + e);
+                    const uint32_t op = r.x >> 28, res = r.x & 0x0fffffffu;
+                    uint32_t v;
+                    if (op == kWpSumBit) {
+                        v = (uint32_t)(sumv[r.y] >> r.z) & 1u;
+                    } else {
+                        const uint32_t a = wp_value(r.y, 0x1fffffffu, u), b = wp_value(r.z, 0x1fffffffu, u);
+                        if (op == kWpXor) v = a ^ b;
+                        else if (op == kWpAnd) v = a & b;
+                        else if (op == kWpAndNot) v = a & (b ^ 1u);
+                        else if (op == kWpNor) v = (a ^ 1u) & (b ^ 1u);
+                        else {
+                            const uint32_t c = wp_value(r.w, 0x1fffffffu, u);
+                            v = op == kWpCh ? ((a & b) ^ ((a ^ 1u) & c)) : ((a & b) ^ (a & c) ^ (b & c));
+                        }
+                    }
+                    if (v) atomicOr(bits + (res >> 5), 1u << (res & 31u));
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            if (lb + 32u < n_levels) {  // first level of the next chunk
+                const uint4 nr = __ldg(reinterpret_cast<const uint4*>(levels) + lb + 32u);
+                if (nr.x + lane < nr.y) ent_n = __ldg(ents4 + nr.x + lane);
+                if (nr.z < nr.w) sum_n = __ldg(sums4 + nr.z);
+            }
         }
         uint32_t* out = aux_shadow + ur[1];
         for (uint32_t i = lane; i < n_vars; i += 32u) out[i] = (bits[i >> 5] >> (i & 31u)) & 1u;
