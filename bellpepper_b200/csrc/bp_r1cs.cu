@@ -731,7 +731,8 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
                     case 0: DISPATCH_FIELD(h, (check_lct<F, false, 0><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
                     case 1: DISPATCH_FIELD(h, (check_lct<F, false, 1><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
                     case 2: DISPATCH_FIELD(h, (check_lct<F, false, 2><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
-                    default: DISPATCH_FIELD(h, (check_lct<F, false, 3><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
+                    case 3: DISPATCH_FIELD(h, (check_lct<F, false, 3><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
+                    default: DISPATCH_FIELD(h, (check_lct<F, false, 4><<<lct_grid(h), kLctThreads, 0, h->stream>>>(m, lv, o, h->fc))); break;
                 }
                 h->launches++;
             } else {
@@ -1213,7 +1214,7 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
         return BP_OK;
     }
     if (!std::strcmp(key, "stream_prefetch")) {
-        if (v < -1 || v > 3) return fail(h, BP_E_ARG, "stream_prefetch out of range");
+        if (v < -1 || v > 4) return fail(h, BP_E_ARG, "stream_prefetch out of range");
         h->lct_prefetch = (int)v;
         drop_graph(h);
         return BP_OK;

@@ -1451,7 +1451,8 @@ template <int F, int RIPPLE> __device__ __forceinline__ void lct_apply(uint32_t*
 
 // PF: 0 = no L2 prefetch (column words three terms ahead, operands one term ahead in registers), 1 = L2 prefetch of the witness
 // element two terms ahead, 2 = of the witness element and the coefficient, 3 = of the coefficient only (a prefetch always
-// brings a whole 128-byte line: for the random witness element that doubles the DRAM bytes of the 64-byte-hinted gather).
+// brings a whole 128-byte line: for the random witness element that doubles the DRAM bytes of the 64-byte-hinted gather),
+// 4 = witness elements two terms ahead in REGISTERS + coefficient prefetch.
 template <int F, bool EMIT, int PF>
 __global__ void __launch_bounds__(kLctThreads, 2) check_lct(CsrView m, LctView v, CheckOut o, FieldConsts fc) {
     __shared__ uint32_t s_ab[2][8][kLctRows];   // A.w / B.w of the tile's rows (8 limbs, < 2^256), limb-major
@@ -1478,19 +1479,44 @@ __global__ void __launch_bounds__(kLctThreads, 2) check_lct(CsrView m, LctView v
             // software pipeline over the slice's L groups (padding groups carry the null column word)
             auto col_at = [&](uint32_t j) { return j < L ? ld32_stream(v.cols + slot0 + 32u * (size_t)j, pol) : kLctNullCol; };
             uint32_t c0 = col_at(0), c1 = col_at(1), c2 = col_at(2);
-            lct_prefetch<PF>(c1, v, m, slot0 + 32u);
-            LctTerm cur;
-            lct_fetch(cur, c0, v, m, slot0);
+            if (PF == 4) {
+                // witness elements TWO terms ahead in registers (a 64-byte DRAM fetch each), coefficients one term ahead behind an
+                // L2 prefetch: the latency cover of PF = 2 without its 128-byte prefetch lines
+                uint32_t wq[8];  // witness element of term j + 1, in flight
+                LctTerm cur;
+                lct_fetch(cur, c0, v, m, slot0);
+                if (((c1 >> kColClsShift) & 7u) != kClsZero) ld256_keep(wq, lct_witness_addr(c1, m));
 #pragma unroll 1
-            for (uint32_t j = 0; j < L; ++j) {
-                const uint32_t c3 = col_at(j + 3u);
-                lct_prefetch<PF>(c2, v, m, slot0 + 32u * (size_t)(j + 2u));
-                LctTerm nxt;
-                lct_fetch(nxt, c1, v, m, slot0 + 32u * (size_t)(j + 1u));
-                lct_apply<F, 17>(acc, cur, gen, mag);  // (one code path for A, B and C lanes: a slice mixes them)
-                cur = nxt;
-                c1 = c2;
-                c2 = c3;
+                for (uint32_t j = 0; j < L; ++j) {
+                    const uint32_t c3 = col_at(j + 3u);
+                    LctTerm nxt;
+                    nxt.cls = (c1 >> kColClsShift) & 7u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) nxt.w[i] = wq[i];
+                    if (is_product_class(nxt.cls)) ld256_stream(nxt.c, v.vals + 2 * (slot0 + 32u * (size_t)(j + 1u)));
+                    const uint32_t cls2 = (c2 >> kColClsShift) & 7u;
+                    if (cls2 != kClsZero) ld256_keep(wq, lct_witness_addr(c2, m));
+                    if (is_product_class(cls2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(v.vals + 2 * (slot0 + 32u * (size_t)(j + 2u))));
+                    lct_apply<F, 17>(acc, cur, gen, mag);
+                    cur = nxt;
+                    c1 = c2;
+                    c2 = c3;
+                }
+            } else {
+                lct_prefetch<PF>(c1, v, m, slot0 + 32u);
+                LctTerm cur;
+                lct_fetch(cur, c0, v, m, slot0);
+#pragma unroll 1
+                for (uint32_t j = 0; j < L; ++j) {
+                    const uint32_t c3 = col_at(j + 3u);
+                    lct_prefetch<PF>(c2, v, m, slot0 + 32u * (size_t)(j + 2u));
+                    LctTerm nxt;
+                    lct_fetch(nxt, c1, v, m, slot0 + 32u * (size_t)(j + 1u));
+                    lct_apply<F, 17>(acc, cur, gen, mag);  // (one code path for A, B and C lanes: a slice mixes them)
+                    cur = nxt;
+                    c1 = c2;
+                    c2 = c3;
+                }
             }
             const uint32_t r = id / 3u;
             if (len) {
