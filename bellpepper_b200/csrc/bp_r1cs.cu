@@ -14,6 +14,7 @@
 #include <nccl.h>  // types only: the library is bound at run time (dlopen), see NcclApi
 
 #include <algorithm>
+#include <mutex>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -86,6 +87,8 @@ struct bp_cs {
     uint64_t fat_terms = 96;   // rows with more terms than this go to the warp-per-row kernels (see eff_fat_terms)
     bool fat_terms_set = false;  // the caller chose the threshold (bp_cs_set_option): it is then used as it is
     int64_t fat_ctas_per_sm = 8;  // grid of check_fat_rows = sm_count * this
+    int64_t fat_int_ctas_per_sm = 6;  // grid of check_fat_int = sm_count * this (it runs BESIDE check_small: see launch_check)
+    int64_t small_ctas_per_sm = 5;    // grid of check_small = sm_count * this
     int64_t kernels_mask = 3;  // measurement aid: bit 0 = launch the thin-row kernels, bit 1 = launch check_fat_rows
     int64_t variant = -1;      // < 0: default; >= 0: bit 0 = no small-row kernel, bit 1 = no shadows in the fat kernel, bit 2 = park az/bz,
                                // bit 3 = no integer pass over the fat rows
@@ -626,7 +629,7 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
             cudaStream_t fs = h->side_stream;
             if (fat_int) {
-                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * 6);
+                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * (uint64_t)h->fat_int_ctas_per_sm);
                 DISPATCH_FIELD(h, (check_fat_int<F, true><<<igrid, block, 0, fs>>>(m, o, fat, (uint32_t)h->n_fat_rows,
                                                                                   (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
                 DISPATCH_FIELD(h, (check_fat_rows<F, true, 0, 4><<<std::min(fat_grid, h->sm_count), block, 0, fs>>>(
@@ -640,7 +643,7 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             CU(h, cudaEventRecord(h->ev_join, fs));
         }
         const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;
-        const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
+        const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * (uint64_t)h->small_ctas_per_sm);
         DISPATCH_FIELD(h, (check_small<F, true><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, 0u,
                                                                                              0xffffffffu)));
         const int lgrid = grid_for(h, h->n_gen_rows + (uint64_t)h->sm_count * block, block, 16);
@@ -690,7 +693,7 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
             cudaStream_t fs = h->side_stream;  // joined below: the check is complete on h->stream when the call returns
             const int fgrid_small = std::min(fat_grid, h->sm_count);
             if (fat_shadow && !(v & 8) && h->fat_int_ok) {  // integer pass first; the modular kernel takes what it could not decide
-                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * 6);
+                const int igrid = (int)std::min<uint64_t>((h->n_fat_rows + 3) / 4, (uint64_t)h->sm_count * (uint64_t)h->fat_int_ctas_per_sm);
                 DISPATCH_FIELD(h, (check_fat_int<F, false><<<igrid, block, 0, fs>>>(m, o, fat, (uint32_t)h->n_fat_rows,
                                                                                    (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
                 // (normally nothing is left: a small grid, grid-stride over whatever there is)
@@ -710,7 +713,7 @@ int launch_check(bp_cs* h, long long* dev_first_bad, uint4* az, uint4* bz, uint4
         if (h->kernels_mask & 1) {
             if (use_small) {
                 const uint64_t sblocks = (h->n_rows + kSmallRows - 1) / kSmallRows;  // one warp per block of rows
-                const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
+                const int sgrid = (int)std::min<uint64_t>((sblocks + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * (uint64_t)h->small_ctas_per_sm);
                 check_small<0, false><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, 0u,
                                                                                        0xffffffffu);
                 h->launches++;
@@ -765,19 +768,15 @@ struct NcclApi {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
-const NcclApi* nccl_api() {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api.lib ? &api : nullptr;
-    tried = true;
+bool nccl_bind(NcclApi& api) {
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
         api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
         if (api.lib) break;
     }
-    if (!api.lib) return nullptr;
+    if (!api.lib) return false;
 #define BP_NCCL_SYM(field, sym)                                         \
     *(void**)(&api.field) = dlsym(api.lib, sym);                        \
-    if (!api.field) { api.lib = nullptr; return nullptr; }
+    if (!api.field) { api.lib = nullptr; return false; }
     BP_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
     BP_NCCL_SYM(CommInitRank, "ncclCommInitRank")
     BP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
@@ -788,7 +787,14 @@ const NcclApi* nccl_api() {
     BP_NCCL_SYM(GroupEnd, "ncclGroupEnd")
     BP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef BP_NCCL_SYM
-    return &api;
+    return true;
+}
+
+const NcclApi* nccl_api() {  // bound once, whichever thread asks first (handles may live on different threads)
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] { (void)nccl_bind(api); });
+    return api.lib ? &api : nullptr;
 }
 
 }  // namespace
@@ -808,6 +814,7 @@ struct bp_group {
     void* peer_mapped[kMaxGroup] = {};        // what cudaIpcOpenMemHandle returned (to close)
     unsigned long long* d_epoch = nullptr;    // exchanges done so far (device counter: a captured graph needs no new argument)
     bool mailbox = false;
+    bool ready = false;                       // bp_group_init completed (teardown is collective only then)
     long long* h_result = nullptr;            // pinned host copy of the last synchronous result
 };
 
@@ -1207,6 +1214,12 @@ int bp_cs_set_option(bp_cs* h, const char* key, int64_t v) {
         if (v < 1 || v > 32) return fail(h, BP_E_ARG, "fat_ctas_per_sm out of range");
         h->fat_ctas_per_sm = v;
         drop_graph(h);  // (a launch dimension, not part of the graph key)
+        return BP_OK;
+    }
+    if (!std::strcmp(key, "fat_int_ctas_per_sm") || !std::strcmp(key, "small_ctas_per_sm")) {
+        if (v < 1 || v > 32) return fail(h, BP_E_ARG, "%s out of range", key);
+        (key[0] == 'f' ? h->fat_int_ctas_per_sm : h->small_ctas_per_sm) = v;
+        drop_graph(h);
         return BP_OK;
     }
     if (!std::strcmp(key, "sparse_upload")) {
@@ -1639,7 +1652,7 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
         const uint32_t blk_ready = i == n_chunks - 1 ? n_blocks : cp.rows[i] / kSmallRows;  // whole 64-row blocks only
         if (blk_ready > blk_done) {
             const uint32_t nb = blk_ready - blk_done;
-            const int sgrid = (int)std::min<uint64_t>((nb + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * 5);
+            const int sgrid = (int)std::min<uint64_t>((nb + kSmallThreads / 32 - 1) / (kSmallThreads / 32), (uint64_t)h->sm_count * (uint64_t)h->small_ctas_per_sm);
             check_small<0, false><<<sgrid, kSmallThreads, kSmallSmem, h->stream>>>(m, o, (uint32_t*)h->deferred.p, h->d_ndef, blk_done,
                                                                                    blk_ready);
             h->launches++;
@@ -1649,7 +1662,7 @@ static int recheck_u8(bp_cs* h, const uint8_t* inputs_u8, const uint8_t* aux_u8,
         uint32_t fat_ready = cp.fat[i];
         if (h->fat_int_ok && fat_ready > fat_done) {
             const uint32_t nf = fat_ready - fat_done;
-            const int igrid = (int)std::min<uint64_t>((nf + 3) / 4, (uint64_t)h->sm_count * 6);
+            const int igrid = (int)std::min<uint64_t>((nf + 3) / 4, (uint64_t)h->sm_count * (uint64_t)h->fat_int_ctas_per_sm);
             DISPATCH_FIELD(h, (check_fat_int<F, false><<<igrid, 128, 0, h->stream>>>(m, o, (const uint32_t*)h->fat_rows.p + fat_done, nf,
                                                                                     (uint32_t*)h->fat_undecided.p, h->d_ndef + 1)));
             h->launches++;
@@ -2290,6 +2303,13 @@ void bp_group_free(bp_group* g) {
     }
     for (int r = 0; r < g->world && r < kMaxGroup; ++r)
         if (g->peer_mapped[r]) cudaIpcCloseMemHandle(g->peer_mapped[r]);
+    // Collective: nobody frees its mailbox while a peer still has it mapped (freeing exported memory before every importer
+    // has closed it is undefined) -- one all-reduce after the closes is the barrier.
+    if (g->ready && g->world > 1 && g->comm && g->d_epoch && h) {
+        const NcclApi* api = nccl_api();
+        if (api && api->AllReduce(g->d_epoch, g->d_epoch, 1, ncclUint64, ncclMin, g->comm, h->stream) == ncclSuccess)
+            cudaStreamSynchronize(h->stream);
+    }
     if (g->d_peer_boxes) cudaFree(g->d_peer_boxes);
     if (g->box) cudaFree(g->box);
     if (g->d_epoch) cudaFree(g->d_epoch);
@@ -2395,6 +2415,7 @@ int bp_group_init(bp_cs* h, const uint8_t id[BP_GROUP_ID_BYTES], int rank, int w
     g->mailbox = mapped != 0 && !getenv("BP_GROUP_NO_MAILBOX");
     if (g->mailbox) CU(h, cudaMemcpyAsync(g->d_peer_boxes, peers.data(), sizeof(GroupSlot*) * world, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    g->ready = true;
     *out = g;
     return BP_OK;
 }

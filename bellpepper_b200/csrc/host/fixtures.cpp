@@ -1,6 +1,7 @@
 // C wrappers over the C++ host front-end (see include/bp_fixtures.h).
 #include "../../../include/bp_fixtures.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -269,6 +270,51 @@ int bp_tcs_witness_program(bp_tcs* t, const uint32_t** words, uint64_t* n_words)
     return BP_OK;
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+// One SHA-256 compression with the x86 SHA extensions (two rounds per SHA256RNDS2), used when the CPU has them: the chaining
+// states of a 4096-block message in ~0.2 ms instead of 1.7 ms with the portable code below.
+__attribute__((target("sha,sse4.1,ssse3"))) static void sha256_compress_shani(uint32_t state[8], const uint8_t* data) {
+    using sha256_detail::K;
+    const __m128i MASK = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i TMP = _mm_loadu_si128((const __m128i*)&state[0]);     // DCBA
+    __m128i STATE1 = _mm_loadu_si128((const __m128i*)&state[4]);  // HGFE
+    TMP = _mm_shuffle_epi32(TMP, 0xB1);                           // CDAB
+    STATE1 = _mm_shuffle_epi32(STATE1, 0x1B);                     // EFGH
+    __m128i STATE0 = _mm_alignr_epi8(TMP, STATE1, 8);             // ABEF
+    STATE1 = _mm_blend_epi16(STATE1, TMP, 0xF0);                  // CDGH
+    const __m128i ABEF_SAVE = STATE0, CDGH_SAVE = STATE1;
+    __m128i M[4];
+    for (int i = 0; i < 4; ++i) M[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(data + 16 * i)), MASK);
+    for (int r = 0; r < 16; ++r) {  // four rounds each
+        __m128i MSG = _mm_add_epi32(M[r & 3], _mm_loadu_si128((const __m128i*)&K[4 * r]));
+        STATE1 = _mm_sha256rnds2_epu32(STATE1, STATE0, MSG);
+        MSG = _mm_shuffle_epi32(MSG, 0x0E);
+        STATE0 = _mm_sha256rnds2_epu32(STATE0, STATE1, MSG);
+        if (r < 12) {  // schedule W[4(r+4) .. 4(r+4)+3] into M[r & 3]
+            __m128i t = _mm_sha256msg1_epu32(M[r & 3], M[(r + 1) & 3]);
+            t = _mm_add_epi32(t, _mm_alignr_epi8(M[(r + 3) & 3], M[(r + 2) & 3], 4));
+            M[r & 3] = _mm_sha256msg2_epu32(t, M[(r + 3) & 3]);
+        }
+    }
+    STATE0 = _mm_add_epi32(STATE0, ABEF_SAVE);
+    STATE1 = _mm_add_epi32(STATE1, CDGH_SAVE);
+    TMP = _mm_shuffle_epi32(STATE0, 0x1B);        // FEBA
+    STATE1 = _mm_shuffle_epi32(STATE1, 0xB1);     // DCHG
+    STATE0 = _mm_blend_epi16(TMP, STATE1, 0xF0);  // DCBA
+    STATE1 = _mm_alignr_epi8(STATE1, TMP, 8);     // HGFE
+    _mm_storeu_si128((__m128i*)&state[0], STATE0);
+    _mm_storeu_si128((__m128i*)&state[4], STATE1);
+}
+static bool have_shani() {
+    static const bool ok = __builtin_cpu_supports("sha") && __builtin_cpu_supports("sse4.1") && __builtin_cpu_supports("ssse3");
+    return ok;
+}
+#else
+static bool have_shani() { return false; }
+static void sha256_compress_shani(uint32_t*, const uint8_t*) {}
+#endif
+
 // Chaining states of sha256 over `len` message bytes: 8 words BEFORE each compression block (block 0: the IV), blocks as the
 // gadget pads them (sha256.rs:50-77).  Plain SHA-256 on the host: what bp_cs_generate_witness_async wants per unit.
 int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, uint64_t max_blocks, uint64_t* n_blocks) {
@@ -285,13 +331,18 @@ int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, u
     for (uint64_t b = 0; b < blocks; ++b) {
         std::memcpy(states + 8 * b, h, sizeof h);
         uint8_t blk[64];
-        for (unsigned i = 0; i < 64; ++i) {
+        if (64 * (b + 1) <= len) std::memcpy(blk, msg + 64 * b, 64);
+        else for (unsigned i = 0; i < 64; ++i) {
             const uint64_t p = 64 * b + i;
             uint8_t v = 0;
             if (p < len) v = msg[p];
             else if (p == len) v = 0x80;
             else if (p >= 64 * blocks - 8) v = (uint8_t)((8 * len) >> (8 * (64 * blocks - 1 - p)));
             blk[i] = v;
+        }
+        if (have_shani() && !getenv("BP_NO_SHANI")) {
+            sha256_compress_shani(h, blk);
+            continue;
         }
         uint32_t w[64];
         for (unsigned i = 0; i < 16; ++i) w[i] = (uint32_t)blk[4 * i] << 24 | (uint32_t)blk[4 * i + 1] << 16 | (uint32_t)blk[4 * i + 2] << 8 | blk[4 * i + 3];

@@ -38,10 +38,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# the CPU baseline's OpenMP team: pinned threads that spin between passes (set before libgomp is loaded), so that the same
-# sample gives the same rate in the GPU arm's cpu_baseline leg and in the --impl reference arm
-os.environ.setdefault("OMP_PROC_BIND", "true")
-os.environ.setdefault("OMP_WAIT_POLICY", "active")
 
 SEED = 0x5962BE3D763D318D
 N_INPUTS = 16

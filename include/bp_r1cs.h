@@ -135,7 +135,8 @@ int bp_cs_set_many(bp_cs* cs, int is_aux, uint64_t n, const uint64_t* idx, const
  * inputs) and n_aux of them -- what WitnessCS holds (witness_cs.rs:45-57: input_assignment / aux_assignment).  The library
  * packs on the host before it sends (every 0/1 value becomes one bit, anything else an (index, value) exception applied by a
  * scatter kernel), so a gadget witness of 10^8 bits costs 14 MB of PCIe traffic instead of 3.5 GB; a witness that is not
- * mostly bits is sent as it is.  Then which_is_unsatisfied.  The _async form leaves the first failing GLOBAL row in DEVICE
+ * mostly bits is sent as it is.  The packing pass uses every hardware thread; several processes on one host (one per GPU)
+ * should share them: environment variable BP_PACK_THREADS = threads per process.  Then which_is_unsatisfied.  The _async form leaves the first failing GLOBAL row in DEVICE
  * memory (INT64_MAX = satisfied); the scalars are consumed before either form returns. */
 int bp_cs_recheck_scalars(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row);
 int bp_cs_recheck_scalars_async(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result);
@@ -237,7 +238,7 @@ typedef struct bp_group bp_group;
 int bp_group_unique_id(uint8_t id[BP_GROUP_ID_BYTES]);
 /* Join `cs` (this rank's row shard) to the group.  world == 1 is valid (id may be NULL) and needs no NCCL. */
 int bp_group_init(bp_cs* cs, const uint8_t id[BP_GROUP_ID_BYTES], int rank, int world, bp_group** out);
-void bp_group_free(bp_group* g);
+void bp_group_free(bp_group* g); /* collective too: a rank's mailbox is freed only after every peer has unmapped it */
 /* *transport: 0 = single rank, 1 = NCCL all-reduce, 2 = peer-memory mailboxes. */
 int bp_group_info(bp_group* g, int* rank, int* world, int* transport);
 /* which_is_unsatisfied over ALL shards (test_cs.rs:239-253): *row = the first unsatisfied GLOBAL row or -1, the same

@@ -51,3 +51,29 @@ def test_product_never_imports_oracle():
                 # the only library the product may bind at run time is NCCL (multi-GPU groups)
                 for m in re.finditer(r"dlopen\s*\(", src):
                     assert "libnccl" in src[max(0, m.start() - 400):m.start()], (f, "dlopen of something that is not NCCL")
+
+
+def test_split_rows_by_nnz_is_host_only_and_balances_terms():
+    """bp_split_rows_by_nnz (shards balanced by terms, not rows) needs no device."""
+    import ctypes
+
+    import numpy as np
+
+    from bellpepper_b200 import ffi
+
+    L = ffi.load()
+    rng = np.random.default_rng(1)
+    lens = rng.integers(0, 6, size=3 * 5000).astype(np.uint32)
+    lens[3 * 100] = 900  # a MultiEq-like fat row
+    lens[3 * 4000 + 2] = 700
+    n = lens.size // 3
+    w = lens.reshape(-1, 3).sum(1).astype(np.int64) + 1
+    for world in (1, 2, 4, 8):
+        b = np.zeros(world + 1, np.uint64)
+        assert L.bp_split_rows_by_nnz(lens.ctypes.data, n, world, b.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) == 0
+        bi = b.astype(np.int64)
+        assert bi[0] == 0 and bi[-1] == n and (np.diff(bi) >= 0).all()
+        per = [int(w[bi[r]:bi[r + 1]].sum()) for r in range(world)]
+        assert max(per) - min(per) <= 2 * 901, per  # within a fat row of each other
+    assert L.bp_split_rows_by_nnz(None, 0, 3, b.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) == 0
+    assert L.bp_split_rows_by_nnz(lens.ctypes.data, n, 0, b.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) == -5
