@@ -14,6 +14,7 @@
 #include <nccl.h>  // types only: the library is bound at run time (dlopen), see NcclApi
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <utility>
@@ -25,6 +26,7 @@
 #include <string>
 
 #include "kernels.cuh"
+#include "host/pack.hpp"
 
 namespace {
 
@@ -2167,10 +2169,8 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
     CU(h, cudaStreamSynchronize(h->stream));  // the pinned buffers of the previous call are free again
     int rc = ensure_pinned(h, h->h_pack, h->h_pack_cap, aux_off + aux_bytes + 64);
     if (rc != BP_OK) return rc;
-    unsigned nt = std::thread::hardware_concurrency();
-    if (const char* e = getenv("BP_PACK_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-    nt = std::max(1u, std::min(nt, 64u));
-    struct Exc { uint64_t idx; uint64_t v[4]; };
+    const unsigned nt = pack_threads();
+    using Exc = PackExc;  // host/pack.hpp: the packing kernel (AVX2 when the CPU has it) lives in its own host-only file
     uint8_t* bits_in = (uint8_t*)h->h_pack;
     uint8_t* bits_aux = bits_in + aux_off;
     std::vector<std::vector<Exc>> exc((size_t)nt * 2);
@@ -2186,30 +2186,20 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
     }
     uint64_t aux_range_bytes = 0;
     for (auto& r : aux_bytes_ranges) aux_range_bytes += r.second - r.first;
-    // bytes [b0, b1) of the bit string of `src` (elements [8*b0, min(8*b1, n)))
-    auto pack_bytes = [&](const uint64_t* src, uint64_t n, uint8_t* dst, uint64_t b0, uint64_t b1, std::vector<Exc>& out) {
-        for (uint64_t b = b0; b < b1; ++b) {
-            uint8_t acc = 0;
-            const uint64_t e0 = 8 * b, e1 = std::min<uint64_t>(e0 + 8, n);
-            for (uint64_t i = e0; i < e1; ++i) {
-                const uint64_t* v = src + 4 * i;
-                if ((v[1] | v[2] | v[3]) == 0 && v[0] <= 1) {
-                    acc |= (uint8_t)(v[0] << (i - e0));
-                } else {
-                    out.push_back(Exc{i, {v[0], v[1], v[2], v[3]}});
-                }
-            }
-            dst[b] = acc;
-        }
-    };
+    // pack_bit_bytes: bytes [b0, b1) of the bit string of `src` (elements [8*b0, min(8*b1, n)))
+    std::atomic<bool> pack_failed{false};
     auto work = [&](unsigned t) {
-        if (n_in) pack_bytes(inputs_le, n_in, bits_in, in_bytes * t / nt, in_bytes * (t + 1) / nt, exc[2 * t]);
-        // thread t takes the slice [s0, s1) of the concatenated aux byte ranges
-        uint64_t s0 = aux_range_bytes * t / nt, s1 = aux_range_bytes * (t + 1) / nt, base = 0;
-        for (auto& r : aux_bytes_ranges) {
-            const uint64_t len = r.second - r.first, lo = std::max(s0, base), hi = std::min(s1, base + len);
-            if (lo < hi) pack_bytes(aux_le, n_aux, bits_aux, r.first + (lo - base), r.first + (hi - base), exc[2 * t + 1]);
-            base += len;
+        try {
+            if (n_in) pack_bit_bytes(inputs_le, n_in, bits_in, in_bytes * t / nt, in_bytes * (t + 1) / nt, exc[2 * t]);
+            // thread t takes the slice [s0, s1) of the concatenated aux byte ranges
+            uint64_t s0 = aux_range_bytes * t / nt, s1 = aux_range_bytes * (t + 1) / nt, base = 0;
+            for (auto& r : aux_bytes_ranges) {
+                const uint64_t len = r.second - r.first, lo = std::max(s0, base), hi = std::min(s1, base + len);
+                if (lo < hi) pack_bit_bytes(aux_le, n_aux, bits_aux, r.first + (lo - base), r.first + (hi - base), exc[2 * t + 1]);
+                base += len;
+            }
+        } catch (...) {  // (an exception list that cannot grow: nothing may leave a thread)
+            pack_failed = true;
         }
     };
     {
@@ -2218,6 +2208,7 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
         work(0);
         for (auto& x : th) x.join();
     }
+    if (pack_failed) return fail(h, BP_E_OOM, "bp_cs_recheck_scalars: out of host memory while packing");
     size_t n_exc[2] = {0, 0};
     for (unsigned t = 0; t < nt; ++t) {
         n_exc[0] += exc[2 * t].size();

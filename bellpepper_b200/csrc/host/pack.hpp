@@ -1,0 +1,29 @@
+// Host-side packing of a witness given as the reference holds it -- 32-byte canonical little-endian scalars, the Vec<Scalar>s of
+// WitnessCS (witness_cs.rs:45-57) -- into what crosses PCIe: one bit per 0/1 value plus an exception list for everything else.
+// Pure host code (g++; no CUDA): bp_cs_recheck_scalars[_async] and the exported bp_pack_scalars use it, and the CPU tests
+// drive it without a device.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+namespace bp {
+
+struct PackExc {  // an element whose value is neither 0 nor 1
+    uint64_t idx;
+    uint64_t v[4];
+};
+
+// Bytes [b0, b1) of the bit string of src[0 .. n): element i is bit (i & 7) of dst[i >> 3] when its value is 0 or 1; any other
+// element leaves a 0 bit and is appended to `out` (ascending index).  Bits past element n - 1 in the last byte are 0.
+// Dispatches once to an AVX2 kernel (8 elements = one output byte per step, software prefetch ahead of the stream) when the CPU
+// has it; environment variable BP_PACK_SIMD=0 forces the portable loop.
+void pack_bit_bytes(const uint64_t* src, uint64_t n, uint8_t* dst, uint64_t b0, uint64_t b1, std::vector<PackExc>& out);
+
+// Threads of one packing pass: BP_PACK_THREADS, else every hardware thread; 1 .. 64.
+unsigned pack_threads();
+
+// "avx2" or "portable": what pack_bit_bytes runs on this CPU (bp_pack_kernel reports it).
+const char* pack_kernel_name();
+
+}  // namespace bp

@@ -411,6 +411,8 @@ def measure(ctx, name, a, headline):
             up = opt(L, h, "recheck_upload_bytes")
             e2e_scalars = {"value": n_rows_total / sc_s, "ms_per_step": sc_s * 1e3, "h2d_bytes_per_step": (up + 7) // 8,
                            "host_bytes_read_per_step": up * 32,
+                           "packer": {"kernel": L.bp_pack_kernel().decode(), "threads": int(os.environ.get("BP_PACK_THREADS", "0")),
+                                      "host_GBps": up * 32 / sc_s / 1e9},
                            "what": "32-byte canonical scalars in pinned host memory -> bp_cs_recheck_scalars: packed on the host (one bit "
                                    "per 0/1 value + exception list, all host threads), H2D of the bits, widened into the witness shadows, "
                                    "check" + ("; each rank packs and sends only the chunks its row shard reads, then the exchange" if world > 1 else "")}

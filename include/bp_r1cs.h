@@ -136,10 +136,23 @@ int bp_cs_set_many(bp_cs* cs, int is_aux, uint64_t n, const uint64_t* idx, const
  * packs on the host before it sends (every 0/1 value becomes one bit, anything else an (index, value) exception applied by a
  * scatter kernel), so a gadget witness of 10^8 bits costs 14 MB of PCIe traffic instead of 3.5 GB; a witness that is not
  * mostly bits is sent as it is.  The packing pass uses every hardware thread; several processes on one host (one per GPU)
- * should share them: environment variable BP_PACK_THREADS = threads per process.  Then which_is_unsatisfied.  The _async form leaves the first failing GLOBAL row in DEVICE
- * memory (INT64_MAX = satisfied); the scalars are consumed before either form returns. */
+ * should share them: environment variable BP_PACK_THREADS = threads per process.  Then which_is_unsatisfied.  The _async form
+ * leaves the first failing GLOBAL row in DEVICE memory (INT64_MAX = satisfied); the scalars are consumed before either form
+ * returns. */
 int bp_cs_recheck_scalars(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row);
 int bp_cs_recheck_scalars_async(bp_cs* cs, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result);
+
+/* The packing pass of bp_cs_recheck_scalars alone: HOST ONLY, no handle and no device -- for a caller that packs once and
+ * re-checks many times, or overlaps the pass with its own work, and then calls bp_cs_recheck_bits (+ bp_cs_set_many for the
+ * exceptions).  n scalars (32-byte canonical little-endian, witness_cs.rs:45-57) -> bits[(n + 7) / 8]: element i is bit
+ * (i & 7) of bits[i >> 3] when its value is 0 or 1; any other element leaves a 0 bit and is reported as exception
+ * (exc_idx[k], exc_vals_le[4k .. 4k + 4)), in ascending index order.  *n_exc = the number found; when it exceeds exc_cap only
+ * the first exc_cap are stored and BP_E_RANGE is returned (call again with more room).  Values are NOT compared with p here
+ * (bp_cs_set_many does that).  Threads as above (BP_PACK_THREADS); one sequential read of the scalars, AVX2 when the CPU has
+ * it (bp_pack_kernel: "avx2" / "portable"; BP_PACK_SIMD=0 forces the portable loop). */
+int bp_pack_scalars(const uint64_t* scalars_le, uint64_t n, uint8_t* bits, uint64_t* exc_idx, uint64_t* exc_vals_le, uint64_t exc_cap,
+                    uint64_t* n_exc);
+const char* bp_pack_kernel(void);
 
 /* ---- witness generation on the device (the "witness evaluation" half: SizedWitness::generate_witness_into, witness_cs.rs:7-41)
  * For a bit-logic gadget circuit (boolean / uint32 / sha256: every aux value is a bit that follows from earlier bits) the NEXT

@@ -76,19 +76,65 @@ def replay(prog: np.ndarray, msg: bytes, states: np.ndarray) -> np.ndarray:
     return out
 
 
-def test_chain_states_match_hashlib():
-    for n in (0, 1, 55, 56, 64, 119, 120, 1000):
+_K256 = [
+    0x428A2F98, 0x71374491, 0xB5C0FBCF, 0xE9B5DBA5, 0x3956C25B, 0x59F111F1, 0x923F82A4, 0xAB1C5ED5, 0xD807AA98, 0x12835B01, 0x243185BE,
+    0x550C7DC3, 0x72BE5D74, 0x80DEB1FE, 0x9BDC06A7, 0xC19BF174, 0xE49B69C1, 0xEFBE4786, 0x0FC19DC6, 0x240CA1CC, 0x2DE92C6F, 0x4A7484AA,
+    0x5CB0A9DC, 0x76F988DA, 0x983E5152, 0xA831C66D, 0xB00327C8, 0xBF597FC7, 0xC6E00BF3, 0xD5A79147, 0x06CA6351, 0x14292967, 0x27B70A85,
+    0x2E1B2138, 0x4D2C6DFC, 0x53380D13, 0x650A7354, 0x766A0ABB, 0x81C2C92E, 0x92722C85, 0xA2BFE8A1, 0xA81A664B, 0xC24B8B70, 0xC76C51A3,
+    0xD192E819, 0xD6990624, 0xF40E3585, 0x106AA070, 0x19A4C116, 0x1E376C08, 0x2748774C, 0x34B0BCB5, 0x391C0CB3, 0x4ED8AA4A, 0x5B9CCA4F,
+    0x682E6FF3, 0x748F82EE, 0x78A5636F, 0x84C87814, 0x8CC70208, 0x90BEFFFA, 0xA4506CEB, 0xBEF9A3F7, 0xC67178F2]
+_IV256 = [0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A, 0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19]
+
+
+def _compress256(state, block):
+    """FIPS 180-4 section 6.2.2 in plain Python (hashlib exposes no intermediate states)."""
+    M = 0xFFFFFFFF
+    rotr = lambda x, r: ((x >> r) | (x << (32 - r))) & M  # noqa: E731
+    w = [int.from_bytes(block[4 * i:4 * i + 4], "big") for i in range(16)]
+    for i in range(16, 64):
+        s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3)
+        s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10)
+        w.append((w[i - 16] + s0 + w[i - 7] + s1) & M)
+    a, b, c, d, e, f, g, h = state
+    for i in range(64):
+        t1 = (h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & M & g)) + _K256[i] + w[i]) & M
+        t2 = ((rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c))) & M
+        a, b, c, d, e, f, g, h = (t1 + t2) & M, a, b, c, (d + t1) & M, e, f, g
+    return [(x + y) & M for x, y in zip(state, (a, b, c, d, e, f, g, h))]
+
+
+def _chain_states_py(msg):
+    padded = msg + b"\x80" + b"\x00" * ((55 - len(msg)) % 64) + (8 * len(msg)).to_bytes(8, "big")
+    assert len(padded) % 64 == 0
+    states, st = [], list(_IV256)
+    for b in range(len(padded) // 64):
+        states.append(st)
+        st = _compress256(st, padded[64 * b:64 * b + 64])
+    return states, st
+
+
+def check_chain_states():
+    import hashlib
+
+    for n in (0, 1, 55, 56, 63, 64, 65, 119, 120, 128, 1000, 64 * 40 - 9):
         msg = fixtures.xorshift_bytes(n)
+        want, final = _chain_states_py(msg)
+        assert b"".join(x.to_bytes(4, "big") for x in final) == hashlib.sha256(msg).digest()  # the restatement itself
         st = fixtures.sha256_chain_states(msg)
-        assert st.shape[0] == (n + 9 + 63) // 64
-        assert list(st[0]) == [0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A, 0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19]
-    # the state after the last block is the digest: run one more byte-block's worth by hashing a longer padded message by hand
-    msg = fixtures.xorshift_bytes(200)
-    st = fixtures.sha256_chain_states(msg)
-    # hashlib cannot expose intermediate states; check the first block boundary through a 64-byte prefix trick instead:
-    # sha256(prefix64 || rest) state after block 0 == state after compressing prefix64 from the IV, which the gadget circuit
-    # also computes -- covered by test_recorded_program_reproduces_the_witness below (witness of block 1 depends on it)
-    assert st.shape == (4, 8)
+        assert st.shape == ((n + 9 + 63) // 64, 8)
+        assert st.tolist() == want, n
+
+
+def test_chain_states_match_sha256():
+    """bp_sha256_chain_states (the hash state before every compression block: what bp_cs_generate_witness_async takes) against
+    plain-Python SHA-256, itself checked against hashlib -- on whichever kernel this CPU selects ..."""
+    check_chain_states()
+
+
+def test_chain_states_match_sha256_portable_kernel(monkeypatch):
+    """... and on the portable one (BP_NO_SHANI is read at every call)."""
+    monkeypatch.setenv("BP_NO_SHANI", "1")
+    check_chain_states()
 
 
 def test_recorded_program_reproduces_the_witness():
