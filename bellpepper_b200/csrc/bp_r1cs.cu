@@ -2160,7 +2160,9 @@ extern "C" int bp_cs_set_many(bp_cs* h, int is_aux, uint64_t n, const uint64_t* 
 // (index + 32 bytes) that a scatter kernel applies after the bits have been widened.  A gadget witness of 10^8 bits is then
 // 14 MB of PCIe traffic instead of 3.5 GB; the packing pass (all host threads, one sequential read of the scalars) is the
 // cost of the call.  A witness with many non-bit values is sent as it is (bp_cs_set_range).
-extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result) {
+// `mont`: the scalars are in their in-memory Montgomery form (x * 2^256 mod p; bp_cs_recheck_scalars_mont) -- the pass looks
+// for the limb patterns of 0 and 2^256 mod p instead of 0 and 1, and the exceptions are converted on the host.
+static int recheck_scalars_impl(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result, bool mont) {
     if (!h || !dev_result || (!aux_le && h->n_aux)) return BP_E_ARG;
     CU(h, cudaSetDevice(h->device));
     const uint64_t n_in = inputs_le ? h->n_inputs : 0, n_aux = h->n_aux;
@@ -2186,16 +2188,22 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
     }
     uint64_t aux_range_bytes = 0;
     for (auto& r : aux_bytes_ranges) aux_range_bytes += r.second - r.first;
-    // pack_bit_bytes: bytes [b0, b1) of the bit string of `src` (elements [8*b0, min(8*b1, n)))
+    // pack_bit_bytes[_mont]: bytes [b0, b1) of the bit string of `src` (elements [8*b0, min(8*b1, n)))
+    uint64_t one_mont[4] = {1, 0, 0, 0};
+    if (mont) mont_one(h->field, one_mont);
+    auto pack_some = [&](const uint64_t* src, uint64_t n, uint8_t* dst, uint64_t b0, uint64_t b1, std::vector<Exc>& out) {
+        if (mont) pack_bit_bytes_mont(src, n, one_mont, dst, b0, b1, out);
+        else pack_bit_bytes(src, n, dst, b0, b1, out);
+    };
     std::atomic<bool> pack_failed{false};
     auto work = [&](unsigned t) {
         try {
-            if (n_in) pack_bit_bytes(inputs_le, n_in, bits_in, in_bytes * t / nt, in_bytes * (t + 1) / nt, exc[2 * t]);
+            if (n_in) pack_some(inputs_le, n_in, bits_in, in_bytes * t / nt, in_bytes * (t + 1) / nt, exc[2 * t]);
             // thread t takes the slice [s0, s1) of the concatenated aux byte ranges
             uint64_t s0 = aux_range_bytes * t / nt, s1 = aux_range_bytes * (t + 1) / nt, base = 0;
             for (auto& r : aux_bytes_ranges) {
                 const uint64_t len = r.second - r.first, lo = std::max(s0, base), hi = std::min(s1, base + len);
-                if (lo < hi) pack_bit_bytes(aux_le, n_aux, bits_aux, r.first + (lo - base), r.first + (hi - base), exc[2 * t + 1]);
+                if (lo < hi) pack_some(aux_le, n_aux, bits_aux, r.first + (lo - base), r.first + (hi - base), exc[2 * t + 1]);
                 base += len;
             }
         } catch (...) {  // (an exception list that cannot grow: nothing may leave a thread)
@@ -2215,14 +2223,30 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
         n_exc[1] += exc[2 * t + 1].size();
     }
     if (n_exc[0] + n_exc[1] > (n_in + (sparse ? 8 * aux_range_bytes : n_aux)) / 16 + 1024) {  // not a bit witness: send it as it is
+        if (mont) {  // ... in canonical form: one conversion pass on the host threads
+            std::vector<uint64_t> canon;
+            try {
+                canon.resize(4 * (size_t)std::max(n_in, n_aux));
+            } catch (...) {
+                return fail(h, BP_E_OOM, "bp_cs_recheck_scalars_mont: no host memory for the canonical copy");
+            }
+            for (int k = 0; k < 2; ++k) {
+                const uint64_t n = k ? n_aux : n_in;
+                if (!n) continue;
+                if (bp_scalars_from_mont(h->field, k ? aux_le : inputs_le, n, canon.data()) != BP_OK)
+                    return fail(h, BP_E_RANGE, "bp_cs_recheck_scalars_mont: an %s element is >= p (not a Montgomery-form scalar)", k ? "aux" : "input");
+                if ((rc = bp_cs_set_range(h, k, 0, n, canon.data())) != BP_OK) return rc;  // (synchronous: canon may be reused)
+            }
+            return check_graphed(h, (long long*)dev_result, nullptr);
+        }
         if (n_in && (rc = bp_cs_set_range(h, 0, 0, n_in, inputs_le)) != BP_OK) return rc;
         if (n_aux && (rc = bp_cs_set_range(h, 1, 0, n_aux, aux_le)) != BP_OK) return rc;
         return check_graphed(h, (long long*)dev_result, nullptr);
     }
     for (int k = 0; k < 2; ++k)  // the exceptions must be field elements (the bits are by construction)
         for (unsigned t = 0; t < nt; ++t)
-            for (const Exc& e : exc[2 * t + k])
-                if (!limbs_below_p(h, e.v))
+            for (Exc& e : exc[2 * t + k])
+                if (mont ? !from_mont(h->field, e.v, e.v) : !limbs_below_p(h, e.v))
                     return fail(h, BP_E_RANGE, "bp_cs_recheck_scalars: %s element %llu is not canonical (>= p)", k ? "aux" : "input",
                                 (unsigned long long)e.idx);
     if (n_in && (rc = set_range_packed(h, 0, 0, n_in, bits_in, true, false)) != BP_OK) return rc;
@@ -2258,9 +2282,17 @@ extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, 
     return check_graphed(h, (long long*)dev_result, nullptr);
 }
 
-extern "C" int bp_cs_recheck_scalars(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row) {
+extern "C" int bp_cs_recheck_scalars_async(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* dev_result) {
+    return recheck_scalars_impl(h, inputs_le, aux_le, dev_result, false);
+}
+
+extern "C" int bp_cs_recheck_scalars_mont_async(bp_cs* h, const uint64_t* inputs_mont, const uint64_t* aux_mont, int64_t* dev_result) {
+    return recheck_scalars_impl(h, inputs_mont, aux_mont, dev_result, true);
+}
+
+static int recheck_scalars_sync(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row, bool mont) {
     if (!h || !row) return BP_E_ARG;
-    int rc = bp_cs_recheck_scalars_async(h, inputs_le, aux_le, (int64_t*)h->d_result);
+    int rc = recheck_scalars_impl(h, inputs_le, aux_le, (int64_t*)h->d_result, mont);
     if (rc != BP_OK) return rc;
     long long fb;
     unsigned int e;
@@ -2268,6 +2300,14 @@ extern "C" int bp_cs_recheck_scalars(bp_cs* h, const uint64_t* inputs_le, const 
     if (e & 1u) return fail(h, BP_E_RANGE, "a term references a variable index that does not exist");
     *row = fb == 0x7fffffffffffffffLL ? -1 : (int64_t)(fb - (long long)h->row_base);
     return BP_OK;
+}
+
+extern "C" int bp_cs_recheck_scalars(bp_cs* h, const uint64_t* inputs_le, const uint64_t* aux_le, int64_t* row) {
+    return recheck_scalars_sync(h, inputs_le, aux_le, row, false);
+}
+
+extern "C" int bp_cs_recheck_scalars_mont(bp_cs* h, const uint64_t* inputs_mont, const uint64_t* aux_mont, int64_t* row) {
+    return recheck_scalars_sync(h, inputs_mont, aux_mont, row, true);
 }
 
 extern "C" {

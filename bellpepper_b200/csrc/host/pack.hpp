@@ -20,6 +20,18 @@ struct PackExc {  // an element whose value is neither 0 nor 1
 // has it; environment variable BP_PACK_SIMD=0 forces the portable loop.
 void pack_bit_bytes(const uint64_t* src, uint64_t n, uint8_t* dst, uint64_t b0, uint64_t b1, std::vector<PackExc>& out);
 
+// The same for scalars as they sit IN MEMORY in the reference's Vec<Scalar> (witness_cs.rs:45-57): blstrs::Scalar and
+// pasta_curves::{Fp, Fq} are 4 x u64 little-endian limbs of the MONTGOMERY form x * 2^256 mod p, so the bit 1 is the limb
+// pattern `one` = 2^256 mod p (mont_one) and 0 is all-zero.  An element that is neither goes to `out` with its limbs as they
+// are (still Montgomery: from_mont converts the few there are).  No pass over the witness to call to_repr() is needed.
+void pack_bit_bytes_mont(const uint64_t* src, uint64_t n, const uint64_t one[4], uint8_t* dst, uint64_t b0, uint64_t b1,
+                         std::vector<PackExc>& out);
+
+// Montgomery constants / conversion on the host (field ids of include/bp_r1cs.h): one = 2^256 mod p; from_mont: x * 2^-256
+// mod p, the canonical residue (false when x >= p: not a value a Scalar can hold).
+void mont_one(int field, uint64_t one[4]);
+bool from_mont(int field, const uint64_t x[4], uint64_t out[4]);
+
 // Threads of one packing pass: BP_PACK_THREADS, else every hardware thread; 1 .. 64.
 unsigned pack_threads();
 

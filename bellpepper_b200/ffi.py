@@ -56,6 +56,10 @@ SIGNATURES = {
     "bp_cs_recheck_scalars_async": (ctypes.c_int, [vp, vp, vp, vp]),
     "bp_pack_scalars": (ctypes.c_int, [vp, ctypes.c_uint64, vp, vp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "bp_pack_kernel": (ctypes.c_char_p, []),
+    "bp_cs_recheck_scalars_mont": (ctypes.c_int, [vp, vp, vp, i64p]),
+    "bp_cs_recheck_scalars_mont_async": (ctypes.c_int, [vp, vp, vp, vp]),
+    "bp_pack_scalars_mont": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint64, vp, vp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
+    "bp_scalars_from_mont": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint64, vp]),
     "bp_cs_set_witness_program": (ctypes.c_int, [vp, vp, ctypes.c_uint64]),
     "bp_cs_generate_witness_async": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, ctypes.c_uint64]),
     "bp_group_unique_id": (ctypes.c_int, [vp]),

@@ -288,6 +288,49 @@ def opt(L, h, key):
     return v.value
 
 
+def time_mont_leg(L, h, torch, field, w_in, w_aux, n_rows_total, first_bad, time_e2e):
+    """e2e with the witness in the in-memory form of blstrs::Scalar / pasta_curves::{Fp,Fq}: 4 x u64 limbs of x * 2^256 mod p."""
+    import numpy as np
+
+    from bellpepper_b200.fields import MODULUS
+
+    p = MODULUS[field]
+    r_limbs = torch.from_numpy(np.array([((1 << 256) % p >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], np.uint64).view(np.int64))
+
+    def to_mont(w):
+        hi0 = (w[:, 1:] == 0).all(dim=1)
+        is_one = hi0 & (w[:, 0] == 1)
+        other = ~(is_one | (hi0 & (w[:, 0] == 0)))
+        idx = torch.nonzero(other).flatten().tolist()
+        if len(idx) > 20000:
+            raise RuntimeError("not a bit witness: the Montgomery leg converts only a few values in Python")
+        m = torch.zeros_like(w)
+        m[is_one] = r_limbs
+        wn = w.numpy().view(np.uint64)
+        for i in idx:
+            v = sum(int(wn[i, j]) << (64 * j) for j in range(4)) * (1 << 256) % p
+            m[i] = torch.from_numpy(np.array([(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], np.uint64).view(np.int64))
+        return m.pin_memory()
+
+    m_in, m_aux = to_mont(w_in), to_mont(w_aux)
+    row = ctypes.c_int64()
+    pm_in, pm_aux = ctypes.c_void_p(m_in.data_ptr()), ctypes.c_void_p(m_aux.data_ptr())
+
+    def step():
+        rc = L.bp_cs_recheck_scalars_mont(h, pm_in, pm_aux, ctypes.byref(row))
+        if rc != 0:
+            raise RuntimeError(f"bp_cs_recheck_scalars_mont -> {rc}: {L.bp_cs_last_error(h)}")
+        return row.value
+
+    s = time_e2e(step)
+    same = row.value == (-1 if first_bad == SAT else first_bad)
+    up = opt(L, h, "recheck_upload_bytes")
+    return {"value": n_rows_total / s, "ms_per_step": s * 1e3, "h2d_bytes_per_step": (up + 7) // 8, "same_verdict": bool(same),
+            "what": "32-byte scalars in their in-memory Montgomery form (what Vec<blstrs::Scalar> / Vec<pasta_curves::Fq> holds) in pinned "
+                    "host memory -> bp_cs_recheck_scalars_mont: the packing pass matches the limb patterns of 0 and 2^256 mod p, "
+                    "exceptions converted on the host; then as bp_cs_recheck_scalars"}
+
+
 def measure(ctx, name, a, headline):
     """Everything bench.py reports for one workload at this N.  Returns the dict on rank 0 (None elsewhere)."""
     import numpy as np
@@ -418,6 +461,13 @@ def measure(ctx, name, a, headline):
                                    "check" + ("; each rank packs and sends only the chunks its row shard reads, then the exchange" if world > 1 else "")}
             e2e_main = dict(e2e_scalars if sc_s < raw_s else e2e_raw)  # the faster of the two reference-format paths is the headline
             e2e_main["other_reference_format_path"] = e2e_raw if sc_s < raw_s else e2e_scalars
+            # (2b) the same witness as it sits IN MEMORY in the reference's Vec<Scalar>: Montgomery limbs (x * 2^256 mod p), no
+            # to_repr() pass on the caller's side (bp_cs_recheck_scalars_mont); informational, single rank
+            if world == 1:
+                try:
+                    e2e_main["montgomery_in_memory_form"] = time_mont_leg(L, h, torch, field, w_in, w_aux, n_rows_total, first_bad, time_e2e)
+                except Exception as e:  # never lose the line over an informational leg
+                    e2e_main["montgomery_in_memory_form"] = {"skipped": str(e)[:200]}
             # (3) the caller already holds the witness bit-packed
             b_in = (w_in[:, 0] & 1).to(torch.uint8)
             b_aux = (w_aux[:, 0] & 1).to(torch.uint8)
@@ -554,6 +604,7 @@ def measure(ctx, name, a, headline):
                               "inside the timed region",
                     "what": e2e_main["what"],
                     **({"other_reference_format_path": e2e_main["other_reference_format_path"]} if "other_reference_format_path" in e2e_main else {}),
+                    **({"montgomery_in_memory_form": e2e_main["montgomery_in_memory_form"]} if "montgomery_in_memory_form" in e2e_main else {}),
                     **({"prepacked_bits": e2e_bits} if e2e_bits else {}),
                     **({"generated_on_device": e2e_generated} if e2e_generated else {})},
             "gpu_launches": n_launch,

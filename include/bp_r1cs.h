@@ -154,6 +154,20 @@ int bp_pack_scalars(const uint64_t* scalars_le, uint64_t n, uint8_t* bits, uint6
                     uint64_t* n_exc);
 const char* bp_pack_kernel(void);
 
+/* The same two calls for scalars AS THEY SIT IN MEMORY in the reference's Vec<Scalar> (WitnessCS::input_assignment /
+ * aux_assignment, witness_cs.rs:45-57): blstrs::Scalar (blstrs 0.7, Cargo.toml:10) and pasta_curves::{Fp, Fq} keep 4 x u64
+ * little-endian limbs of the MONTGOMERY form x * 2^256 mod p, so the binding can hand over `vec.as_ptr()` without a to_repr()
+ * pass over 10^8 elements: the packing pass looks for the limb patterns of 0 and of 2^256 mod p, and converts the (few) other
+ * elements on the host.  An element >= p is not a Scalar: BP_E_RANGE.  A witness that is not mostly bits is converted on the
+ * host threads (bp_scalars_from_mont) and sent like bp_cs_set_range.  bp_pack_scalars_mont reports its exceptions in
+ * CANONICAL form (ready for bp_cs_set_many). */
+int bp_cs_recheck_scalars_mont(bp_cs* cs, const uint64_t* inputs_mont, const uint64_t* aux_mont, int64_t* row);
+int bp_cs_recheck_scalars_mont_async(bp_cs* cs, const uint64_t* inputs_mont, const uint64_t* aux_mont, int64_t* dev_result);
+int bp_pack_scalars_mont(int field, const uint64_t* scalars_mont, uint64_t n, uint8_t* bits, uint64_t* exc_idx, uint64_t* exc_vals_le,
+                         uint64_t exc_cap, uint64_t* n_exc);
+/* Host only: n Montgomery-form scalars -> canonical little-endian limbs (x * 2^-256 mod p), all host threads. */
+int bp_scalars_from_mont(int field, const uint64_t* scalars_mont, uint64_t n, uint64_t* scalars_le);
+
 /* ---- witness generation on the device (the "witness evaluation" half: SizedWitness::generate_witness_into, witness_cs.rs:7-41)
  * For a bit-logic gadget circuit (boolean / uint32 / sha256: every aux value is a bit that follows from earlier bits) the NEXT
  * witness of an already synthesized circuit need not be produced by re-running the gadgets' host closures

@@ -51,6 +51,10 @@ extern "C" {
     pub fn bp_cs_recheck_scalars_async(cs: *mut bp_cs, inputs_le: *const u64, aux_le: *const u64, dev_result: *mut i64) -> c_int;
     pub fn bp_pack_scalars(scalars_le: *const u64, n: u64, bits: *mut u8, exc_idx: *mut u64, exc_vals_le: *mut u64, exc_cap: u64, n_exc: *mut u64) -> c_int;
     pub fn bp_pack_kernel() -> *const c_char;
+    pub fn bp_cs_recheck_scalars_mont(cs: *mut bp_cs, inputs_mont: *const u64, aux_mont: *const u64, row: *mut i64) -> c_int;
+    pub fn bp_cs_recheck_scalars_mont_async(cs: *mut bp_cs, inputs_mont: *const u64, aux_mont: *const u64, dev_result: *mut i64) -> c_int;
+    pub fn bp_pack_scalars_mont(field: c_int, scalars_mont: *const u64, n: u64, bits: *mut u8, exc_idx: *mut u64, exc_vals_le: *mut u64, exc_cap: u64, n_exc: *mut u64) -> c_int;
+    pub fn bp_scalars_from_mont(field: c_int, scalars_mont: *const u64, n: u64, scalars_le: *mut u64) -> c_int;
     pub fn bp_cs_check_async(cs: *mut bp_cs, dev_result: *mut i64) -> c_int;
     pub fn bp_cs_eval(cs: *mut bp_cs, az: *mut u64, bz: *mut u64, cz: *mut u64) -> c_int;
     pub fn bp_cs_eval_async(cs: *mut bp_cs, dev_az: *mut u64, dev_bz: *mut u64, dev_cz: *mut u64) -> c_int;

@@ -106,3 +106,66 @@ def test_pack_scalars_other_kernels_and_thread_counts(env):
     assert lines[-1] == "ok"
     if env.get("BP_PACK_SIMD") == "0":
         assert lines[0] == "portable"
+
+
+# ---- scalars in their in-memory Montgomery form (blstrs::Scalar / pasta_curves::{Fp,Fq}: x * 2^256 mod p) ---------------------
+def _limbs(x):
+    return [(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+
+
+def _to_int(l):
+    return sum(int(v) << (64 * i) for i, v in enumerate(l))
+
+
+def run_mont_cases(L):
+    from bellpepper_b200.fields import MODULUS
+
+    rng = np.random.default_rng(7)
+    for fid in (0, 1, 2):
+        p = MODULUS[fid]
+        R = (1 << 256) % p
+        for n, n_exc in [(0, 0), (1, 0), (5, 2), (8, 0), (9, 9), (1000, 0), (4099, 50), (262147, 300)]:
+            vals = [int(b) for b in rng.integers(0, 2, size=n)]
+            where = rng.choice(n, size=min(n, n_exc), replace=False) if n else []
+            for k, w in enumerate(where):
+                # values around the traps: 2, p - 1, the integer whose CANONICAL form has the limbs of R (a bit only as Montgomery),
+                # the integer 1/R (its Montgomery form is the canonical 1), random
+                vals[w] = [2, p - 1, R, pow(R, -1, p), int.from_bytes(rng.bytes(32), "little") % p][k % 5]
+            mont = np.array([_limbs(v * R % p) for v in vals], np.uint64).reshape(n, 4)
+            exc = [i for i, v in enumerate(vals) if v > 1]
+            want_bits = np.packbits(np.array([v if v <= 1 else 0 for v in vals], np.uint8), bitorder="little") if n else np.zeros(0, np.uint8)
+            bits = np.full((n + 7) // 8 + 2, 0xCD, np.uint8)
+            cap = max(1, len(exc))
+            idx = np.zeros(cap, np.uint64)
+            ev = np.zeros((cap, 4), np.uint64)
+            k = ctypes.c_uint64()
+            rc = L.bp_pack_scalars_mont(fid, mont.ctypes.data if n else None, n, bits.ctypes.data, idx.ctypes.data, ev.ctypes.data, cap, ctypes.byref(k))
+            assert rc == 0 and k.value == len(exc), (fid, n, rc, k.value, len(exc))
+            assert (bits[: (n + 7) // 8] == want_bits).all() and (bits[(n + 7) // 8:] == 0xCD).all()
+            assert [int(i) for i in idx[: len(exc)]] == exc
+            assert [_to_int(ev[j]) for j in range(len(exc))] == [vals[i] for i in exc]  # canonical again
+            # the whole array back to canonical form
+            canon = np.zeros((max(n, 1), 4), np.uint64)
+            assert L.bp_scalars_from_mont(fid, mont.ctypes.data if n else None, n, canon.ctypes.data) == 0
+            assert [_to_int(canon[i]) for i in range(n)] == vals
+        # a limb pattern >= p is not a scalar
+        bad = np.array([_limbs(1 * R % p), _limbs(p), _limbs(0)], np.uint64)
+        bits = np.zeros(1, np.uint8)
+        idx, ev, k = np.zeros(4, np.uint64), np.zeros((4, 4), np.uint64), ctypes.c_uint64()
+        assert L.bp_pack_scalars_mont(fid, bad.ctypes.data, 3, bits.ctypes.data, idx.ctypes.data, ev.ctypes.data, 4, ctypes.byref(k)) == ffi.BP_E_RANGE
+        assert L.bp_scalars_from_mont(fid, bad.ctypes.data, 3, np.zeros((3, 4), np.uint64).ctypes.data) == ffi.BP_E_RANGE
+    assert L.bp_pack_scalars_mont(3, bad.ctypes.data, 3, bits.ctypes.data, idx.ctypes.data, ev.ctypes.data, 4, ctypes.byref(k)) == ffi.BP_E_ARG
+    assert L.bp_pack_scalars_mont(-1, bad.ctypes.data, 3, bits.ctypes.data, idx.ctypes.data, ev.ctypes.data, 4, ctypes.byref(k)) == ffi.BP_E_ARG
+
+
+def test_pack_scalars_mont_matches_python_ints():
+    run_mont_cases(ffi.load())
+
+
+def test_pack_scalars_mont_portable_kernel():
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from bellpepper_b200 import ffi\nimport test_pack_cpu as t\nL = ffi.load()\n"
+            "assert L.bp_pack_kernel() == b'portable'\nt.run_mont_cases(L)\nprint('ok')\n") % (ROOT, os.path.join(ROOT, "tests"))
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "BP_PACK_SIMD": "0", "BP_PACK_THREADS": "3"}, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.split()[-1] == "ok", out.stderr[-2000:]
