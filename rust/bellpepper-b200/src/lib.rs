@@ -243,6 +243,25 @@ impl<Scalar: B200Field> B200ConstraintSystem<Scalar> {
         if row < 0 { None } else { Some(&self.constraint_paths[row as usize]) }
     }
 
+    /// `recheck` without touching the values on the Rust side: the two slices are handed over as they sit in memory.
+    /// `blstrs::Scalar` and `pasta_curves::{Fp, Fq}` are `[u64; 4]` Montgomery limbs (x * 2^256 mod p, little-endian); the
+    /// library's packing pass matches the limb patterns of 0 and 1 in that form and converts the few other elements itself
+    /// (include/bp_r1cs.h: bp_cs_recheck_scalars_mont), so no `to_repr()` pass over the witness is needed.  A scalar type
+    /// with another in-memory layout must use `recheck`.
+    pub fn recheck_in_memory(&mut self, inputs: &[Scalar], aux: &[Scalar]) -> Option<&str> {
+        assert_eq!(std::mem::size_of::<Scalar>(), 32, "Scalar is not four 64-bit Montgomery limbs");
+        assert_eq!(std::mem::align_of::<Scalar>() % 8, 0);
+        self.flush();
+        assert_eq!(inputs.len(), self.input_names.len());
+        assert_eq!(aux.len(), self.aux_names.len());
+        let mut row = 0i64;
+        let rc = unsafe {
+            ffi::bp_cs_recheck_scalars_mont(self.h, inputs.as_ptr() as *const u64, aux.as_ptr() as *const u64, &mut row)
+        };
+        self.check(rc);
+        if row < 0 { None } else { Some(&self.constraint_paths[row as usize]) }
+    }
+
     pub fn num_constraints(&self) -> usize { self.constraint_paths.len() }
     pub fn num_inputs(&self) -> usize { self.input_names.len() }
 
