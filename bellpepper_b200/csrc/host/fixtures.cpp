@@ -71,6 +71,21 @@ template <class CS> void alloc_message_bits(CS& cs, const uint8_t* msg, uint64_t
         }
 }
 
+// The reference's boolean tests build each operand with `dyn_construct` (boolean.rs:1120-1148): a constant, or a bit allocated
+// in the operand's own namespace, possibly negated.
+template <class CS> Boolean boolean_operand(CS& cs, int kind, const char* name) {
+    auto ns = cs.ns([&] { return std::string(name); });
+    switch (kind) {
+        case 0: return Boolean::constant(true);
+        case 1: return Boolean::constant(false);
+        case 2: return Boolean::from(AllocatedBit::alloc(ns, (OptBool)1));
+        case 3: return Boolean::from(AllocatedBit::alloc(ns, (OptBool)0));
+        case 4: return Boolean::from(AllocatedBit::alloc(ns, (OptBool)1)).not_();
+        case 5: return Boolean::from(AllocatedBit::alloc(ns, (OptBool)0)).not_();
+    }
+    throw std::out_of_range("operand kind");
+}
+
 void bits_to_bytes_be(const std::vector<Boolean>& bits, uint8_t* out) {
     for (size_t i = 0; i < bits.size() / 8; ++i) {
         uint8_t b = 0;
@@ -371,6 +386,41 @@ int bp_tcs_num_unpack(bp_tcs* t, const uint64_t value[4], int strict, uint8_t* b
             if (!cs.field()->is_canonical(v)) throw std::out_of_range("value >= p");
             const AllocatedNum n = AllocatedNum::alloc(cs, [&] { return v; });
             const std::vector<Boolean> bits = strict ? n.to_bits_le_strict(cs) : n.to_bits_le(cs);
+            if (bits_out)
+                for (size_t i = 0; i < bits.size(); ++i) bits_out[i] = (uint8_t)bits[i].get_value();
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
+int bp_tcs_boolean_op(bp_tcs* t, int op, int kind_a, int kind_b, int kind_c, int* result_kind, int* result_value) {
+    if (!t || op < 0 || op > 5) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            const Boolean a = boolean_operand(cs, kind_a, "a"), b = boolean_operand(cs, kind_b, "b");
+            Boolean r = Boolean::constant(false);
+            switch (op) {
+                case 0: r = Boolean::xor_(cs, a, b); break;
+                case 1: r = Boolean::and_(cs, a, b); break;
+                case 2: r = Boolean::or_(cs, a, b); break;
+                case 3: r = Boolean::sha256_ch(cs, a, b, boolean_operand(cs, kind_c, "c")); break;
+                case 4: r = Boolean::sha256_maj(cs, a, b, boolean_operand(cs, kind_c, "c")); break;
+                case 5: Boolean::enforce_equal(cs, a, b); break;
+            }
+            if (result_kind) *result_kind = r.kind == Boolean::Is ? 0 : r.kind == Boolean::Not ? 1 : 2;
+            if (result_value) *result_value = (int)r.get_value();
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
+int bp_tcs_u64_bits(bp_tcs* t, uint64_t value, uint8_t bits_out[64]) {
+    if (!t) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            const std::vector<Boolean> bits = u64_into_boolean_vec_le(cs, &value);
             if (bits_out)
                 for (size_t i = 0; i < bits.size(); ++i) bits_out[i] = (uint8_t)bits[i].get_value();
         };

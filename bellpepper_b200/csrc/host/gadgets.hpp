@@ -184,6 +184,36 @@ struct Boolean {  // boolean.rs:368-376
         return from(AllocatedBit::and_(cs, a.bit, b.bit));
     }
 
+    // boolean.rs:519-533: a or b = not(and(not a, not b)), in the namespace "not and (not a) (not b)"
+    template <class CS> static Boolean or_(CS&& cs, const Boolean& a, const Boolean& b) {
+        auto ns = cs.ns([] { return std::string("not and (not a) (not b)"); });
+        return and_(ns, a.not_(), b.not_()).not_();
+    }
+
+    // boolean.rs:383-427: one row `0 * 0 = ...` (two constants: nothing, or Unsatisfiable)
+    template <class CS> static void enforce_equal(CS&& cs, const Boolean& a, const Boolean& b) {
+        if (a.kind == Constant && b.kind == Constant) {
+            if (a.c != b.c) throw SynthesisError::unsatisfiable();
+            return;
+        }
+        const Field* f = cs.field();
+        auto zero = [](LinearCombination lc) { return lc; };
+        if ((a.kind == Constant && a.c) || (b.kind == Constant && b.c)) {
+            const Boolean& x = (a.kind == Constant && a.c) ? b : a;
+            cs.enforce([] { return std::string("enforce equal to one"); }, zero, zero,
+                       [&](LinearCombination lc) { return std::move(lc) + one_var() - x.lc(f, one_var(), Fr::one()); });
+            return;
+        }
+        if (a.kind == Constant || b.kind == Constant) {  // a false constant
+            const Boolean& x = a.kind == Constant ? b : a;
+            cs.enforce([] { return std::string("enforce equal to zero"); }, zero, zero,
+                       [&](LinearCombination) { return x.lc(f, one_var(), Fr::one()); });
+            return;
+        }
+        cs.enforce([] { return std::string("enforce equal"); }, zero, zero,
+                   [&](LinearCombination) { return a.lc(f, one_var(), Fr::one()) - b.lc(f, one_var(), Fr::one()); });
+    }
+
     template <class CS> static Boolean sha256_ch(CS&& cs, const Boolean& a, const Boolean& b, const Boolean& c) {  // boolean.rs:536-641
         const OptBool va = a.get_value(), vb = b.get_value(), vc = c.get_value();
         const OptBool chv = (va < 0 || vb < 0 || vc < 0) ? kNone : (OptBool)((va & vb) ^ ((va ^ 1) & vc));
@@ -242,6 +272,24 @@ template <class CS> std::vector<AllocatedBit> field_into_allocated_bits_le(CS&& 
     for (unsigned i = 0; i < kNumBits; ++i) {
         auto ns = cs.ns([&] { return "bit " + std::to_string(i); });
         bits.push_back(AllocatedBit::alloc(ns, value ? (OptBool)Field::bit(*value, i) : kNone));
+    }
+    return bits;
+}
+
+// boolean.rs:306-318
+template <class CS> std::vector<Boolean> field_into_boolean_vec_le(CS&& cs, const Fr* value) {
+    std::vector<Boolean> out;
+    for (const AllocatedBit& b : field_into_allocated_bits_le(cs, value)) out.push_back(Boolean::from(b));
+    return out;
+}
+
+// boolean.rs:274-304: 64 freshly allocated bits "bit i", little-endian, of `value` (nullptr = no assignment)
+template <class CS> std::vector<Boolean> u64_into_boolean_vec_le(CS&& cs, const uint64_t* value) {
+    std::vector<Boolean> bits;
+    bits.reserve(64);
+    for (unsigned i = 0; i < 64; ++i) {
+        auto ns = cs.ns([&] { return "bit " + std::to_string(i); });
+        bits.push_back(Boolean::from(AllocatedBit::alloc(ns, value ? (OptBool)((*value >> i) & 1) : kNone)));
     }
     return bits;
 }

@@ -23,6 +23,8 @@ _SIGS = {
     "bp_tcs_sha256": (ctypes.c_int, [vp, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, u64p]),
     "bp_tcs_sha256_ranges": (ctypes.c_int, [vp, vp, ctypes.c_uint64, u64p, ctypes.c_uint64, vp, u64p, u64p]),
     "bp_tcs_blake2s": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, vp]),
+    "bp_tcs_boolean_op": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "bp_tcs_u64_bits": (ctypes.c_int, [vp, ctypes.c_uint64, vp]),
     "bp_tcs_num_unpack": (ctypes.c_int, [vp, vp, ctypes.c_int, vp]),
     "bp_tcs_num_arith": (ctypes.c_int, [vp, vp, vp]),
     "bp_tcs_num_chain": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp]),
@@ -147,6 +149,23 @@ class Tcs:
     @staticmethod
     def _limbs(value: int) -> np.ndarray:
         return np.frombuffer(int(value).to_bytes(32, "little"), dtype="<u8").copy()
+
+    BOOLEAN_OPS = {"xor": 0, "and": 1, "or": 2, "sha256_ch": 3, "sha256_maj": 4, "enforce_equal": 5}
+    OPERAND_KINDS = ["True", "False", "AllocatedTrue", "AllocatedFalse", "NegatedAllocatedTrue", "NegatedAllocatedFalse"]
+
+    def boolean_op(self, op: str, a: str, b: str, c: str = "True"):
+        """Boolean::xor / and / or / sha256_ch / sha256_maj / enforce_equal over operands built like the reference tests'
+        dyn_construct (boolean.rs:1109-2003); returns (result kind: 'Is' / 'Not' / 'Constant', result value)."""
+        k, v = ctypes.c_int(), ctypes.c_int()
+        kinds = [self.OPERAND_KINDS.index(x) for x in (a, b, c)]
+        self._ck(self.L.bp_tcs_boolean_op(self.t, self.BOOLEAN_OPS[op], *kinds, ctypes.byref(k), ctypes.byref(v)))
+        return ["Is", "Not", "Constant"][k.value], bool(v.value)
+
+    def u64_bits(self, value: int):
+        """u64_into_boolean_vec_le (boolean.rs:274-304); returns the 64 bit values, little-endian."""
+        bits = np.zeros(64, np.uint8)
+        self._ck(self.L.bp_tcs_u64_bits(self.t, value, bits.ctypes.data))
+        return bits
 
     def num_unpack(self, value: int, strict: bool = False):
         """AllocatedNum::alloc + to_bits_le[_strict] (num.rs:128-274); returns the 255 bits, little-endian."""

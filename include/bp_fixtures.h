@@ -66,6 +66,16 @@ int bp_tcs_num_unpack(bp_tcs* t, const uint64_t value[4], int strict, uint8_t* b
 int bp_tcs_num_arith(bp_tcs* t, const uint64_t a[4], const uint64_t b[4]);
 int bp_tcs_num_chain(bp_tcs* t, uint64_t n_steps, uint64_t unpack_every, const uint64_t x0[4], const uint64_t y0[4]);
 
+/* Boolean gadgets the way the reference's tests drive them (boolean.rs:1109-2003): operands "a", "b" (and "c" for op 3, 4), each
+ * built in its own namespace like the tests' dyn_construct -- kind 0 = Constant(true), 1 = Constant(false), 2 / 3 = an allocated
+ * true / false bit ("a/boolean"), 4 / 5 = the same, negated -- then op 0 = Boolean::xor (boolean.rs:472-491), 1 = and (:494-516),
+ * 2 = or (:519-533), 3 = sha256_ch (:536-641), 4 = sha256_maj (:644-759), 5 = enforce_equal (:383-427; two unequal constants:
+ * BP_E_STATE, "unsatisfiable constraint system").  *result_kind = 0 Is / 1 Not / 2 Constant, *result_value = its value
+ * (both nullable; op 5 reports Constant(false)).
+ * bp_tcs_u64_bits: u64_into_boolean_vec_le (boolean.rs:274-304) at the root: "bit i/boolean". */
+int bp_tcs_boolean_op(bp_tcs* t, int op, int kind_a, int kind_b, int kind_c, int* result_kind, int* result_value);
+int bp_tcs_u64_bits(bp_tcs* t, uint64_t value, uint8_t bits_out[64]);
+
 /* blake2s() gadget over `len` message bytes, each bit allocated as "input bit <byte> <bit>" least significant first,
  * with an 8-byte personalization (crates/bellpepper/src/gadgets/blake2s.rs:344-406, tests :498-555).  digest = the 32
  * output bytes (the gadget's output bits are little-endian per byte). */

@@ -138,6 +138,23 @@ def boolean_negation(new_cs):  # boolean.rs:1028-1070
     assert b.kind == G.CONST and b.c is True
 
 
+def binop_result(op, first, second):
+    """Both operands allocated: (path of the variable the operation allocates, path of its constraint, the variable's value).
+    xor works on the bits under the negations; and picks and / and not / nor by the operands' polarity; or = not(and(not a,
+    not b)) inside the namespace "not and (not a) (not b)" (boolean.rs:472-533; the tables at :1154-1771)."""
+    na, nb = first.startswith("Negated"), second.startswith("Negated")
+    ba, bb = first.endswith("AllocatedTrue"), second.endswith("AllocatedTrue")
+    if op == "xor":
+        return "xor result", "xor constraint", int(ba ^ bb)
+    if op == "and":
+        name = "nor" if na and nb else ("and not" if na or nb else "and")
+        return f"{name} result", f"{name} constraint", int(val(first) & val(second))
+    assert op == "or"
+    name = "and" if na and nb else ("and not" if na or nb else "nor")
+    ns = "not and (not a) (not b)"
+    return f"{ns}/{name} result", f"{ns}/{name} constraint", int(not (val(first) | val(second)))
+
+
 def boolean_binops(new_cs, verdict):
     """Boolean::xor / and / or over every pair of operand kinds (boolean.rs:1109-1774).  The reference spells out a 36-row table
     per operation; the rows follow one rule each, stated here, and the named result variable is checked where one exists."""
@@ -145,8 +162,6 @@ def boolean_binops(new_cs, verdict):
         for second in VARIANTS:
             ca, cb = is_constant(first), is_constant(second)
             na, nb = first.startswith("Negated"), second.startswith("Negated")
-            # the allocated bits' own values (before negation)
-            ba, bb = first.endswith("AllocatedTrue"), second.endswith("AllocatedTrue")
 
             # xor (table 1154-1313): constants fold; a true constant negates the other; Is^Not -> Not(xor); value = bits' xor
             cs = new_cs()
@@ -161,8 +176,9 @@ def boolean_binops(new_cs, verdict):
                 assert c.kind == (G.NOT if other_neg ^ const_true else G.IS)
             else:
                 assert c.kind == (G.NOT if na ^ nb else G.IS)
-                assert cs.get("xor result") == int(ba ^ bb) and c.bit.value == (ba ^ bb)
-                flip(cs, verdict, "xor result", "xor constraint")
+                var, con, v = binop_result("xor", first, second)
+                assert cs.get(var) == v and c.bit.value == bool(v)
+                flip(cs, verdict, var, con)
 
             # and (table 1366-1545): false folds to Constant(false); true returns the other; Is&Is -> and, Is&Not -> and not,
             # Not&Not -> nor; the result is always Is
@@ -178,9 +194,9 @@ def boolean_binops(new_cs, verdict):
             elif ca or cb:
                 assert c.kind == (G.NOT if (nb if ca else na) else G.IS)
             else:
-                name = "nor" if na and nb else ("and not" if na or nb else "and")
-                assert c.kind == G.IS and cs.get(f"{name} result") == int(val(first) & val(second))
-                flip(cs, verdict, f"{name} result", f"{name} constraint")
+                var, con, v = binop_result("and", first, second)
+                assert c.kind == G.IS and cs.get(var) == v
+                flip(cs, verdict, var, con)
 
             # or = not(and(not a, not b)) in the namespace "not and (not a) (not b)" (table 1596-1771)
             cs = new_cs()
@@ -196,10 +212,9 @@ def boolean_binops(new_cs, verdict):
                 assert c.kind == (G.NOT if (nb if ca else na) else G.IS)
             else:
                 # not a / not b are Is where the operand was negated: Is&Is -> and, mixed -> and not, Not&Not -> nor
-                name = "and" if na and nb else ("and not" if na or nb else "nor")
-                assert c.kind == G.NOT
-                assert cs.get(f"not and (not a) (not b)/{name} result") == int(not (val(first) | val(second)))
-                flip(cs, verdict, f"not and (not a) (not b)/{name} result", f"not and (not a) (not b)/{name} constraint")
+                var, con, v = binop_result("or", first, second)
+                assert c.kind == G.NOT and cs.get(var) == v
+                flip(cs, verdict, var, con)
 
 
 def boolean_sha256_ch_maj(new_cs, field, verdict):  # boolean.rs:1823-2003

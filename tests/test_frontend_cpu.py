@@ -134,3 +134,64 @@ def test_blake2s_identical_to_oracle_gadgets(fid, n_bytes):  # blake2s.rs:443-45
         same(t.host_csr(), oracle_csr(cs))
         for row in (0, cs.num_constraints() // 2, cs.num_constraints() - 1) if cs.num_constraints() else ():
             assert t.row_path(row) == cs.constraints[row][3]
+
+
+# ---- Boolean xor / and / or / sha256_ch / sha256_maj / enforce_equal over every operand kind (boolean.rs:1109-2003) --------
+def _python_boolean_op(F, op, a_kind, b_kind, c_kind):
+    import kat_scenarios as S
+
+    cs = TestConstraintSystem(F)
+    a, b = S.construct(cs, a_kind, "a"), S.construct(cs, b_kind, "b")
+    if op == "xor":
+        r = G.Boolean.xor(cs, a, b)
+    elif op == "and":
+        r = G.Boolean.and_(cs, a, b)
+    elif op == "or":
+        r = S.boolean_or(cs, a, b)
+    elif op == "enforce_equal":
+        G.Boolean.enforce_equal(cs, F, a, b)
+        r = G.Boolean.constant(False)
+    else:
+        c = S.construct(cs, c_kind, "c")
+        r = (G.Boolean.sha256_ch if op == "sha256_ch" else G.Boolean.sha256_maj)(cs, F, a, b, c)
+    return cs, ["Is", "Not", "Constant"][r.kind], bool(r.get_value())
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+def test_boolean_ops_identical_to_oracle_gadgets_over_all_operand_kinds(fid):
+    from oracle.r1cs_py import Unsatisfiable
+
+    F = FIELDS[fid]
+    kinds = fixtures.Tcs.OPERAND_KINDS
+    n = 0
+    for op in ("xor", "and", "or", "enforce_equal", "sha256_ch", "sha256_maj"):
+        for a in kinds:
+            for b in kinds:
+                for c in (kinds if op.startswith("sha256") else ["True"]):
+                    try:
+                        cs, want_kind, want_value = _python_boolean_op(F, op, a, b, c)
+                    except Unsatisfiable:
+                        with fixtures.Tcs(fid, device=-1, named=True) as t:
+                            with pytest.raises(RuntimeError, match="unsatisfiable"):
+                                t.boolean_op(op, a, b, c)
+                        continue
+                    with fixtures.Tcs(fid, device=-1, named=True) as t:
+                        kind, value = t.boolean_op(op, a, b, c)
+                        assert (kind, value) == (want_kind, want_value), (op, a, b, c)
+                        assert t.num_constraints() == cs.num_constraints()
+                        same(t.host_csr(), oracle_csr(cs))
+                        for row in range(cs.num_constraints()):  # the reference's paths, row for row
+                            assert t.row_path(row) == cs.constraints[row][3]
+                    n += 1
+    assert n == 3 * 36 + (36 - 2) + 2 * 216  # (enforce_equal of True with False, either way round, is the error case)
+
+
+def test_u64_into_boolean_vec_le():  # boolean.rs:1776-1794
+    with fixtures.Tcs(0, device=-1, named=True) as t:
+        bits = t.u64_bits(17234652694787248421)
+        assert t.num_constraints() == 64 and t.num_aux() == 64
+        assert t.row_path(5) == "bit 5/boolean constraint"
+        lens, cols, coeffs, inputs, aux = t.host_csr()
+    assert [int(bits[63 - i]) for i in (0, 1, 2, 3, 4, 5, 20, 21, 22)] == [1, 1, 1, 0, 1, 1, 1, 0, 0]
+    assert sum(int(b) << i for i, b in enumerate(bits)) == 17234652694787248421
+    assert c_api.Instance(0, lens, cols, coeffs, inputs, aux).check(1, True) == -1

@@ -63,3 +63,61 @@ def test_uint32_ops_on_device(fid):
     S.uint32_sha256_maj_ch(new_cs, F, verdict, 6)
     S.uint32_addmany(new_cs, F, verdict, 8)  # the flipped result bit breaks a MultiEq row (full-width coefficients 2^k)
     assert stats["device_checks"] == 6 + 12 + 24
+
+
+# ---- the same boolean tests through the C++ front-end (csrc/host/gadgets.hpp) streaming into a device handle ----------------
+def new_tcs():
+    from bellpepper_b200 import fixtures
+
+    return fixtures.Tcs(0, device=0, named=True)
+
+
+@pytest.mark.parametrize("op", ["xor", "and", "or", "sha256_ch", "sha256_maj"])
+def test_cpp_front_end_boolean_ops_on_device(op):
+    """boolean.rs:1109-2003 with the reference's own flow: build, is_satisfied, get the result variable, set it wrong,
+    which_is_unsatisfied names the gadget's constraint -- gadgets, paths and verdicts all on the product side."""
+    three = op.startswith("sha256")
+    n_flips = 0
+    for a in S.VARIANTS:
+        for b in S.VARIANTS:
+            for c in (S.VARIANTS if three else ["True"]):
+                va, vb, vc = S.val(a), S.val(b), S.val(c)
+                expected = {"xor": va ^ vb, "and": va & vb, "or": va | vb, "sha256_ch": (va & vb) ^ ((not va) & vc),
+                            "sha256_maj": (va & vb) ^ (va & vc) ^ (vb & vc)}[op]
+                consts = [S.is_constant(x) for x in ((a, b, c) if three else (a, b))]
+                with new_tcs() as t:
+                    kind, value = t.boolean_op(op, a, b, c)
+                    assert t.is_satisfied()
+                    assert value == bool(expected), (op, a, b, c)
+                    if all(consts):
+                        assert t.num_constraints() == 0 and kind == "Constant"
+                    if not any(consts):
+                        if three:
+                            var, con, v = op[7:], op[7:] + " computation", int(expected)
+                        else:
+                            var, con, v = S.binop_result(op, a, b)
+                        assert t.get(var) == v
+                        t.set(var, 1 - v)
+                        assert t.which_is_unsatisfied() == con
+                        t.set(var, v)
+                        assert t.is_satisfied()
+                        n_flips += 1
+    assert n_flips == (64 if three else 16)
+
+
+def test_cpp_front_end_enforce_equal_and_u64_bits_on_device():  # boolean.rs:935-1026, 1776-1794
+    for a in S.VARIANTS:
+        for b in S.VARIANTS:
+            with new_tcs() as t:
+                if S.is_constant(a) and S.is_constant(b) and S.val(a) != S.val(b):
+                    with pytest.raises(RuntimeError, match="unsatisfiable"):
+                        t.boolean_op("enforce_equal", a, b)
+                    continue
+                t.boolean_op("enforce_equal", a, b)
+                assert t.is_satisfied() == (S.val(a) == S.val(b)), (a, b)
+    with new_tcs() as t:
+        bits = t.u64_bits(17234652694787248421)
+        assert t.is_satisfied() and t.num_constraints() == 64
+        assert sum(int(x) << i for i, x in enumerate(bits)) == 17234652694787248421
+        t.set("bit 63/boolean", 2)
+        assert t.which_is_unsatisfied() == "bit 63/boolean constraint"
