@@ -2210,11 +2210,10 @@ static int recheck_scalars_impl(bp_cs* h, const uint64_t* inputs_le, const uint6
             pack_failed = true;
         }
     };
-    {
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
+    try {
+        run_on_threads(nt, work);
+    } catch (...) {
+        return fail(h, BP_E_OOM, "bp_cs_recheck_scalars: out of host memory while packing");
     }
     if (pack_failed) return fail(h, BP_E_OOM, "bp_cs_recheck_scalars: out of host memory while packing");
     size_t n_exc[2] = {0, 0};

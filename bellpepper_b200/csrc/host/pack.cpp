@@ -208,12 +208,7 @@ int pack_all(int field, const uint64_t* scalars, uint64_t n, uint8_t* bits, uint
                 failed = true;
             }
         };
-        {
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-            work(0);
-            for (auto& x : th) x.join();
-        }
+        bp::run_on_threads(nt, work);
         if (failed) return BP_E_OOM;
         uint64_t k = 0;
         bool not_a_scalar = false;
@@ -260,10 +255,7 @@ int bp_scalars_from_mont(int field, const uint64_t* scalars_mont, uint64_t n, ui
             if (!bp::from_mont(field, scalars_mont + 4 * i, scalars_le + 4 * i)) bad = true;
     };
     try {
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
+        bp::run_on_threads(nt, work);
     } catch (...) {
         return BP_E_OOM;
     }

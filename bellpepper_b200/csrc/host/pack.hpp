@@ -5,6 +5,7 @@
 #pragma once
 
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 namespace bp {
@@ -31,6 +32,21 @@ void pack_bit_bytes_mont(const uint64_t* src, uint64_t n, const uint64_t one[4],
 // mod p, the canonical residue (false when x >= p: not a value a Scalar can hold).
 void mont_one(int field, uint64_t one[4]);
 bool from_mont(int field, const uint64_t x[4], uint64_t out[4]);
+
+// work(0 .. nt - 1), each on its own thread (work(0) on the caller's).  A thread that cannot be created is not an error: its
+// share runs on the caller's thread instead.  `work` must not throw.
+template <class W> void run_on_threads(unsigned nt, W&& work) {
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    unsigned started = 1;
+    try {
+        for (; started < nt; ++started) th.emplace_back(work, started);
+    } catch (...) {  // std::system_error: no more threads
+    }
+    work(0u);
+    for (unsigned t = started; t < nt; ++t) work(t);
+    for (auto& x : th) x.join();
+}
 
 // Threads of one packing pass: BP_PACK_THREADS, else every hardware thread; 1 .. 64.
 unsigned pack_threads();
