@@ -36,7 +36,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources()
     if force or _stale(LIB, srcs):
         cmd = ["nvcc", *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "bp_r1cs.cu"),
-               os.path.join(CSRC, "host", "fixtures.cpp"), os.path.join(CSRC, "host", "pack.cpp"), "-ldl"]
+               os.path.join(CSRC, "host", "fixtures.cpp"), os.path.join(CSRC, "host", "pack.cpp"), os.path.join(CSRC, "host", "structure_hash.cpp"), "-ldl"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         if os.environ.get("BP_EXPERIMENTAL_VARIANTS") == "1":

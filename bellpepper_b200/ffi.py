@@ -54,6 +54,7 @@ SIGNATURES = {
     "bp_cs_set_many": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, vp, vp]),
     "bp_cs_recheck_scalars": (ctypes.c_int, [vp, vp, vp, i64p]),
     "bp_cs_recheck_scalars_async": (ctypes.c_int, [vp, vp, vp, vp]),
+    "bp_structure_hash": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp, ctypes.c_char_p]),
     "bp_pack_scalars": (ctypes.c_int, [vp, ctypes.c_uint64, vp, vp, vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "bp_pack_kernel": (ctypes.c_char_p, []),
     "bp_cs_recheck_scalars_mont": (ctypes.c_int, [vp, vp, vp, i64p]),

@@ -103,6 +103,13 @@ int bp_cs_enforce(bp_cs* cs, uint64_t n_rows, const uint32_t* lens, const uint32
 /* num_inputs / num_constraints (test_cs.rs:266, 295) and sizes. */
 int bp_cs_counts(bp_cs* cs, uint64_t* n_inputs, uint64_t* n_aux, uint64_t* n_rows, uint64_t* nnz);
 
+/* TestConstraintSystem::hash (test_cs.rs:64-115, 214-237) from flat rows -- the arrays bp_cs_enforce takes / bp_cs_export
+ * writes: BLAKE2s-256 over (n_inputs, n_aux, n_rows) and, per LC, its terms with same-variable coefficients added and zero
+ * coefficients dropped (proc_lc), inputs before aux, ascending index; coefficients as big-endian to_repr().  HOST ONLY, no
+ * handle.  out_hex receives 64 hex digits + NUL: two front-ends that emit the same matrices get the same string. */
+int bp_structure_hash(int field, uint64_t n_inputs, uint64_t n_aux, uint64_t n_rows, const uint32_t* lens, const uint32_t* cols,
+                      const uint64_t* coeffs_le, char out_hex[65]);
+
 /* ---- the hot path ----------------------------------------------------------------------------------
  * which_is_unsatisfied / is_satisfied (test_cs.rs:239-264): *row = index of the FIRST row with
  * (A.w)(B.w) != C.w, or -1 when every row holds.  The host side maps the row to its path.

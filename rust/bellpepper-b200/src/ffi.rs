@@ -49,6 +49,7 @@ extern "C" {
     pub fn bp_cs_set_many(cs: *mut bp_cs, is_aux: c_int, n: u64, idx: *const u64, vals_le: *const u64) -> c_int;
     pub fn bp_cs_recheck_scalars(cs: *mut bp_cs, inputs_le: *const u64, aux_le: *const u64, row: *mut i64) -> c_int;
     pub fn bp_cs_recheck_scalars_async(cs: *mut bp_cs, inputs_le: *const u64, aux_le: *const u64, dev_result: *mut i64) -> c_int;
+    pub fn bp_structure_hash(field: c_int, n_inputs: u64, n_aux: u64, n_rows: u64, lens: *const u32, cols: *const u32, coeffs_le: *const u64, out_hex: *mut c_char) -> c_int;
     pub fn bp_pack_scalars(scalars_le: *const u64, n: u64, bits: *mut u8, exc_idx: *mut u64, exc_vals_le: *mut u64, exc_cap: u64, n_exc: *mut u64) -> c_int;
     pub fn bp_pack_kernel() -> *const c_char;
     pub fn bp_cs_recheck_scalars_mont(cs: *mut bp_cs, inputs_mont: *const u64, aux_mont: *const u64, row: *mut i64) -> c_int;
