@@ -77,3 +77,18 @@ def test_split_rows_by_nnz_is_host_only_and_balances_terms():
         assert max(per) - min(per) <= 2 * 901, per  # within a fat row of each other
     assert L.bp_split_rows_by_nnz(None, 0, 3, b.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) == 0
     assert L.bp_split_rows_by_nnz(lens.ctypes.data, n, 0, b.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))) == -5
+
+
+def test_fixture_header_binding_and_both_libraries_agree():
+    """include/bp_fixtures.h (the C++ front-end's C entry points) <-> bellpepper_b200/fixtures.py <-> what libbp_r1cs.so and the
+    host-only libbp_frontend.so export."""
+    from bellpepper_b200 import fixtures
+
+    text = open(os.path.join(ROOT, "include", "bp_fixtures.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(bp_[a-z0-9_]+)\s*\(", text)))
+    assert len(syms) >= 25
+    assert set(syms) == set(fixtures._SIGS), set(syms) ^ set(fixtures._SIGS)
+    for lib in (fixtures._lib(), fixtures._host_lib()):
+        for s in syms:
+            assert hasattr(lib, s), s
