@@ -92,3 +92,19 @@ def test_fixture_header_binding_and_both_libraries_agree():
     for lib in (fixtures._lib(), fixtures._host_lib()):
         for s in syms:
             assert hasattr(lib, s), s
+
+
+def test_rust_binding_declares_the_header():
+    """rust/bellpepper-b200/src/ffi.rs (uncompiled here: no Rust toolchain) names exactly the header's entry points, each with
+    the header's number of arguments."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bp_r1cs.h")).read(), flags=re.S)
+    rs = open(os.path.join(ROOT, "rust", "bellpepper-b200", "src", "ffi.rs")).read()
+
+    def arity(args):
+        args = args.strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+
+    c = {m.group(1): arity(m.group(2)) for m in re.finditer(r"\b(bp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)}
+    r = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (bp_[a-z0-9_]+)\s*\(([^)]*)\)", rs)}
+    assert set(c) == set(r), set(c) ^ set(r)
+    assert c == r, {k: (c[k], r[k]) for k in c if c[k] != r[k]}
