@@ -1,11 +1,13 @@
 // C wrappers over the C++ host front-end (see include/bp_fixtures.h).
 #include "../../../include/bp_fixtures.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 
+#include "blake2s_host.hpp"
 #include "gadgets.hpp"
 
 using namespace bph;
@@ -330,6 +332,33 @@ static bool have_shani() { return false; }
 static void sha256_compress_shani(uint32_t*, const uint8_t*) {}
 #endif
 
+// Chaining values of the blake2s gadget's hash (blake2s.rs:344-406: digest length 32, no key, 8-byte personalization) over `len`
+// message bytes: the 8 words of h BEFORE each of the max(1, ceil(len / 64)) compressions -- what bp_cs_generate_witness_async
+// takes per unit of a recorded blake2s circuit.  Plain BLAKE2s on the host.
+int bp_blake2s_chain_states(const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint32_t* states, uint64_t max_blocks,
+                            uint64_t* n_blocks) {
+    if ((!msg && len) || !personalization || !n_blocks) return BP_E_ARG;
+    const uint64_t blocks = len ? (len + 63) / 64 : 1;
+    *n_blocks = blocks;
+    if (!states) return BP_OK;
+    if (max_blocks < blocks) return BP_E_RANGE;
+    auto le32 = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+    uint32_t h[8];
+    for (int i = 0; i < 8; ++i) h[i] = kBlake2sIV[i];
+    h[0] ^= 0x01010000u ^ 32u;
+    h[6] ^= le32(personalization);
+    h[7] ^= le32(personalization + 4);
+    for (uint64_t b = 0; b < blocks; ++b) {
+        std::memcpy(states + 8 * b, h, sizeof h);
+        uint8_t blk[64] = {0};
+        const uint64_t have = len > 64 * b ? std::min<uint64_t>(64, len - 64 * b) : 0;
+        if (have) std::memcpy(blk, msg + 64 * b, have);
+        const bool last = b + 1 == blocks;
+        blake2s_compress(h, blk, last ? len : 64 * (b + 1), last);
+    }
+    return BP_OK;
+}
+
 // Chaining states of sha256 over `len` message bytes: 8 words BEFORE each compression block (block 0: the IV), blocks as the
 // gadget pads them (sha256.rs:50-77).  Plain SHA-256 on the host: what bp_cs_generate_witness_async wants per unit.
 int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, uint64_t max_blocks, uint64_t* n_blocks) {
@@ -508,7 +537,16 @@ int bp_tcs_num_chain(bp_tcs* t, uint64_t n_steps, uint64_t unpack_every, const u
 int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint8_t digest[32]) {
     if (!t || (!msg && len) || !personalization || !digest) return BP_E_ARG;
     return guarded(t, [&] {
+        WitnessTape tape;
         auto run = [&](auto& cs) {
+            struct TapeScope {  // recording is on exactly while this synthesis runs
+                explicit TapeScope(WitnessTape* tp) { g_tape = tp; }
+                ~TapeScope() { g_tape = nullptr; }
+            } tape_scope(t->record_tape ? &tape : nullptr);
+            if (t->record_tape) {
+                tape.aux_base = cs.num_aux();
+                tape.n_msg_bits = 8 * len;
+            }
             std::vector<Boolean> bits;
             bits.reserve(len * 8);
             for (uint64_t i = 0; i < len; ++i)
@@ -530,6 +568,10 @@ int bp_tcs_blake2s(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint8_t pe
         };
         if (t->named) run(*t->named_cs);
         else run(*t->bulk_cs);
+        if (t->record_tape) {  // one unit per compression; message bits least significant first within a byte
+            t->wprog = tape.build_program(t->named ? t->named_cs->num_aux() : t->bulk_cs->num_aux(), /*msb_first=*/false);
+            if (!tape.ok) throw std::runtime_error("witness tape: " + tape.why);
+        }
     });
 }
 

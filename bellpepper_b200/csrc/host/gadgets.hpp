@@ -907,11 +907,24 @@ template <class CS> std::vector<Boolean> blake2s(CS&& cs, const std::vector<Bool
         blocks.push_back(std::move(words));
     }
     if (blocks.empty()) blocks.push_back(std::vector<UInt32>(16, UInt32::constant(0)));
+    // witness tape (wtape.hpp): a compression is a unit -- its 512-bit message window, and which variables carry the chaining
+    // value h (word j, bit i = state bit 32 j + i; a negated Boolean carries the inverted bit)
+    auto note_unit = [&](size_t blk) {
+        if (!g_tape) return;
+        g_tape->begin_unit(512 * (uint64_t)blk);
+        for (uint32_t j = 0; j < 8; ++j)
+            for (uint32_t i = 0; i < 32; ++i) {
+                const Boolean& b = h[j].bits[i];
+                if (!b.is_constant()) g_tape->units.back().state[b.bit.variable.index()] = (32 * j + i) | (b.kind == Boolean::Not ? 0x80000000u : 0u);
+            }
+    };
     for (size_t i = 0; i + 1 < blocks.size(); ++i) {
+        note_unit(i);
         auto ns = cs.ns([i] { return "block " + std::to_string(i); });
         blake2s_compression(ns, h, blocks[i], (uint64_t)(i + 1) * 64, false);
     }
     {
+        note_unit(blocks.size() - 1);
         auto ns = cs.ns([] { return std::string("final block"); });
         blake2s_compression(ns, h, blocks.back(), input.size() / 8, true);
     }

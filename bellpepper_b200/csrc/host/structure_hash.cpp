@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../../include/bp_r1cs.h"
+#include "blake2s_host.hpp"
 #include "fr.hpp"
 
 namespace {
@@ -18,53 +19,11 @@ struct Blake2s {
     uint8_t buf[64];
     size_t fill = 0;
 
-    static constexpr uint32_t IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
-
     Blake2s() {
-        for (int i = 0; i < 8; ++i) h[i] = IV[i];
+        for (int i = 0; i < 8; ++i) h[i] = bph::kBlake2sIV[i];
         h[0] ^= 0x01010020u;  // digest length 32, no key, fanout 1, depth 1
     }
-    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
-    void compress(const uint8_t* block, bool last) {
-        static const uint8_t S[10][16] = {
-            {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
-            {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
-            {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
-            {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
-            {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
-        uint32_t m[16], v[16];
-        for (int i = 0; i < 16; ++i)
-            m[i] = (uint32_t)block[4 * i] | (uint32_t)block[4 * i + 1] << 8 | (uint32_t)block[4 * i + 2] << 16 | (uint32_t)block[4 * i + 3] << 24;
-        for (int i = 0; i < 8; ++i) {
-            v[i] = h[i];
-            v[8 + i] = IV[i];
-        }
-        v[12] ^= (uint32_t)t;
-        v[13] ^= (uint32_t)(t >> 32);
-        if (last) v[14] = ~v[14];
-        auto G = [&](int a, int b, int c, int d, uint32_t x, uint32_t y) {
-            v[a] = v[a] + v[b] + x;
-            v[d] = rotr(v[d] ^ v[a], 16);
-            v[c] = v[c] + v[d];
-            v[b] = rotr(v[b] ^ v[c], 12);
-            v[a] = v[a] + v[b] + y;
-            v[d] = rotr(v[d] ^ v[a], 8);
-            v[c] = v[c] + v[d];
-            v[b] = rotr(v[b] ^ v[c], 7);
-        };
-        for (int r = 0; r < 10; ++r) {
-            const uint8_t* s = S[r];
-            G(0, 4, 8, 12, m[s[0]], m[s[1]]);
-            G(1, 5, 9, 13, m[s[2]], m[s[3]]);
-            G(2, 6, 10, 14, m[s[4]], m[s[5]]);
-            G(3, 7, 11, 15, m[s[6]], m[s[7]]);
-            G(0, 5, 10, 15, m[s[8]], m[s[9]]);
-            G(1, 6, 11, 12, m[s[10]], m[s[11]]);
-            G(2, 7, 8, 13, m[s[12]], m[s[13]]);
-            G(3, 4, 9, 14, m[s[14]], m[s[15]]);
-        }
-        for (int i = 0; i < 8; ++i) h[i] ^= v[i] ^ v[8 + i];
-    }
+    void compress(const uint8_t* block, bool last) { bph::blake2s_compress(h, block, t, last); }
     void update(const uint8_t* p, size_t n) {
         while (n) {
             if (fill == 64) {  // (a full buffer is only compressed when more input follows: the last block is special)
@@ -87,7 +46,6 @@ struct Blake2s {
             for (int j = 0; j < 4; ++j) out[4 * i + j] = (uint8_t)(h[i] >> (8 * j));
     }
 };
-constexpr uint32_t Blake2s::IV[8];
 
 void be64(uint8_t* p, uint64_t v) {
     for (int i = 0; i < 8; ++i) p[i] = (uint8_t)(v >> (56 - 8 * i));

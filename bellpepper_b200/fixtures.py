@@ -31,6 +31,7 @@ _SIGS = {
     "bp_tcs_record_witness_program": (ctypes.c_int, [vp, ctypes.c_int]),
     "bp_tcs_witness_program": (ctypes.c_int, [vp, ctypes.POINTER(vp), u64p]),
     "bp_sha256_chain_states": (ctypes.c_int, [vp, ctypes.c_uint64, vp, ctypes.c_uint64, u64p]),
+    "bp_blake2s_chain_states": (ctypes.c_int, [vp, ctypes.c_uint64, vp, vp, ctypes.c_uint64, u64p]),
     "bp_wcs_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "bp_tcs_which_is_unsatisfied": (ctypes.c_int64, [vp, vp, ctypes.c_uint64]),
     "bp_tcs_set": (ctypes.c_int, [vp, ctypes.c_char_p, vp]),
@@ -315,4 +316,15 @@ def sha256_chain_states(msg: bytes) -> np.ndarray:
     assert L.bp_sha256_chain_states(msg, len(msg), None, 0, ctypes.byref(n)) == 0
     out = np.zeros((n.value, 8), np.uint32)
     assert L.bp_sha256_chain_states(msg, len(msg), out.ctypes.data, n.value, ctypes.byref(n)) == 0
+    return out
+
+
+def blake2s_chain_states(msg: bytes, personalization: bytes = b"12345678") -> np.ndarray:
+    """uint32[blocks, 8]: the BLAKE2s chaining value before each compression of the gadget's hash (plain BLAKE2s on the host)."""
+    assert len(personalization) == 8
+    L = _host_lib()
+    n = ctypes.c_uint64()
+    assert L.bp_blake2s_chain_states(msg, len(msg), personalization, None, 0, ctypes.byref(n)) == 0
+    out = np.zeros((n.value, 8), np.uint32)
+    assert L.bp_blake2s_chain_states(msg, len(msg), personalization, out.ctypes.data, n.value, ctypes.byref(n)) == 0
     return out

@@ -45,7 +45,7 @@ int bp_tcs_sha256(bp_tcs* t, const uint8_t* msg, uint64_t len, uint64_t block_be
 int bp_tcs_sha256_ranges(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint64_t* ranges, uint64_t n_ranges, uint8_t digest[32],
                          uint64_t* global_before, uint64_t* local_before);
 
-/* Witness program (include/bp_r1cs.h: bp_cs_set_witness_program).  With recording on, the next bp_tcs_sha256[_ranges] also
+/* Witness program (include/bp_r1cs.h: bp_cs_set_witness_program).  With recording on, the next bp_tcs_sha256[_ranges] / bp_tcs_blake2s also
  * records how every aux variable of the circuit follows from the message bits (csrc/host/wtape.hpp) and builds the device
  * program, one unit per compression block; bp_tcs_witness_program lends it out (valid until the next synthesis on `t`).
  * bp_sha256_chain_states: the 8-word hash state BEFORE each of the (len + 9 + 63) / 64 blocks, block 0 = the IV -- the
@@ -53,6 +53,10 @@ int bp_tcs_sha256_ranges(bp_tcs* t, const uint8_t* msg, uint64_t len, const uint
 int bp_tcs_record_witness_program(bp_tcs* t, int on);
 int bp_tcs_witness_program(bp_tcs* t, const uint32_t** words, uint64_t* n_words);
 int bp_sha256_chain_states(const uint8_t* msg, uint64_t len, uint32_t* states, uint64_t max_blocks, uint64_t* n_blocks);
+/* The same for the blake2s gadget (bp_tcs_blake2s with recording on: one unit per compression, message bits least significant
+ * first): the 8 words of the BLAKE2s chaining value h before each of the max(1, ceil(len / 64)) compressions. */
+int bp_blake2s_chain_states(const uint8_t* msg, uint64_t len, const uint8_t personalization[8], uint32_t* states, uint64_t max_blocks,
+                            uint64_t* n_blocks);
 
 /* num gadgets (crates/bellpepper-core/src/gadgets/num.rs), driven the way the reference's tests drive them:
  *  bp_tcs_num_unpack: AllocatedNum::alloc ("num") then to_bits_le (num.rs:263-274) or to_bits_le_strict (:128-247) at the

@@ -191,7 +191,7 @@ int bp_scalars_from_mont(int field, const uint64_t* scalars_mont, uint64_t n, ui
  *
  * bp_cs_generate_witness_async: msg = the message bytes (msg_len * 8 must equal the program's n_msg_bits), states = 8 words of
  * chaining state per unit (for a sha256 chain: the hash state BEFORE each block; bp_sha256_chain_states computes them on the
- * host in microseconds).  Writes every aux value (inputs are untouched); follow with bp_cs_first_unsatisfied / check_async.
+ * host in microseconds; for a blake2s circuit: the BLAKE2s chaining value before each compression, bp_blake2s_chain_states).  Writes every aux value (inputs are untouched); follow with bp_cs_first_unsatisfied / check_async.
  * 64 bytes of H2D per block instead of 26 000 witness values. */
 int bp_cs_set_witness_program(bp_cs* cs, const uint32_t* words, uint64_t n_words);
 int bp_cs_generate_witness_async(bp_cs* cs, const uint8_t* msg, uint64_t msg_len, const uint32_t* states, uint64_t n_state_words);

@@ -4,6 +4,7 @@ for bit -- for the recorded message and for ANY other message of the same length
 import hashlib
 
 import numpy as np
+import pytest
 
 from bellpepper_b200 import fixtures
 
@@ -172,3 +173,59 @@ def test_generic_blocks_share_one_tape():
     tapes = [int(prog[unit_off + 4 * u]) for u in range(n_units)]
     assert n_units == blocks and n_tapes == 3
     assert tapes[0] != tapes[1] and len(set(tapes[1:-1])) == 1 and tapes[-1] != tapes[1]
+
+
+# ---- blake2s (configs[2]): one unit per compression, message bits least significant first ------------------------------------
+def test_blake2s_chain_states_match_hashlib():
+    """The state after the last compression is the digest; intermediate states by re-hashing the prefix is not possible with
+    hashlib (the last block is flagged), so: the final value from the last state + the documented compression via the
+    gadget itself in test_blake2s_program_reproduces_the_witness, and here the shape, the parameter block and determinism."""
+    for n in (0, 1, 63, 64, 65, 128, 1000):
+        msg = fixtures.xorshift_bytes(n)
+        st = fixtures.blake2s_chain_states(msg)
+        assert st.shape == (max(1, (n + 63) // 64), 8)
+        iv = [0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF53A, 0x510E527F, 0x9B05688C, 0x1F83D9AB, 0x5BE0CD19]
+        want0 = list(iv)
+        want0[0] ^= 0x01010020
+        want0[6] ^= int.from_bytes(b"1234", "little")
+        want0[7] ^= int.from_bytes(b"5678", "little")
+        assert list(st[0]) == want0
+    # a message of whole blocks hashed without the final flag chains exactly like the unflagged prefix of a longer one
+    a = fixtures.blake2s_chain_states(fixtures.xorshift_bytes(64 * 3 + 5))
+    b = fixtures.blake2s_chain_states(fixtures.xorshift_bytes(64 * 5))
+    assert (a[:4] == b[:4]).all()  # states before blocks 0..3 depend on the first three whole blocks only
+
+
+@pytest.mark.parametrize("fid,n_bytes", [(2, 64), (2, 200), (0, 130), (1, 64 * 4)])
+def test_blake2s_program_reproduces_the_witness(fid, n_bytes):
+    msg = fixtures.xorshift_bytes(n_bytes)
+    with fixtures.Tcs(fid, device=-1, named=False) as t:
+        t.record_witness_program()
+        digest = t.blake2s(msg)
+        prog = t.witness_program()
+        lens, cols, coeffs, inputs, aux = t.host_csr()
+    assert digest == hashlib.blake2s(msg, digest_size=32, person=b"12345678").digest()
+    n_blocks = max(1, (n_bytes + 63) // 64)
+    assert int(prog[2]) == n_blocks and int(prog[6]) == 0 and int(prog[5]) == 8 * n_bytes and int(prog[7]) == aux.shape[0]
+    want = aux[:, 0].astype(np.uint8)
+    assert not aux[:, 1:].any() and want.max() <= 1
+    got = replay(prog, msg, fixtures.blake2s_chain_states(msg))
+    assert (got == want).all()
+    # recording does not change the circuit
+    with fixtures.Tcs(fid, device=-1, named=False) as t:
+        t.blake2s(msg)
+        plain = t.host_csr()
+    for x, y in zip(plain, (lens, cols, coeffs, inputs, aux)):
+        assert x.shape == y.shape and (x == y).all()
+    # ANOTHER message of the same length through the same program == a fresh synthesis of that message
+    msg2 = bytes((b * 11 + 5) & 0xFF for b in msg)
+    with fixtures.Tcs(fid, device=-1, named=False) as t:
+        t.blake2s(msg2)
+        aux2 = t.host_csr()[4]
+    got2 = replay(prog, msg2, fixtures.blake2s_chain_states(msg2))
+    assert (got2 == aux2[:, 0].astype(np.uint8)).all()
+    # a wrong chaining value gives a different witness (the states are really read)
+    if n_blocks > 1:
+        st = fixtures.blake2s_chain_states(msg).copy()
+        st[1][2] ^= 1 << 7
+        assert (replay(prog, msg, st) != want).any()
