@@ -266,12 +266,16 @@ def witness_cs_selftest(field: int, device: int = 0) -> int:
     return int(_lib().bp_wcs_selftest(field, device))
 
 
-def blake2s_into_new_handle(field: int, device: int, n_bytes: int):
+def blake2s_into_new_handle(field: int, device: int, n_bytes: int, record_witness_program: bool = False):
     """BASELINE configs[2]: blake2s gadget over an n_bytes preimage (xorshift bytes), streamed into a fresh device handle."""
     blocks = max(1, (n_bytes + 63) // 64)
     t = Tcs(field, device, named=False, reserve=(blocks * 21600 + 4096, blocks * 140000 + 65536, blocks * 21700 + 4096))
+    if record_witness_program:
+        t.record_witness_program()
     digest = t.blake2s(xorshift_bytes(n_bytes))
     info = {"rows_total": t.num_constraints(), "row0": 0, "bytes": n_bytes, "digest": digest.hex(), "tcs": t}
+    if record_witness_program:
+        info["witness_program"] = t.witness_program()
     return vp(t.handle), info
 
 

@@ -10,7 +10,8 @@ exchange over the ranks' peer mailboxes (include/bp_r1cs.h: bp_group_check_async
 
 The top level of the line is BASELINE configs[1] (sha256 x4096, Pallas: the config the metric is quoted on).  `workloads` holds
 the same measurements for the other configs BASELINE names at this N: configs[3] (synthetic 2^24, t = 6, BLS12-381 Fr: the
-256-bit Montgomery path and the 1/2/4/8 scaling curve) always, configs[4] (synthetic 2^27, t = 32, Pallas) at N = 8.
+256-bit Montgomery path and the 1/2/4/8 scaling curve) always, configs[4] (synthetic 2^27, t = 32, Pallas) at N = 8, configs[2]
+(blake2s, 64 KiB preimage, Vesta Fr: one GPU by definition) at N = 1.
 
 Per workload:
   value        constraints/s, matrices and witness resident in HBM, CUDA events on the launching stream, max over ranks
@@ -493,7 +494,7 @@ def measure(ctx, name, a, headline):
                 assert L.bp_cs_set_option(h, b"sparse_upload", 0) == 0
             # (4) no witness upload at all: the device generates it from the MESSAGE (64 bytes per block) with the program the
             # front-end recorded at synthesis; the host computes the 8-word chaining state per block (plain SHA-256)
-            if info.get("witness_program") is not None:
+            if kind == "sha256" and info.get("witness_program") is not None:
                 from bellpepper_b200 import fixtures
 
                 prog = info["witness_program"]
@@ -874,6 +875,12 @@ def main():
     results = {}
     for n in names:
         results[n] = measure(ctx, n, a, n == head_name)
+    if a.workload == "default" and not a.no_extra and world == 1:
+        # configs[2] (blake2s, 64 KiB preimage, Vesta Fr, one GPU): last, and never at the cost of the line
+        try:
+            results["blake2s_64KiB_vesta"] = measure(ctx, "blake2s_64KiB_vesta", a, False)
+        except Exception as e:
+            results["blake2s_64KiB_vesta"] = {"error": str(e)[:300]}
     if rank == 0:
         head = results[head_name]
         out = dict(base)
