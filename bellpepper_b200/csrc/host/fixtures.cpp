@@ -445,6 +445,55 @@ int bp_tcs_boolean_op(bp_tcs* t, int op, int kind_a, int kind_b, int kind_c, int
     });
 }
 
+// The reference's uint32 tests (uint32.rs:492-780): a = UInt32::alloc in "a_bit", b (and c for op 1) constants, the last operand
+// allocated in "c_bit" / "d_bit"; op 0: (a xor b) in "first xor", then xor c in "second xor"; op 1: (a xor b) in "xor", then
+// addmany [r, c, d] in "addition" under a MultiEq; op 2 / 3: sha256_maj / sha256_ch(a, b, c) at the root.
+int bp_tcs_uint32_op(bp_tcs* t, int op, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t* result, uint32_t* n_constant_bits) {
+    if (!t || op < 0 || op > 3) return BP_E_ARG;
+    return guarded(t, [&] {
+        auto run = [&](auto& cs) {
+            using CSv = std::remove_reference_t<decltype(cs)>;
+            auto alloc_in = [&](const char* name, uint32_t v) {
+                auto ns = cs.ns([&] { return std::string(name); });
+                return UInt32::alloc(ns, v);
+            };
+            const UInt32 a_bit = alloc_in("a_bit", a);
+            const UInt32 b_bit = UInt32::constant(b);
+            UInt32 r = UInt32::constant(0);
+            if (op == 0) {
+                const UInt32 c_bit = alloc_in("c_bit", c);
+                { auto ns = cs.ns([] { return std::string("first xor"); }); r = a_bit.xor_(ns, b_bit); }
+                { auto ns = cs.ns([] { return std::string("second xor"); }); r = r.xor_(ns, c_bit); }
+            } else if (op == 1) {
+                const UInt32 c_bit = UInt32::constant(c);
+                const UInt32 d_bit = alloc_in("d_bit", d);
+                { auto ns = cs.ns([] { return std::string("xor"); }); r = a_bit.xor_(ns, b_bit); }
+                {
+                    MultiEq<CSv> me(cs);
+                    auto ns = me.ns([] { return std::string("addition"); });
+                    const UInt32 ops[3] = {r, c_bit, d_bit};
+                    r = UInt32::addmany(ns, ops, 3);
+                }  // the MultiEq drops here: its wide row is emitted
+            } else {
+                const UInt32 c_bit = alloc_in("c_bit", c);
+                r = op == 2 ? UInt32::sha256_maj(cs, a_bit, b_bit, c_bit) : UInt32::sha256_ch(cs, a_bit, b_bit, c_bit);
+            }
+            uint32_t v = 0, n_const = 0;
+            for (unsigned i = 0; i < 32; ++i) {
+                const OptBool bv = r.bits[i].get_value();
+                if (bv < 0) throw SynthesisError::assignment_missing();
+                v |= (uint32_t)bv << i;
+                n_const += r.bits[i].is_constant();
+            }
+            if (result) *result = v;
+            if (n_constant_bits) *n_constant_bits = n_const;
+            cs.flush();
+        };
+        if (t->named) run(*t->named_cs);
+        else run(*t->bulk_cs);
+    });
+}
+
 int bp_tcs_u64_bits(bp_tcs* t, uint64_t value, uint8_t bits_out[64]) {
     if (!t) return BP_E_ARG;
     return guarded(t, [&] {

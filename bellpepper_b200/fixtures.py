@@ -25,6 +25,7 @@ _SIGS = {
     "bp_tcs_blake2s": (ctypes.c_int, [vp, vp, ctypes.c_uint64, vp, vp]),
     "bp_tcs_boolean_op": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "bp_tcs_u64_bits": (ctypes.c_int, [vp, ctypes.c_uint64, vp]),
+    "bp_tcs_uint32_op": (ctypes.c_int, [vp, ctypes.c_int] + [ctypes.c_uint32] * 4 + [ctypes.POINTER(ctypes.c_uint32)] * 2),
     "bp_tcs_num_unpack": (ctypes.c_int, [vp, vp, ctypes.c_int, vp]),
     "bp_tcs_num_arith": (ctypes.c_int, [vp, vp, vp]),
     "bp_tcs_num_chain": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp]),
@@ -161,6 +162,14 @@ class Tcs:
         kinds = [self.OPERAND_KINDS.index(x) for x in (a, b, c)]
         self._ck(self.L.bp_tcs_boolean_op(self.t, self.BOOLEAN_OPS[op], *kinds, ctypes.byref(k), ctypes.byref(v)))
         return ["Is", "Not", "Constant"][k.value], bool(v.value)
+
+    UINT32_OPS = {"xor": 0, "addmany": 1, "sha256_maj": 2, "sha256_ch": 3}
+
+    def uint32_op(self, op: str, a: int, b: int, c: int, d: int = 0):
+        """The reference's uint32 test circuits (uint32.rs:492-780); returns (value of the result word, number of constant bits)."""
+        r, k = ctypes.c_uint32(), ctypes.c_uint32()
+        self._ck(self.L.bp_tcs_uint32_op(self.t, self.UINT32_OPS[op], a, b, c, d, ctypes.byref(r), ctypes.byref(k)))
+        return r.value, k.value
 
     def u64_bits(self, value: int):
         """u64_into_boolean_vec_le (boolean.rs:274-304); returns the 64 bit values, little-endian."""

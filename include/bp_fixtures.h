@@ -80,6 +80,13 @@ int bp_tcs_num_chain(bp_tcs* t, uint64_t n_steps, uint64_t unpack_every, const u
 int bp_tcs_boolean_op(bp_tcs* t, int op, int kind_a, int kind_b, int kind_c, int* result_kind, int* result_value);
 int bp_tcs_u64_bits(bp_tcs* t, uint64_t value, uint8_t bits_out[64]);
 
+/* UInt32 gadgets the way the reference's tests drive them (crates/bellpepper/src/gadgets/uint32.rs:492-780): a allocated in
+ * "a_bit", b constant; op 0 = xor: c allocated in "c_bit", (a ^ b) in "first xor", ^ c in "second xor" (:492-535); op 1 = addmany:
+ * c constant, d allocated in "d_bit", (a ^ b) in "xor", then addmany [r, c, d] in "addition" under a MultiEq (:581-635: flipping
+ * "addition/result bit 0/boolean" breaks the MultiEq row); op 2 / 3 = sha256_maj / sha256_ch(a, b, c) with c in "c_bit"
+ * (:694-780).  *result = the value of the result word, *n_constant_bits = how many of its bits are constants. */
+int bp_tcs_uint32_op(bp_tcs* t, int op, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t* result, uint32_t* n_constant_bits);
+
 /* blake2s() gadget over `len` message bytes, each bit allocated as "input bit <byte> <bit>" least significant first,
  * with an 8-byte personalization (crates/bellpepper/src/gadgets/blake2s.rs:344-406, tests :498-555).  digest = the 32
  * output bytes (the gadget's output bits are little-endian per byte). */

@@ -195,3 +195,57 @@ def test_u64_into_boolean_vec_le():  # boolean.rs:1776-1794
     assert [int(bits[63 - i]) for i in (0, 1, 2, 3, 4, 5, 20, 21, 22)] == [1, 1, 1, 0, 1, 1, 1, 0, 0]
     assert sum(int(b) << i for i, b in enumerate(bits)) == 17234652694787248421
     assert c_api.Instance(0, lens, cols, coeffs, inputs, aux).check(1, True) == -1
+
+
+# ---- UInt32 xor / addmany / sha256_maj / sha256_ch as the reference's tests build them (uint32.rs:492-780) -------------------
+def _python_uint32_op(F, op, a, b, c, d):
+    cs = TestConstraintSystem(F)
+    with cs.namespace("a_bit") as ns:
+        a_bit = G.UInt32.alloc(ns, a)
+    b_bit = G.UInt32.constant(b)
+    if op == "xor":
+        with cs.namespace("c_bit") as ns:
+            c_bit = G.UInt32.alloc(ns, c)
+        with cs.namespace("first xor") as ns:
+            r = G.UInt32.xor(a_bit, ns, b_bit)
+        with cs.namespace("second xor") as ns:
+            r = G.UInt32.xor(r, ns, c_bit)
+    elif op == "addmany":
+        c_bit = G.UInt32.constant(c)
+        with cs.namespace("d_bit") as ns:
+            d_bit = G.UInt32.alloc(ns, d)
+        with cs.namespace("xor") as ns:
+            r = G.UInt32.xor(a_bit, ns, b_bit)
+        me = G.MultiEq(cs, F)
+        with me.namespace("addition") as ns:
+            r = G.UInt32.addmany(ns, F, [r, c_bit, d_bit])
+        me.finish()
+    else:
+        with cs.namespace("c_bit") as ns:
+            c_bit = G.UInt32.alloc(ns, c)
+        r = (G.UInt32.sha256_maj if op == "sha256_maj" else G.UInt32.sha256_ch)(cs, F, a_bit, b_bit, c_bit)
+    return cs, r
+
+
+@pytest.mark.parametrize("fid", [0, 2])
+def test_uint32_ops_identical_to_oracle_gadgets(fid):
+    import kat_scenarios as S
+
+    F = FIELDS[fid]
+    rng = S.XorShift()
+    for op in ("xor", "addmany", "sha256_maj", "sha256_ch"):
+        for _ in range(12):
+            a, b, c, d = (rng.next_u32() for _ in range(4))
+            cs, r = _python_uint32_op(F, op, a, b, c, d)
+            want = {"xor": a ^ b ^ c, "addmany": ((a ^ b) + c + d) & 0xFFFFFFFF, "sha256_maj": (a & b) ^ (a & c) ^ (b & c),
+                    "sha256_ch": (a & b) ^ (~a & 0xFFFFFFFF & c)}[op]
+            assert r.value == want
+            with fixtures.Tcs(fid, device=-1, named=True) as t:
+                value, n_const = t.uint32_op(op, a, b, c, d)
+                assert value == want and n_const == sum(bit.kind == G.CONST for bit in r.bits)
+                assert t.num_constraints() == cs.num_constraints()
+                same(t.host_csr(), oracle_csr(cs))
+                for row in range(cs.num_constraints()):
+                    assert t.row_path(row) == cs.constraints[row][3]
+            if op == "addmany":
+                assert cs.constraints[-1][3] == "multieq 0" and "addition/result bit 0/boolean" in cs.named_objects

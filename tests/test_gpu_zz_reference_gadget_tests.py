@@ -121,3 +121,27 @@ def test_cpp_front_end_enforce_equal_and_u64_bits_on_device():  # boolean.rs:935
         assert sum(int(x) << i for i, x in enumerate(bits)) == 17234652694787248421
         t.set("bit 63/boolean", 2)
         assert t.which_is_unsatisfied() == "bit 63/boolean constraint"
+
+
+def test_cpp_front_end_uint32_ops_on_device():
+    """uint32.rs:492-780 through the C++ front-end on the device: satisfied, the expected word, and -- test_uint32_addmany's last
+    step -- flipping "addition/result bit 0/boolean" leaves every bit boolean but breaks the MultiEq row."""
+    rng = S.XorShift()
+    for op in ("xor", "addmany", "sha256_maj", "sha256_ch"):
+        for _ in range(6):
+            a, b, c, d = (rng.next_u32() for _ in range(4))
+            want = {"xor": a ^ b ^ c, "addmany": ((a ^ b) + c + d) & 0xFFFFFFFF, "sha256_maj": (a & b) ^ (a & c) ^ (b & c),
+                    "sha256_ch": (a & b) ^ (~a & 0xFFFFFFFF & c)}[op]
+            with new_tcs() as t:
+                value, n_const = t.uint32_op(op, a, b, c, d)
+                assert value == want
+                assert t.is_satisfied()
+                if op == "addmany":
+                    assert n_const == 0
+                    path = "addition/result bit 0/boolean"
+                    old = t.get(path)
+                    assert old == (want & 1)
+                    t.set(path, 1 - old)
+                    assert t.which_is_unsatisfied() == "multieq 0"
+                    t.set(path, old)
+                    assert t.is_satisfied()
