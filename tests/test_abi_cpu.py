@@ -108,3 +108,42 @@ def test_rust_binding_declares_the_header():
     r = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (bp_[a-z0-9_]+)\s*\(([^)]*)\)", rs)}
     assert set(c) == set(r), set(c) ^ set(r)
     assert c == r, {k: (c[k], r[k]) for k in c if c[k] != r[k]}
+
+
+def _c_to_rust(arg):
+    """One C parameter (or return type) of include/bp_r1cs.h -> the Rust FFI type that binds it."""
+    arg = re.sub(r"\[[^\]]*\]", "*", arg.strip())  # arrays decay to pointers
+    toks = re.findall(r"[A-Za-z_][A-Za-z0-9_]*|\*", arg)
+    types = {"const", "void", "int", "char", "uint8_t", "uint32_t", "uint64_t", "int64_t", "bp_cs", "bp_group"}
+    if toks and toks[-1] not in types and toks[-1] != "*":
+        toks = toks[:-1]  # the parameter's name
+    elif len(toks) >= 2 and toks[-1] == "*" and toks[-2] not in types:
+        toks = toks[:-2] + ["*"]  # `uint8_t id[N]`: the name sits before the decayed `*`
+    base = [t for t in toks if t not in ("const", "*")]
+    assert len(base) == 1, arg
+    r = {"void": "c_void", "int": "c_int", "char": "c_char", "uint8_t": "u8", "uint32_t": "u32", "uint64_t": "u64", "int64_t": "i64",
+         "bp_cs": "bp_cs", "bp_group": "bp_group"}[base[0]]
+    stars, const = toks.count("*"), "const" in toks
+    if stars == 0:
+        return r
+    inner = f"*{'const' if const else 'mut'} {r}"
+    return inner if stars == 1 else f"*mut {inner}"
+
+
+def test_rust_binding_types_match_the_header():
+    """Every parameter and return type of rust/bellpepper-b200/src/ffi.rs is the Rust spelling of the header's C type
+    (pointer depth, constness, integer width): what a compiler would check, checked here because the image has no rustc."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bp_r1cs.h")).read(), flags=re.S)
+    rs = open(os.path.join(ROOT, "rust", "bellpepper-b200", "src", "ffi.rs")).read()
+    c = {m.group(2): (m.group(1).strip(), [a for a in m.group(3).split(",") if a.strip() not in ("", "void")])
+         for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(bp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)}
+    r = {m.group(1): ([a.split(":", 1)[1].strip() for a in m.group(2).split(",") if ":" in a], (m.group(3) or "").strip())
+         for m in re.finditer(r"pub fn (bp_[a-z0-9_]+)\s*\(([^)]*)\)\s*(?:->\s*([^;]+))?;", rs)}
+    assert len(c) >= 50 and set(c) == set(r)
+    for name, (ret, args) in c.items():
+        assert [_c_to_rust(a) for a in args] == r[name][0], name
+        assert ("" if ret == "void" else _c_to_rust(ret + " x" if "*" not in ret else ret)) == r[name][1], name
+    # the checker itself notices a wrong width / constness / depth
+    assert _c_to_rust("const uint64_t* vals_le") == "*const u64" and _c_to_rust("bp_cs** out") == "*mut *mut bp_cs"
+    assert _c_to_rust("uint8_t id[BP_GROUP_ID_BYTES]") == "*mut u8" and _c_to_rust("const uint8_t id[BP_GROUP_ID_BYTES]") == "*const u8"
+    assert _c_to_rust("int64_t* row") != _c_to_rust("uint64_t* row") and _c_to_rust("int is_aux") == "c_int"
