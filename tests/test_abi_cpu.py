@@ -147,3 +147,26 @@ def test_rust_binding_types_match_the_header():
     assert _c_to_rust("const uint64_t* vals_le") == "*const u64" and _c_to_rust("bp_cs** out") == "*mut *mut bp_cs"
     assert _c_to_rust("uint8_t id[BP_GROUP_ID_BYTES]") == "*mut u8" and _c_to_rust("const uint8_t id[BP_GROUP_ID_BYTES]") == "*const u8"
     assert _c_to_rust("int64_t* row") != _c_to_rust("uint64_t* row") and _c_to_rust("int is_aux") == "c_int"
+
+
+def test_ctypes_binding_arities_and_scalar_types_match_the_header():
+    """bellpepper_b200/ffi.py: every entry has the header's number of parameters; non-pointer parameters have the header's width
+    and signedness (a pointer is a c_void_p / POINTER / c_char_p there)."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bp_r1cs.h")).read(), flags=re.S)
+    scalars = {"c_int": ctypes.c_int, "u32": ctypes.c_uint32, "u64": ctypes.c_uint64, "i64": ctypes.c_int64, "u8": ctypes.c_uint8}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(bp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        ret, name, args = m.group(1).strip(), m.group(2), [a for a in m.group(3).split(",") if a.strip() not in ("", "void")]
+        res, argtypes = ffi.SIGNATURES[name]
+        assert len(argtypes) == len(args), name
+        for a, t in zip(args, argtypes):
+            r = _c_to_rust(a)
+            if r.startswith("*"):
+                assert t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "_type_") and not isinstance(t._type_, str), (name, a, t)
+            else:
+                assert t is scalars[r], (name, a, t)
+        if ret == "void":
+            assert res is None, name
+        elif "*" in ret:
+            assert res in (ctypes.c_char_p, ctypes.c_void_p), name
+        else:
+            assert res is scalars[_c_to_rust(ret + " x")], name
