@@ -170,3 +170,28 @@ def test_ctypes_binding_arities_and_scalar_types_match_the_header():
             assert res in (ctypes.c_char_p, ctypes.c_void_p), name
         else:
             assert res is scalars[_c_to_rust(ret + " x")], name
+
+
+def test_fixture_binding_arities_and_scalar_types_match_the_header():
+    from bellpepper_b200 import fixtures
+
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bp_fixtures.h")).read(), flags=re.S)
+    hdr = hdr.replace("bp_tcs", "bp_cs")  # (an opaque handle either way: reuse the type table)
+    scalars = {"c_int": ctypes.c_int, "u32": ctypes.c_uint32, "u64": ctypes.c_uint64, "i64": ctypes.c_int64, "u8": ctypes.c_uint8}
+    n = 0
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(bp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        ret, name, args = m.group(1).strip(), m.group(2).replace("bp_cs_", "bp_tcs_", 1), [a for a in m.group(3).split(",") if a.strip() not in ("", "void")]
+        if name not in fixtures._SIGS:
+            name = m.group(2)  # bp_sha256_chain_states, bp_blake2s_chain_states, bp_wcs_selftest keep their names
+        res, argtypes = fixtures._SIGS[name]
+        assert len(argtypes) == len(args), name
+        for a, t in zip(args, argtypes):
+            r = _c_to_rust(a)
+            if r.startswith("*"):
+                assert t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "_type_") and not isinstance(t._type_, str), (name, a, t)
+            else:
+                assert t is scalars[r], (name, a, t)
+        if ret != "void" and "*" not in ret:
+            assert res is scalars[_c_to_rust(ret + " x")], name
+        n += 1
+    assert n == len(fixtures._SIGS)
